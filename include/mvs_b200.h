@@ -1,0 +1,157 @@
+/*
+ * mvs_b200.h — C ABI of libmvs_b200.so: the B200 (sm_100a) plane-sweep hot path of MVSNet / CVP-MVSNet.
+ *
+ * The reference (ToughStoneX/Self-Supervised-MVS) has no FFI layer: its boundary for this path is the
+ * Python surface train.py imports.  Each entry point below names the reference
+ * function (file:line under /root/reference) whose arithmetic it replaces; the Python mirror of that
+ * surface lives in self-supervised-mvs_b200/ and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented "host"; the caller owns all
+ *     memory (inputs, outputs, workspaces); kernels never allocate, free or retain pointers.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no internal sync.
+ *   - return value: 0 = ok, <0 = error (MVS_E_*); mvs_last_error() returns a thread-local message.
+ *   - dtype codes select the STORAGE type of activations; all accumulation is fp32.
+ *
+ * Activation layout "C8": channels are blocked by 8 and the block is innermost:
+ *       maps    [B][C/8][H][W][8]          volumes [B][C/8][D][H][W][8]
+ *   so one (voxel, channel-block) is a 16-byte (fp16/bf16) or 32-byte (fp32) vector, consecutive w are
+ *   contiguous (coalesced gathers / stores), and a TMA box over (8, W, H, D, C/8) lands in shared memory
+ *   as the K-major, row-contiguous operand the tcgen05 implicit-GEMM convolution consumes.
+ *   Single-channel volumes (cost_reg, prob) are plain fp32 [B][D][H][W].
+ */
+#ifndef MVS_B200_H
+#define MVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_B200_VERSION 100 /* major*100 + minor */
+
+enum { MVS_F32 = 0, MVS_F16 = 1, MVS_BF16 = 2 };
+enum { MVS_OK = 0, MVS_E_ARG = -1, MVS_E_SHAPE = -2, MVS_E_LAUNCH = -3, MVS_E_UNSUPPORTED = -4 };
+#define MVS_MAX_SRC 8
+
+int mvs_version(void);
+const char* mvs_last_error(void);
+/* 1 when this library is the host-emulation build used by the CPU unit tests (tests/emu), else 0. */
+int mvs_is_emulation(void);
+
+/* ---- layout ------------------------------------------------------------------------------------------- */
+/* fp32 [B][C][S] (S = H*W or D*H*W) -> C8 [B][C/8][S][8] in `dtype`.  C % 8 == 0. */
+int mvs_pack_c8(const float* src, void* dst, int B, int C, int64_t S, int dtype, void* stream);
+/* inverse of mvs_pack_c8 */
+int mvs_unpack_c8(const void* src, float* dst, int B, int C, int64_t S, int dtype, void* stream);
+
+/* ---- projection algebra -------------------------------------------------------------------------------- */
+/* rt[s][b][0..8] = rot (row major), rt[s][b][9..11] = trans of  proj[b][s+1] @ inverse(proj[b][0]),
+ * proj = [B][N][4][4] fp32, rt = [N-1][B][12] fp32.  Replaces jdacs/models/module.py:116-118 (fp64 inside). */
+int mvs_compose_proj(const float* proj, float* rt, int B, int N, void* stream);
+/* same from intrinsics/extrinsics: P = [[K E[:3]],[0,0,0,1]].  ref_in [B][3][3], src_in [B][nsrc][3][3],
+ * ref_ex [B][4][4], src_ex [B][nsrc][4][4]; intrinsics rows 0,1 are divided by `down` first
+ * (conditionIntrinsics).  Replaces jdacs-ms/models/modules.py:22-37, 71-80, 222-231. */
+int mvs_compose_proj_ke(const float* ref_in, const float* src_in, const float* ref_ex, const float* src_ex,
+                        float down, float* rt, int B, int nsrc, void* stream);
+
+/* ---- a1/a2: stand-alone homography warp (API parity with homo_warping) ------------------------------------ */
+/* src [B][C][H][W] fp32 -> out [B][C][D][H][W] fp32.  depth is [B][D] (per_pixel=0) or [B][D][H][W] (1).
+ * rt = [B][12].  jdacs/models/module.py:105-140, jdacs-ms/models/modules.py:62-104. */
+int mvs_homo_warp_fwd(const float* src, const float* rt, const float* depth, int per_pixel, float* out,
+                      int B, int C, int D, int H, int W, int align_corners, void* stream);
+/* grad_src [B][C][H][W] must be zero-initialised by the caller (4-tap scatter add). */
+int mvs_homo_warp_bwd(const float* grad_out, const float* rt, const float* depth, int per_pixel, float* grad_src,
+                      int B, int C, int D, int H, int W, int align_corners, void* stream);
+
+/* ---- a1+a3+a4: fused warp + bilinear gather + running variance ------------------------------------------------
+ * ref, srcs[i]: C8 maps [B][C/8][H][W][8] (dtype_in); var: C8 volume [B][C/8][D][H][W][8] (dtype_out).
+ * srcs = HOST array of nsrc device pointers; rt = [nsrc][B][12].
+ * var = S2/N - (S1/N)^2, N = nsrc+1, S1 = ref + sum warped, S2 = ref^2 + sum warped^2;
+ * ref_sq_in_sum=1 starts S1 from ref^2 (CVP aliasing, jdacs-ms/models/network.py:114-116).
+ * Replaces jdacs/models/mvsnet.py:120-136, jdacs-ms/models/network.py:114-137, modules.py:209-261. */
+int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int nsrc, const float* rt, const float* depth,
+                     int per_pixel, void* var, int B, int C, int D, int H, int W, int dtype_in, int dtype_out,
+                     int align_corners, int ref_sq_in_sum, void* stream);
+/* grad_var: C8 volume (dtype_out).  grad_ref and grad_srcs[i]: fp32 C8 maps, zero-initialised by the caller. */
+int mvs_warp_var_bwd(const void* grad_var, const void* ref, const void* const* srcs, int nsrc, const float* rt,
+                     const float* depth, int per_pixel, float* grad_ref, float* const* grad_srcs, int B, int C,
+                     int D, int H, int W, int dtype_in, int dtype_out, int align_corners, int ref_sq_in_sum,
+                     void* stream);
+
+/* ---- a5/a6: 3-D convolution stack ------------------------------------------------------------------------------ */
+typedef struct {
+    int B, Cin, Cout;
+    int Din, Hin, Win;     /* input volume  */
+    int Dout, Hout, Wout;  /* output volume */
+    int stride;            /* 1 or 2 */
+    int transposed;        /* 0: Conv3d(k=3,pad=1,stride)   1: ConvTranspose3d(k=3,pad=1,stride,output_padding=stride-1) */
+    int dtype_in, dtype_out;
+    int relu;              /* apply ReLU after the affine */
+    int algo;              /* 0 auto, 1 SIMT fp32 direct, 2 tcgen05 implicit GEMM */
+} mvs_conv3d_desc;
+
+/* torch weight ([Cout][Cin][27] for Conv3d, [Cin][Cout][27] for ConvTranspose3d) -> gather form
+ * G[27][Cin][CoutPad] fp32, CoutPad = round_up(Cout, 8), so that out[o] = sum_tap x[in(o,tap)] . G[tap]. */
+int mvs_pack_conv3d_weight(const float* w, float* g, int Cin, int Cout, int transposed, void* stream);
+/* y = [relu]( conv(x) * scale + shift ) + skip;  scale/shift [Cout] fp32 or NULL, skip (dtype_out, y's layout) or NULL.
+ * x: C8 volume.  y: C8 volume, or plain fp32 [B][D][H][W] when Cout == 1.
+ * Replaces ConvBnReLU3D / ConvTranspose3d+BN+ReLU / prob: jdacs/models/module.py:35-42, mvsnet.py:37-74,
+ * jdacs-ms/models/network.py:44-74. */
+int mvs_conv3d_fwd(const mvs_conv3d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
+                   const void* skip, void* y, void* stream);
+/* training: gradient w.r.t. the torch-layout weight ([Cout][Cin][27] or, transposed, [Cin][Cout][27]; zero-initialised
+ * by the caller).  x: C8 volume (dtype_in), grad_y: C8 fp32 volume of the un-activated convolution output.
+ * (The gradient w.r.t. x needs no entry point of its own: it is mvs_conv3d_fwd of grad_y with the same torch weight
+ * packed under the opposite `transposed` flag, exactly how ATen defines conv_transpose3d.) */
+int mvs_conv3d_bwd_weight(const mvs_conv3d_desc* d, const void* x, const float* grad_y, float* grad_w, void* stream);
+
+/* batch-norm helpers for training mode (statistics over B*D*H*W per channel), C8 fp32 volumes.
+ * sums = [2][C] (sum, sum of squares), zero-initialised by the caller.  jdacs/models/module.py:39-42. */
+int mvs_bn_stats(const float* x, float* sums, int B, int C, int64_t S, void* stream);
+/* y = [relu]((x - mean) * invstd * gamma + beta) + skip        (skip may be NULL) */
+int mvs_bn_act_fwd(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                   const float* skip, float* y, int B, int C, int64_t S, int relu, void* stream);
+/* backward pass 1: red[0][c] = sum g, red[1][c] = sum g*xhat with g = grad_y * relu'(.) (= grad_beta, grad_gamma);
+ * red zero-initialised by the caller. */
+int mvs_bn_act_bwd_reduce(const float* x, const float* grad_y, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, float* red, int B, int C, int64_t S, int relu,
+                          void* stream);
+/* backward pass 2: grad_x = gamma*invstd*(g - red[0]/M - xhat*red[1]/M), M = B*S */
+int mvs_bn_act_bwd_apply(const float* x, const float* grad_y, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, const float* red, float* grad_x, int B, int C,
+                         int64_t S, int relu, void* stream);
+
+/* ---- a7/a8: softmax + soft-argmin + photometric confidence ------------------------------------------------------ */
+/* cost [B][D][H][W] fp32; depth [B][D] or [B][D][H][W]; outputs (any may be NULL): depth_out [B][H][W] fp32,
+ * index_out [B][H][W] int64 = trunc(sum_d p_d*d), conf_out [B][H][W] = p[i-1]+p[i]+p[i+1]+p[i+2], prob_out [B][D][H][W].
+ * jdacs/models/mvsnet.py:141-151, module.py:145-148, jdacs-ms/models/modules.py:324-331, network.py:183-189. */
+int mvs_softargmin_fwd(const float* cost, const float* depth, int per_pixel, float* depth_out, int64_t* index_out,
+                       float* conf_out, float* prob_out, int B, int D, int H, int W, void* stream);
+/* grad_cost[d] = p_d (depth_d - E[depth]) grad_depth */
+int mvs_softargmin_bwd(const float* cost, const float* depth, int per_pixel, const float* grad_depth,
+                       float* grad_cost, int B, int D, int H, int W, void* stream);
+
+/* ---- a9: CVP per-pixel depth hypotheses ---------------------------------------------------------------------- */
+/* hypos[b][k][h][w] = depth_up[b][h][w] + (k-half)*interval_b, interval_b = mean_pixels |delta_d| (fp64).
+ * ref_in, src_in0 [B][3][3]; ref_ex, src_ex0 [B][4][4] (source view 0 only); ws = [B] doubles, zero-initialised.
+ * jdacs-ms/models/modules.py:107-206. */
+int mvs_depth_hypo_refine(const float* depth_up, const float* ref_in, const float* src_in0, const float* ref_ex,
+                          const float* src_ex0, float* hypos, double* ws, int B, int H, int W, int half, void* stream);
+
+/* ---- a10: photometric inverse warp (loss side) ------------------------------------------------------------------ */
+/* img [B][H][W][C] fp32; left_cam/right_cam [B][2][4][4] ([0]=E, [1][:3][:3]=K); depth [B][H][W];
+ * warped [B][H][W][C], mask [B][H][W].  cam_ws = [B][24] floats of scratch.
+ * jdacs/losses/homography.py:186-238, 292-374. */
+int mvs_invwarp_fwd(const float* img, const float* left_cam, const float* right_cam, const float* depth,
+                    float* warped, float* mask, float* cam_ws, int B, int H, int W, int C, void* stream);
+/* grad_depth [B][H][W] (written); grad_img [B][H][W][C] or NULL (zero-initialised, scatter add). */
+int mvs_invwarp_bwd(const float* img, const float* left_cam, const float* right_cam, const float* depth,
+                    const float* grad_warped, float* grad_depth, float* grad_img, float* cam_ws, int B, int H,
+                    int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVS_B200_H */

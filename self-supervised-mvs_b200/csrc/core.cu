@@ -1,0 +1,145 @@
+// core.cu — library identity, error reporting, C8 layout packing, projection algebra.
+#include "mvs_rt.h"
+#include "linalg.h"
+#include <string.h>
+
+#ifdef MVS_CPU_EMU
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+#endif
+
+static thread_local char g_err[512] = "";
+
+int mvs_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" int mvs_version(void) { return MVS_B200_VERSION; }
+extern "C" const char* mvs_last_error(void) { return g_err; }
+extern "C" int mvs_is_emulation(void) {
+#ifdef MVS_CPU_EMU
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------- layout
+// One thread moves one (b, channel-block, s) vector.  Reads are strided by S across the 8 channels but
+// coalesced across threads (consecutive s); writes are one 16/32-byte vector per thread.
+template <typename T>
+__global__ void pack_c8_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int64_t S, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t s = i % S;
+    const int64_t bc = i / S;  // b * (C/8) + cb
+    const int cb = (int)(bc % (C / 8));
+    const int64_t b = bc / (C / 8);
+    const float* p = src + (b * C + (int64_t)cb * 8) * S + s;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (int64_t)k * S);
+    V8<T>::store(dst + i * 8, v);
+}
+
+template <typename T>
+__global__ void unpack_c8_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int64_t S, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t s = i % S;
+    const int64_t bc = i / S;
+    const int cb = (int)(bc % (C / 8));
+    const int64_t b = bc / (C / 8);
+    float v[8];
+    V8<T>::load(src + i * 8, v);
+    float* p = dst + (b * C + (int64_t)cb * 8) * S + s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[(int64_t)k * S] = v[k];
+}
+
+extern "C" int mvs_pack_c8(const float* src, void* dst, int B, int C, int64_t S, int dtype, void* stream) {
+    MVS_REQUIRE(src && dst, MVS_E_ARG, "mvs_pack_c8: null pointer");
+    MVS_REQUIRE(B > 0 && C > 0 && S > 0 && C % 8 == 0, MVS_E_SHAPE, "mvs_pack_c8: C=%d must be a positive multiple of 8", C);
+    const int64_t total = (int64_t)B * (C / 8) * S;
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(pack_c8_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, src, (T*)dst, C, S, total));
+    return MVS_CHECK_LAUNCH("mvs_pack_c8");
+}
+
+extern "C" int mvs_unpack_c8(const void* src, float* dst, int B, int C, int64_t S, int dtype, void* stream) {
+    MVS_REQUIRE(src && dst, MVS_E_ARG, "mvs_unpack_c8: null pointer");
+    MVS_REQUIRE(B > 0 && C > 0 && S > 0 && C % 8 == 0, MVS_E_SHAPE, "mvs_unpack_c8: C=%d must be a positive multiple of 8", C);
+    const int64_t total = (int64_t)B * (C / 8) * S;
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(unpack_c8_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, (const T*)src, dst, C, S, total));
+    return MVS_CHECK_LAUNCH("mvs_unpack_c8");
+}
+
+// ---------------------------------------------------------------------------------------------- projections
+__device__ static void rel_rt(const double* src, const double* ref, float* rt) {
+    double inv[16];
+    inv4(ref, inv);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += src[r * 4 + k] * inv[k * 4 + c];
+            if (c < 3) rt[r * 3 + c] = (float)s; else rt[9 + r] = (float)s;
+        }
+    }
+}
+
+__global__ void compose_proj_kernel(const float* __restrict__ proj, float* __restrict__ rt, int B, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = s * B + b
+    if (i >= (N - 1) * B) return;
+    const int s = i / B, b = i % B;
+    double ref[16], src[16];
+    for (int k = 0; k < 16; ++k) {
+        ref[k] = (double)proj[((int64_t)b * N) * 16 + k];
+        src[k] = (double)proj[((int64_t)b * N + s + 1) * 16 + k];
+    }
+    rel_rt(src, ref, rt + (int64_t)i * 12);
+}
+
+__device__ static void ke_to_proj(const float* K, const float* E, float down, double* P) {
+    // the reference divides K[:2] by the level ratio and multiplies K @ E[:3] in fp32; the products are
+    // formed in fp64 here from the same fp32 inputs.
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                const double kv = (r < 2) ? (double)(K[r * 3 + k] / down) : (double)K[r * 3 + k];
+                s += kv * (double)E[k * 4 + c];
+            }
+            P[r * 4 + c] = s;
+        }
+    P[12] = 0.0; P[13] = 0.0; P[14] = 0.0; P[15] = 1.0;
+}
+
+__global__ void compose_proj_ke_kernel(const float* __restrict__ ref_in, const float* __restrict__ src_in,
+                                       const float* __restrict__ ref_ex, const float* __restrict__ src_ex, float down,
+                                       float* __restrict__ rt, int B, int nsrc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = s * B + b
+    if (i >= nsrc * B) return;
+    const int s = i / B, b = i % B;
+    double ref[16], src[16];
+    ke_to_proj(ref_in + (int64_t)b * 9, ref_ex + (int64_t)b * 16, down, ref);
+    ke_to_proj(src_in + ((int64_t)b * nsrc + s) * 9, src_ex + ((int64_t)b * nsrc + s) * 16, down, src);
+    rel_rt(src, ref, rt + (int64_t)i * 12);
+}
+
+extern "C" int mvs_compose_proj(const float* proj, float* rt, int B, int N, void* stream) {
+    MVS_REQUIRE(proj && rt, MVS_E_ARG, "mvs_compose_proj: null pointer");
+    MVS_REQUIRE(B > 0 && N >= 2 && N - 1 <= MVS_MAX_SRC, MVS_E_SHAPE, "mvs_compose_proj: need 2 <= N <= %d views, got %d", MVS_MAX_SRC + 1, N);
+    MVS_LAUNCH(compose_proj_kernel, dim3(mvs_cdiv((N - 1) * B, 64)), dim3(64), stream, proj, rt, B, N);
+    return MVS_CHECK_LAUNCH("mvs_compose_proj");
+}
+
+extern "C" int mvs_compose_proj_ke(const float* ref_in, const float* src_in, const float* ref_ex, const float* src_ex,
+                                   float down, float* rt, int B, int nsrc, void* stream) {
+    MVS_REQUIRE(ref_in && src_in && ref_ex && src_ex && rt, MVS_E_ARG, "mvs_compose_proj_ke: null pointer");
+    MVS_REQUIRE(B > 0 && nsrc >= 1 && nsrc <= MVS_MAX_SRC, MVS_E_SHAPE, "mvs_compose_proj_ke: need 1 <= nsrc <= %d, got %d", MVS_MAX_SRC, nsrc);
+    MVS_REQUIRE(down > 0.f, MVS_E_ARG, "mvs_compose_proj_ke: down must be positive");
+    MVS_LAUNCH(compose_proj_ke_kernel, dim3(mvs_cdiv(nsrc * B, 64)), dim3(64), stream, ref_in, src_in, ref_ex, src_ex, down, rt, B, nsrc);
+    return MVS_CHECK_LAUNCH("mvs_compose_proj_ke");
+}

@@ -1,0 +1,340 @@
+// warp.cu — plane-sweep homography warp.
+//   * mvs_warp_var_fwd/bwd : fused warp + bilinear gather + running sum / sum-of-squares -> variance volume.
+//     The per-source warped volumes, the sampling grid and S1/S2 never exist in memory: one pass reads every
+//     feature map (L2 resident, 1.3-2.6 MB each) and writes the variance volume once.
+//   * mvs_homo_warp_fwd/bwd: the stand-alone homo_warping() API (NCHW in, NCDHW out) for drop-in parity.
+// Reference arithmetic: jdacs/models/module.py:105-140, mvsnet.py:120-136; jdacs-ms/models/modules.py:62-104,
+// 209-261, network.py:114-137.  Sampler semantics: ATen grid_sampler_2d bilinear / zeros padding.
+#include "mvs_rt.h"
+
+struct SrcPtrs { const void* p[MVS_MAX_SRC]; };
+struct GradPtrs { float* p[MVS_MAX_SRC]; };
+
+// ray = rot @ (x, y, 1): depth-independent part of the homography (module.py:125).
+__device__ __forceinline__ void pixel_ray(const float* __restrict__ rt, float x, float y, float (&ray)[3]) {
+    ray[0] = __ldg(rt + 0) * x + __ldg(rt + 1) * y + __ldg(rt + 2);
+    ray[1] = __ldg(rt + 3) * x + __ldg(rt + 4) * y + __ldg(rt + 5);
+    ray[2] = __ldg(rt + 6) * x + __ldg(rt + 7) * y + __ldg(rt + 8);
+}
+
+// (ray * depth + trans) -> projective divide -> normalise as the reference does -> un-normalise as
+// grid_sample does (module.py:126-134 then ATen grid_sampler_unnormalize; hazard H1).
+__device__ __forceinline__ void source_coord(const float (&ray)[3], const float* __restrict__ rt, float depth, int H,
+                                             int W, int align_corners, float& ix, float& iy) {
+    const float px = ray[0] * depth + __ldg(rt + 9);
+    const float py = ray[1] * depth + __ldg(rt + 10);
+    const float pz = ray[2] * depth + __ldg(rt + 11);
+    const float u = px / pz, v = py / pz;
+    const float xn = u / ((float)(W - 1) * 0.5f) - 1.f;
+    const float yn = v / ((float)(H - 1) * 0.5f) - 1.f;
+    if (align_corners) {
+        ix = (xn + 1.f) / 2.f * (float)(W - 1);
+        iy = (yn + 1.f) / 2.f * (float)(H - 1);
+    } else {
+        ix = ((xn + 1.f) * (float)W - 1.f) / 2.f;
+        iy = ((yn + 1.f) * (float)H - 1.f) / 2.f;
+    }
+}
+
+// The four bilinear taps of (ix, iy): pixel offset y*W+x (or -1 when the tap is outside the map; NaN and
+// inf coordinates fail every comparison and drop all taps) and weight, in ATen order nw, ne, sw, se.
+struct Taps { int off[4]; float w[4]; };
+__device__ __forceinline__ void bilinear_taps(float ix, float iy, int H, int W, Taps& t) {
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float x1 = x0 + 1.f, y1 = y0 + 1.f;
+    const bool vx0 = (x0 >= 0.f) && (x0 <= (float)(W - 1)), vx1 = (x1 >= 0.f) && (x1 <= (float)(W - 1));
+    const bool vy0 = (y0 >= 0.f) && (y0 <= (float)(H - 1)), vy1 = (y1 >= 0.f) && (y1 <= (float)(H - 1));
+    const float wx0 = x1 - ix, wx1 = ix - x0, wy0 = y1 - iy, wy1 = iy - y0;
+    const int xi = vx0 ? (int)x0 : (vx1 ? (int)x1 - 1 : 0);
+    const int yi = vy0 ? (int)y0 : (vy1 ? (int)y1 - 1 : 0);
+    const int base = yi * W + xi;
+    t.off[0] = (vx0 && vy0) ? base : -1;          t.w[0] = wx0 * wy0;
+    t.off[1] = (vx1 && vy0) ? base + 1 : -1;      t.w[1] = wx1 * wy0;
+    t.off[2] = (vx0 && vy1) ? base + W : -1;      t.w[2] = wx0 * wy1;
+    t.off[3] = (vx1 && vy1) ? base + W + 1 : -1;  t.w[3] = wx1 * wy1;
+}
+
+template <typename T>
+__device__ __forceinline__ void gather8(const T* __restrict__ map, const Taps& t, float (&out)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (t.off[i] >= 0) {
+            float v[8];
+            V8<T>::load(map + (int64_t)t.off[i] * 8, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] += v[k] * t.w[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused forward
+// thread = (pixel, channel-block, depth chunk).  Lanes run along w, so the gathers of a warp touch
+// neighbouring source pixels and each plane is stored as 32 consecutive 16/32-byte vectors.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128)
+warp_var_fwd_kernel(const TI* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
+                    const float* __restrict__ depth, int per_pixel, TO* __restrict__ var, int B, int CB, int D, int H,
+                    int W, int dper, int align_corners, int ref_sq_in_sum) {
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int nchunk = (D + dper - 1) / dper;
+    int y = blockIdx.y;
+    const int dc = y % nchunk; y /= nchunk;
+    const int cb = y % CB;
+    const int b = y / CB;
+    const float fx = (float)(p % W), fy = (float)(p / W);
+    const int64_t map_off = ((int64_t)b * CB + cb) * HW * 8;
+
+    float r[8], r2[8];
+    V8<TI>::load(ref + map_off + (int64_t)p * 8, r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r2[k] = r[k] * r[k];
+
+    float ray[MVS_MAX_SRC][3];
+#pragma unroll
+    for (int s = 0; s < MVS_MAX_SRC; ++s)
+        if (s < nsrc) pixel_ray(rt + ((int64_t)s * B + b) * 12, fx, fy, ray[s]);
+
+    const float n = (float)(nsrc + 1);
+    const int d_end = min(D, (dc + 1) * dper);
+    for (int d = dc * dper; d < d_end; ++d) {
+        const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+        float s1[8], s2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s1[k] = ref_sq_in_sum ? r2[k] : r[k]; s2[k] = r2[k]; }
+#pragma unroll
+        for (int s = 0; s < MVS_MAX_SRC; ++s) {
+            if (s < nsrc) {
+                float ix, iy;
+                source_coord(ray[s], rt + ((int64_t)s * B + b) * 12, dv, H, W, align_corners, ix, iy);
+                Taps t;
+                bilinear_taps(ix, iy, H, W, t);
+                float wv[8];
+                gather8<TI>(reinterpret_cast<const TI*>(srcs.p[s]) + map_off, t, wv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s1[k] += wv[k]; s2[k] += wv[k] * wv[k]; }
+            }
+        }
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float m = s1[k] / n; o[k] = s2[k] / n - m * m; }
+        V8<TO>::store(var + ((((int64_t)b * CB + cb) * D + d) * HW + p) * 8, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused backward
+// d var / d w_i = 2 w_i / N - 2 S1 / N^2 ;  d var / d ref = 2 r / N - 2 S1 / N^2  (x 2r on the S1 term when the
+// reference feature entered S1 squared).  S1 is recomputed; each source is then re-sampled and its gradient
+// scattered to the 4 taps with fp32 atomics (the grid carries no gradient: module.py:115, hazard H13).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128)
+warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, SrcPtrs srcs, int nsrc,
+                    const float* __restrict__ rt, const float* __restrict__ depth, int per_pixel,
+                    float* __restrict__ gref, GradPtrs gsrcs, int B, int CB, int D, int H, int W, int dper,
+                    int align_corners, int ref_sq_in_sum) {
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int nchunk = (D + dper - 1) / dper;
+    int y = blockIdx.y;
+    const int dc = y % nchunk; y /= nchunk;
+    const int cb = y % CB;
+    const int b = y / CB;
+    const float fx = (float)(p % W), fy = (float)(p / W);
+    const int64_t map_off = ((int64_t)b * CB + cb) * HW * 8;
+
+    float r[8];
+    V8<TI>::load(ref + map_off + (int64_t)p * 8, r);
+    float ray[MVS_MAX_SRC][3];
+#pragma unroll
+    for (int s = 0; s < MVS_MAX_SRC; ++s)
+        if (s < nsrc) pixel_ray(rt + ((int64_t)s * B + b) * 12, fx, fy, ray[s]);
+
+    const float n = (float)(nsrc + 1);
+    const float inv_n = 1.f / n;
+    float gr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gr[k] = 0.f;
+
+    const int d_end = min(D, (dc + 1) * dper);
+    for (int d = dc * dper; d < d_end; ++d) {
+        const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+        float g[8];
+        V8<TO>::load(gvar + ((((int64_t)b * CB + cb) * D + d) * HW + p) * 8, g);
+        float s1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s1[k] = ref_sq_in_sum ? r[k] * r[k] : r[k];
+#pragma unroll
+        for (int s = 0; s < MVS_MAX_SRC; ++s) {
+            if (s < nsrc) {
+                float ix, iy;
+                source_coord(ray[s], rt + ((int64_t)s * B + b) * 12, dv, H, W, align_corners, ix, iy);
+                Taps t;
+                bilinear_taps(ix, iy, H, W, t);
+                float wv[8];
+                gather8<TI>(reinterpret_cast<const TI*>(srcs.p[s]) + map_off, t, wv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s1[k] += wv[k];
+            }
+        }
+        float m2[8];  // 2 * S1 / N^2
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m2[k] = 2.f * s1[k] * inv_n * inv_n;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float dr = ref_sq_in_sum ? (2.f * r[k] * inv_n - m2[k] * 2.f * r[k]) : (2.f * r[k] * inv_n - m2[k]);
+            gr[k] += g[k] * dr;
+        }
+#pragma unroll
+        for (int s = 0; s < MVS_MAX_SRC; ++s) {
+            if (s < nsrc && gsrcs.p[s] != nullptr) {
+                float ix, iy;
+                source_coord(ray[s], rt + ((int64_t)s * B + b) * 12, dv, H, W, align_corners, ix, iy);
+                Taps t;
+                bilinear_taps(ix, iy, H, W, t);
+                float wv[8];
+                gather8<TI>(reinterpret_cast<const TI*>(srcs.p[s]) + map_off, t, wv);
+                float c[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c[k] = g[k] * (2.f * wv[k] * inv_n - m2[k]);
+                float* gs = gsrcs.p[s] + map_off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (t.off[i] >= 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) atomicAdd(gs + (int64_t)t.off[i] * 8 + k, c[k] * t.w[i]);
+                    }
+                }
+            }
+        }
+    }
+    if (gref != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(gref + map_off + (int64_t)p * 8 + k, gr[k]);
+    }
+}
+
+static int depth_chunk(int D, int HW, int B, int CB) {
+    // enough (pixel-tile x chunk) blocks for >= ~4 waves of 148 SMs x 8 resident blocks, chunks of >= 8 planes
+    int dper = D;
+    const int64_t tiles = (int64_t)mvs_cdiv(HW, 128) * B * CB;
+    while (dper > 8 && tiles * ((D + dper - 1) / dper) < 148 * 8 * 4) dper = (dper + 1) / 2;
+    return dper;
+}
+
+static int check_warp_var(const void* ref, const void* const* srcs, int nsrc, const float* rt, const float* depth,
+                          int B, int C, int D, int H, int W) {
+    MVS_REQUIRE(ref && srcs && rt && depth, MVS_E_ARG, "warp_var: null pointer");
+    MVS_REQUIRE(nsrc >= 1 && nsrc <= MVS_MAX_SRC, MVS_E_SHAPE, "warp_var: need 1 <= nsrc <= %d, got %d", MVS_MAX_SRC, nsrc);
+    for (int s = 0; s < nsrc; ++s) MVS_REQUIRE(srcs[s], MVS_E_ARG, "warp_var: source %d is null", s);
+    MVS_REQUIRE(B > 0 && D > 0 && H > 1 && W > 1, MVS_E_SHAPE, "warp_var: bad dims B=%d D=%d H=%d W=%d", B, D, H, W);
+    MVS_REQUIRE(C > 0 && C % 8 == 0, MVS_E_SHAPE, "warp_var: C=%d must be a multiple of 8 (C8 layout)", C);
+    MVS_REQUIRE((int64_t)B * (C / 8) * D <= 65535 * 8, MVS_E_SHAPE, "warp_var: B*C/8*D too large for the launch grid");
+    return MVS_OK;
+}
+
+extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int nsrc, const float* rt, const float* depth,
+                                int per_pixel, void* var, int B, int C, int D, int H, int W, int dtype_in, int dtype_out,
+                                int align_corners, int ref_sq_in_sum, void* stream) {
+    int rc = check_warp_var(ref, srcs, nsrc, rt, depth, B, C, D, H, W);
+    if (rc) return rc;
+    MVS_REQUIRE(var, MVS_E_ARG, "mvs_warp_var_fwd: null output");
+    SrcPtrs sp;
+    for (int s = 0; s < MVS_MAX_SRC; ++s) sp.p[s] = s < nsrc ? srcs[s] : nullptr;
+    const int CB = C / 8, HW = H * W;
+    const int dper = depth_chunk(D, HW, B, CB);
+    const dim3 grid(mvs_cdiv(HW, 128), (unsigned)(B * CB * ((D + dper - 1) / dper)));
+    MVS_DISPATCH_DTYPE(dtype_in, TI, MVS_DISPATCH_DTYPE(dtype_out, TO,
+        MVS_LAUNCH((warp_var_fwd_kernel<TI, TO>), grid, dim3(128), stream, (const TI*)ref, sp, nsrc, rt, depth, per_pixel,
+                   (TO*)var, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum)));
+    return MVS_CHECK_LAUNCH("mvs_warp_var_fwd");
+}
+
+extern "C" int mvs_warp_var_bwd(const void* grad_var, const void* ref, const void* const* srcs, int nsrc, const float* rt,
+                                const float* depth, int per_pixel, float* grad_ref, float* const* grad_srcs, int B, int C,
+                                int D, int H, int W, int dtype_in, int dtype_out, int align_corners, int ref_sq_in_sum,
+                                void* stream) {
+    int rc = check_warp_var(ref, srcs, nsrc, rt, depth, B, C, D, H, W);
+    if (rc) return rc;
+    MVS_REQUIRE(grad_var && grad_srcs, MVS_E_ARG, "mvs_warp_var_bwd: null pointer");
+    SrcPtrs sp;
+    GradPtrs gp;
+    for (int s = 0; s < MVS_MAX_SRC; ++s) { sp.p[s] = s < nsrc ? srcs[s] : nullptr; gp.p[s] = s < nsrc ? grad_srcs[s] : nullptr; }
+    const int CB = C / 8, HW = H * W;
+    const int dper = depth_chunk(D, HW, B, CB);
+    const dim3 grid(mvs_cdiv(HW, 128), (unsigned)(B * CB * ((D + dper - 1) / dper)));
+    MVS_DISPATCH_DTYPE(dtype_in, TI, MVS_DISPATCH_DTYPE(dtype_out, TO,
+        MVS_LAUNCH((warp_var_bwd_kernel<TI, TO>), grid, dim3(128), stream, (const TO*)grad_var, (const TI*)ref, sp, nsrc, rt,
+                   depth, per_pixel, grad_ref, gp, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum)));
+    return MVS_CHECK_LAUNCH("mvs_warp_var_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone warp
+// thread = (b, d, h, w); loops over channels of an NCHW fp32 map.  API-parity path, not the fused one.
+__global__ void __launch_bounds__(256)
+homo_warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ rt, const float* __restrict__ depth,
+                     int per_pixel, float* __restrict__ out, int B, int C, int D, int H, int W, int align_corners) {
+    const int HW = H * W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * D * HW) return;
+    const int p = (int)(i % HW);
+    const int d = (int)((i / HW) % D);
+    const int b = (int)(i / ((int64_t)HW * D));
+    float ray[3], ix, iy;
+    pixel_ray(rt + (int64_t)b * 12, (float)(p % W), (float)(p / W), ray);
+    const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+    source_coord(ray, rt + (int64_t)b * 12, dv, H, W, align_corners, ix, iy);
+    Taps t;
+    bilinear_taps(ix, iy, H, W, t);
+    for (int c = 0; c < C; ++c) {
+        const float* m = src + ((int64_t)b * C + c) * HW;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (t.off[k] >= 0) acc += __ldg(m + t.off[k]) * t.w[k];
+        out[(((int64_t)b * C + c) * D + d) * HW + p] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+homo_warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ rt, const float* __restrict__ depth,
+                     int per_pixel, float* __restrict__ gsrc, int B, int C, int D, int H, int W, int align_corners) {
+    const int HW = H * W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * D * HW) return;
+    const int p = (int)(i % HW);
+    const int d = (int)((i / HW) % D);
+    const int b = (int)(i / ((int64_t)HW * D));
+    float ray[3], ix, iy;
+    pixel_ray(rt + (int64_t)b * 12, (float)(p % W), (float)(p / W), ray);
+    const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+    source_coord(ray, rt + (int64_t)b * 12, dv, H, W, align_corners, ix, iy);
+    Taps t;
+    bilinear_taps(ix, iy, H, W, t);
+    for (int c = 0; c < C; ++c) {
+        const float g = __ldg(gout + (((int64_t)b * C + c) * D + d) * HW + p);
+        float* m = gsrc + ((int64_t)b * C + c) * HW;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (t.off[k] >= 0) atomicAdd(m + t.off[k], g * t.w[k]);
+    }
+}
+
+extern "C" int mvs_homo_warp_fwd(const float* src, const float* rt, const float* depth, int per_pixel, float* out,
+                                 int B, int C, int D, int H, int W, int align_corners, void* stream) {
+    MVS_REQUIRE(src && rt && depth && out, MVS_E_ARG, "mvs_homo_warp_fwd: null pointer");
+    MVS_REQUIRE(B > 0 && C > 0 && D > 0 && H > 1 && W > 1, MVS_E_SHAPE, "mvs_homo_warp_fwd: bad dims");
+    const int64_t total = (int64_t)B * D * H * W;
+    MVS_LAUNCH(homo_warp_fwd_kernel, dim3(mvs_cdiv(total, 256)), dim3(256), stream, src, rt, depth, per_pixel, out, B, C, D, H, W, align_corners);
+    return MVS_CHECK_LAUNCH("mvs_homo_warp_fwd");
+}
+
+extern "C" int mvs_homo_warp_bwd(const float* grad_out, const float* rt, const float* depth, int per_pixel, float* grad_src,
+                                 int B, int C, int D, int H, int W, int align_corners, void* stream) {
+    MVS_REQUIRE(grad_out && rt && depth && grad_src, MVS_E_ARG, "mvs_homo_warp_bwd: null pointer");
+    MVS_REQUIRE(B > 0 && C > 0 && D > 0 && H > 1 && W > 1, MVS_E_SHAPE, "mvs_homo_warp_bwd: bad dims");
+    const int64_t total = (int64_t)B * D * H * W;
+    MVS_LAUNCH(homo_warp_bwd_kernel, dim3(mvs_cdiv(total, 256)), dim3(256), stream, grad_out, rt, depth, per_pixel, grad_src, B, C, D, H, W, align_corners);
+    return MVS_CHECK_LAUNCH("mvs_homo_warp_bwd");
+}

@@ -1,0 +1,403 @@
+"""Host-side operators of the plane-sweep path: thin torch.autograd wrappers over the C ABI.
+
+Tensors in the "C8" layout are ordinary torch tensors of shape [B, C/8, H, W, 8] (maps) or
+[B, C/8, D, H, W, 8] (volumes); see include/mvs_b200.h.  PyTorch is used for device memory, streams and
+autograd bookkeeping only; every arithmetic step of the path is a kernel of libmvs_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Conv3dDesc, call, dtype_code, ptr
+
+Tensor = torch.Tensor
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def pack_c8(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
+    """fp32 [B,C,*spatial] -> C8 [B,C/8,*spatial,8] in `dtype`."""
+    x = _f32c(x)
+    b, c = x.shape[0], x.shape[1]
+    if c % 8:
+        raise ValueError("C8 layout needs a channel count divisible by 8, got %d" % c)
+    sp = tuple(x.shape[2:])
+    s = 1
+    for v in sp:
+        s *= v
+    out = torch.empty((b, c // 8) + sp + (8,), dtype=dtype, device=x.device)
+    call("mvs_pack_c8", x, ptr(x), ptr(out), b, c, s, dtype_code(dtype))
+    return out
+
+
+def unpack_c8(x: Tensor) -> Tensor:
+    """C8 [B,C/8,*spatial,8] -> fp32 [B,C,*spatial]."""
+    x = x.detach().contiguous()
+    b, cb = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:-1])
+    s = 1
+    for v in sp:
+        s *= v
+    out = torch.empty((b, cb * 8) + sp, dtype=torch.float32, device=x.device)
+    call("mvs_unpack_c8", x, ptr(x), ptr(out), b, cb * 8, s, dtype_code(x.dtype))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ projections
+def compose_proj(proj_matrices: Tensor) -> Tensor:
+    """[B,N,4,4] -> rt [N-1,B,12] (rot row-major | trans) of proj[:, s+1] @ inverse(proj[:, 0])."""
+    p = _f32c(proj_matrices)
+    b, n = p.shape[0], p.shape[1]
+    rt = torch.empty(n - 1, b, 12, dtype=torch.float32, device=p.device)
+    call("mvs_compose_proj", p, ptr(p), ptr(rt), b, n)
+    return rt
+
+
+def compose_proj_ke(ref_in: Tensor, src_in: Tensor, ref_ex: Tensor, src_ex: Tensor, down: float = 1.0) -> Tensor:
+    """(K, E) pairs -> rt [nsrc,B,12]; src_in [B,nsrc,3,3], src_ex [B,nsrc,4,4]; K[:2] is divided by `down`."""
+    ref_in, src_in, ref_ex, src_ex = _f32c(ref_in), _f32c(src_in), _f32c(ref_ex), _f32c(src_ex)
+    b, nsrc = src_in.shape[0], src_in.shape[1]
+    rt = torch.empty(nsrc, b, 12, dtype=torch.float32, device=ref_in.device)
+    call("mvs_compose_proj_ke", ref_in, ptr(ref_in), ptr(src_in), ptr(ref_ex), ptr(src_ex), float(down), ptr(rt), b, nsrc)
+    return rt
+
+
+# ------------------------------------------------------------------------------------------------ stand-alone warp
+class _HomoWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src_fea: Tensor, rt: Tensor, depth: Tensor, align_corners: bool) -> Tensor:
+        src = _f32c(src_fea)
+        depth = _f32c(depth)
+        b, c, h, w = src.shape
+        d = depth.shape[1]
+        per_pixel = int(depth.dim() == 4)
+        out = torch.empty(b, c, d, h, w, dtype=torch.float32, device=src.device)
+        call("mvs_homo_warp_fwd", src, ptr(src), ptr(rt), ptr(depth), per_pixel, ptr(out), b, c, d, h, w, int(align_corners))
+        ctx.save_for_backward(rt, depth)
+        ctx.meta = (b, c, d, h, w, per_pixel, int(align_corners))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        rt, depth = ctx.saved_tensors
+        b, c, d, h, w, per_pixel, ac = ctx.meta
+        g = _f32c(grad_out)
+        gsrc = torch.zeros(b, c, h, w, dtype=torch.float32, device=g.device)
+        call("mvs_homo_warp_bwd", g, ptr(g), ptr(rt), ptr(depth), per_pixel, ptr(gsrc), b, c, d, h, w, ac)
+        return gsrc, None, None, None
+
+
+def homo_warp(src_fea: Tensor, rt: Tensor, depth: Tensor, align_corners: bool = False) -> Tensor:
+    """[B,C,H,W] x rt[B,12] x depth([B,D] | [B,D,H,W]) -> [B,C,D,H,W]; gradient reaches src_fea only (hazard H13)."""
+    return _HomoWarp.apply(src_fea, rt.contiguous(), depth, align_corners)
+
+
+# ------------------------------------------------------------------------------------------------ fused warp + variance
+def _ptr_array(tensors: Sequence[Optional[Tensor]]):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class _WarpVariance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rt: Tensor, depth: Tensor, dtype: torch.dtype, align_corners: bool, ref_sq_in_sum: bool,
+                ref_fea: Tensor, *src_feas: Tensor) -> Tensor:
+        fdt = torch.float32 if dtype == torch.float32 else dtype
+        ref8 = pack_c8(ref_fea, fdt)
+        src8 = [pack_c8(s, fdt) for s in src_feas]
+        depth = _f32c(depth)
+        b, c, h, w = ref_fea.shape
+        d = depth.shape[1]
+        per_pixel = int(depth.dim() == 4)
+        var = torch.empty(b, c // 8, d, h, w, 8, dtype=dtype, device=ref_fea.device)
+        call("mvs_warp_var_fwd", ref8, ptr(ref8), _ptr_array(src8), len(src8), ptr(rt), ptr(depth), per_pixel, ptr(var),
+             b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), int(align_corners), int(ref_sq_in_sum))
+        ctx.save_for_backward(rt, depth, ref8, *src8)
+        ctx.meta = (b, c, d, h, w, per_pixel, fdt, dtype, int(align_corners), int(ref_sq_in_sum))
+        return var
+
+    @staticmethod
+    def backward(ctx, grad_var: Tensor):
+        rt, depth, ref8, *src8 = ctx.saved_tensors
+        b, c, d, h, w, per_pixel, fdt, dtype, ac, rsq = ctx.meta
+        g = grad_var.detach().to(dtype).contiguous()
+        need = ctx.needs_input_grad
+        gref = torch.zeros(b, c // 8, h, w, 8, dtype=torch.float32, device=g.device) if need[5] else None
+        gsrc = [torch.zeros(b, c // 8, h, w, 8, dtype=torch.float32, device=g.device) if need[6 + i] else None
+                for i in range(len(src8))]
+        call("mvs_warp_var_bwd", g, ptr(g), ptr(ref8), _ptr_array(src8), len(src8), ptr(rt), ptr(depth), per_pixel,
+             ptr(gref), _ptr_array(gsrc), b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), ac, rsq)
+        outs = [None if t is None else unpack_c8(t) for t in [gref] + gsrc]
+        return (None, None, None, None, None, *outs)
+
+
+def warp_variance(ref_fea: Tensor, src_feas: Sequence[Tensor], rt: Tensor, depth: Tensor,
+                  dtype: torch.dtype = torch.float32, align_corners: bool = False, ref_sq_in_sum: bool = False) -> Tensor:
+    """Variance cost volume (C8, `dtype`) of the reference map and nsrc warped source maps ([B,C,H,W] fp32 each)."""
+    if len(src_feas) < 1 or len(src_feas) > _lib.MAX_SRC:
+        raise ValueError("need 1..%d source views, got %d" % (_lib.MAX_SRC, len(src_feas)))
+    return _WarpVariance.apply(rt.contiguous(), depth, dtype, align_corners, ref_sq_in_sum, ref_fea, *src_feas)
+
+
+# ------------------------------------------------------------------------------------------------ 3-D convolution
+def _out_extent(n: int, stride: int, transposed: bool) -> int:
+    if stride == 1:
+        return n
+    if transposed:
+        return 2 * n
+    if n % 2:
+        raise ValueError("stride-2 Conv3d needs even extents, got %d (the reference U-Net has the same constraint)" % n)
+    return n // 2
+
+
+def pack_conv3d_weight(weight: Tensor, transposed: bool) -> Tensor:
+    """torch Conv3d [Cout,Cin,3,3,3] / ConvTranspose3d [Cin,Cout,3,3,3] weight -> gather form G[27,Cin,CoutPad] fp32."""
+    w = _f32c(weight)
+    if tuple(w.shape[2:]) != (3, 3, 3):
+        raise ValueError("only 3x3x3 kernels are on the path")
+    cin, cout = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
+    g = torch.empty(27, cin, (cout + 7) // 8 * 8, dtype=torch.float32, device=w.device)
+    call("mvs_pack_conv3d_weight", w, ptr(w), ptr(g), cin, cout, int(transposed))
+    return g
+
+
+def _desc(x: Tensor, cout: int, stride: int, transposed: bool, out_dtype: torch.dtype, relu: bool, algo: int) -> Conv3dDesc:
+    b, cb, d, h, w, _ = x.shape
+    return Conv3dDesc(b, cb * 8, cout, d, h, w, _out_extent(d, stride, transposed), _out_extent(h, stride, transposed),
+                      _out_extent(w, stride, transposed), stride, int(transposed), dtype_code(x.dtype),
+                      dtype_code(out_dtype), int(relu), algo)
+
+
+def conv3d_raw(x: Tensor, g: Tensor, cout: int, stride: int = 1, transposed: bool = False,
+               scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, skip: Optional[Tensor] = None,
+               relu: bool = False, out_dtype: Optional[torch.dtype] = None, algo: int = 0) -> Tensor:
+    """y = [relu](conv(x) * scale + shift) + skip on C8 volumes (no autograd).  cout == 1 gives plain fp32 [B,D,H,W]."""
+    x = x.contiguous()
+    out_dtype = torch.float32 if cout == 1 else (out_dtype or x.dtype)
+    d = _desc(x, cout, stride, transposed, out_dtype, relu, algo)
+    if cout == 1:
+        y = torch.empty(d.B, d.Dout, d.Hout, d.Wout, dtype=torch.float32, device=x.device)
+    else:
+        y = torch.empty(d.B, cout // 8, d.Dout, d.Hout, d.Wout, 8, dtype=out_dtype, device=x.device)
+    if skip is not None:
+        skip = skip.contiguous()
+        if skip.shape != y.shape or skip.dtype != y.dtype:
+            raise ValueError("skip tensor must match the output (%s %s vs %s %s)" % (tuple(skip.shape), skip.dtype, tuple(y.shape), y.dtype))
+    call("mvs_conv3d_fwd", x, C.byref(d), ptr(x), ptr(g), ptr(scale), ptr(shift), ptr(skip), ptr(y))
+    return y
+
+
+def _pad_single_channel(t: Tensor) -> Tensor:
+    """plain [B,D,H,W] -> C8 [B,1,D,H,W,8] with the value in channel 0."""
+    out = torch.zeros(t.shape[0], 1, t.shape[1], t.shape[2], t.shape[3], 8, dtype=torch.float32, device=t.device)
+    out[..., 0] = t.unsqueeze(1)
+    return out
+
+
+class _Conv3d(torch.autograd.Function):
+    """Un-activated 3x3x3 (transposed) convolution with optional bias, fp32 C8, differentiable (training path)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, transposed: bool) -> Tensor:
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        g = pack_conv3d_weight(weight, transposed)
+        y = conv3d_raw(x, g, cout, stride, transposed, shift=None if bias is None else _f32c(bias), algo=1)
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (stride, transposed, cout, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x, weight = ctx.saved_tensors
+        stride, transposed, cout, has_bias = ctx.meta
+        gy = _f32c(gy)
+        gbias = None
+        w_eff = _f32c(weight)
+        if cout == 1:  # lift the single-channel gradient (and weight) to one C8 block
+            if has_bias:
+                gbias = gy.sum().reshape(1)
+            gy = _pad_single_channel(gy)
+            pad_shape = list(w_eff.shape)
+            pad_shape[1 if transposed else 0] = 8
+            w8 = torch.zeros(pad_shape, dtype=torch.float32, device=w_eff.device)
+            if transposed:
+                w8[:, :1] = w_eff
+            else:
+                w8[:1] = w_eff
+            w_eff, cout_eff = w8, 8
+        else:
+            cout_eff = cout
+            if has_bias:
+                gbias = gy.sum(dim=(0, 2, 3, 4)).reshape(-1)  # [B,Cb,D,H,W,8] -> [Cb*8]
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            # adjoint: the same torch weight packed under the opposite flag (ATen's definition of conv_transpose)
+            g_adj = pack_conv3d_weight(w_eff, not transposed)
+            cin = x.shape[1] * 8
+            if stride == 2 and not transposed:
+                gx = conv3d_raw(gy, g_adj, cin, 2, True, algo=1)
+            elif stride == 2 and transposed:
+                gx = conv3d_raw(gy, g_adj, cin, 2, False, algo=1)
+            else:
+                gx = conv3d_raw(gy, g_adj, cin, 1, not transposed, algo=1)
+        if ctx.needs_input_grad[1]:
+            d = _desc(x, cout_eff, stride, transposed, torch.float32, False, 1)
+            gw8 = torch.zeros_like(w_eff)
+            xc = x.contiguous()
+            call("mvs_conv3d_bwd_weight", xc, C.byref(d), ptr(xc), ptr(gy), ptr(gw8))
+            if cout == 1:
+                gw = gw8[:, :1].contiguous() if transposed else gw8[:1].contiguous()
+            else:
+                gw = gw8
+        return gx, gw, gbias, None, None
+
+
+def conv3d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int = 1, transposed: bool = False) -> Tensor:
+    return _Conv3d.apply(x, weight, bias, stride, transposed)
+
+
+class _BnAct(torch.autograd.Function):
+    """Training-mode BatchNorm3d (+ReLU) (+skip) on an fp32 C8 volume; returns (y, batch_mean, batch_var_biased)."""
+
+    @staticmethod
+    def forward(ctx, z: Tensor, gamma: Tensor, beta: Tensor, skip: Optional[Tensor], relu: bool, eps: float):
+        z = z.contiguous()
+        b, cb = z.shape[0], z.shape[1]
+        c = cb * 8
+        s = z[0, 0].numel() // 8
+        sums = torch.zeros(2, c, dtype=torch.float32, device=z.device)
+        call("mvs_bn_stats", z, ptr(z), ptr(sums), b, c, s)
+        m = float(b * s)
+        mean = sums[0] / m
+        var = (sums[1] / m - mean * mean).clamp_min_(0.0)
+        invstd = torch.rsqrt(var + eps)
+        gamma_c, beta_c = _f32c(gamma), _f32c(beta)
+        y = torch.empty_like(z)
+        skip_c = None if skip is None else skip.contiguous()
+        call("mvs_bn_act_fwd", z, ptr(z), ptr(mean), ptr(invstd), ptr(gamma_c), ptr(beta_c), ptr(skip_c), ptr(y), b, c, s, int(relu))
+        ctx.save_for_backward(z, mean, invstd, gamma_c, beta_c)
+        ctx.meta = (b, c, s, int(relu), skip is not None)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy: Tensor, _gm, _gv):
+        z, mean, invstd, gamma, beta = ctx.saved_tensors
+        b, c, s, relu, has_skip = ctx.meta
+        gy = _f32c(gy)
+        red = torch.zeros(2, c, dtype=torch.float32, device=z.device)
+        call("mvs_bn_act_bwd_reduce", z, ptr(z), ptr(gy), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(red), b, c, s, relu)
+        gz = torch.empty_like(z)
+        call("mvs_bn_act_bwd_apply", z, ptr(z), ptr(gy), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(red), ptr(gz), b, c, s, relu)
+        return gz, red[1].clone(), red[0].clone(), (gy if has_skip else None), None, None
+
+
+def bn_act_train(z: Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, skip: Optional[Tensor] = None, relu: bool = True) -> Tensor:
+    """Batch-statistics BN + ReLU + skip; updates bn.running_* like nn.BatchNorm3d.train() (momentum, unbiased var)."""
+    y, mean, var = _BnAct.apply(z, bn.weight, bn.bias, skip, relu, bn.eps)
+    if bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            n = z.shape[0] * (z[0, 0].numel() // 8)
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+            bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=mom)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+    return y
+
+
+def fold_bn(bn: torch.nn.modules.batchnorm._BatchNorm) -> Tuple[Tensor, Tensor]:
+    """Eval-mode BN as a per-channel affine: scale = gamma / sqrt(running_var + eps), shift = beta - mean * scale."""
+    scale = (bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)).contiguous()
+    shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+    return scale, shift
+
+
+# ------------------------------------------------------------------------------------------------ soft-argmin
+class _SoftArgmin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cost: Tensor, depth: Tensor, want_prob: bool):
+        cost, depth = _f32c(cost), _f32c(depth)
+        b, d, h, w = cost.shape
+        per_pixel = int(depth.dim() == 4)
+        dev = cost.device
+        out = torch.empty(b, h, w, dtype=torch.float32, device=dev)
+        index = torch.empty(b, h, w, dtype=torch.int64, device=dev)
+        conf = torch.empty(b, h, w, dtype=torch.float32, device=dev)
+        prob = torch.empty(b, d, h, w, dtype=torch.float32, device=dev) if want_prob else None
+        call("mvs_softargmin_fwd", cost, ptr(cost), ptr(depth), per_pixel, ptr(out), ptr(index), ptr(conf), ptr(prob), b, d, h, w)
+        ctx.save_for_backward(cost, depth)
+        ctx.meta = (b, d, h, w, per_pixel)
+        ctx.mark_non_differentiable(index, conf)
+        if prob is None:
+            prob = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(prob)
+        return out, index, conf, prob
+
+    @staticmethod
+    def backward(ctx, g_depth: Tensor, _gi, _gc, _gp):
+        cost, depth = ctx.saved_tensors
+        b, d, h, w, per_pixel = ctx.meta
+        g = _f32c(g_depth)
+        gcost = torch.empty_like(cost)
+        call("mvs_softargmin_bwd", cost, ptr(cost), ptr(depth), per_pixel, ptr(g), ptr(gcost), b, d, h, w)
+        return gcost, None, None
+
+
+def soft_argmin(cost_reg: Tensor, depth: Tensor, want_prob: bool = False):
+    """cost_reg [B,D,H,W] -> (depth [B,H,W], index int64, confidence, prob or None); gradient reaches cost_reg only."""
+    out, index, conf, prob = _SoftArgmin.apply(cost_reg, depth, want_prob)
+    return out, index, conf, (prob if want_prob else None)
+
+
+# ------------------------------------------------------------------------------------------------ CVP hypotheses
+def depth_hypo_refine(depth_up: Tensor, ref_in: Tensor, src_in0: Tensor, ref_ex: Tensor, src_ex0: Tensor, half: int = 4) -> Tensor:
+    """[B,H,W] -> [B,2*half,H,W] = depth_up + k * mean|delta_d| (no gradient; the reference builds it under no_grad)."""
+    depth_up = _f32c(depth_up)
+    b, h, w = depth_up.shape
+    ref_in, src_in0, ref_ex, src_ex0 = _f32c(ref_in), _f32c(src_in0), _f32c(ref_ex), _f32c(src_ex0)
+    hyp = torch.empty(b, 2 * half, h, w, dtype=torch.float32, device=depth_up.device)
+    ws = torch.zeros(b, dtype=torch.float64, device=depth_up.device)
+    call("mvs_depth_hypo_refine", depth_up, ptr(depth_up), ptr(ref_in), ptr(src_in0), ptr(ref_ex), ptr(src_ex0), ptr(hyp), ptr(ws), b, h, w, half)
+    return hyp
+
+
+# ------------------------------------------------------------------------------------------------ loss-side inverse warp
+class _InvWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img: Tensor, left_cam: Tensor, right_cam: Tensor, depth: Tensor):
+        img_c, depth_c = _f32c(img), _f32c(depth)
+        left, right = _f32c(left_cam), _f32c(right_cam)
+        b, h, w, c = img_c.shape
+        warped = torch.empty_like(img_c)
+        mask = torch.empty(b, h, w, 1, dtype=torch.float32, device=img_c.device)
+        ws = torch.empty(b, 24, dtype=torch.float32, device=img_c.device)
+        call("mvs_invwarp_fwd", img_c, ptr(img_c), ptr(left), ptr(right), ptr(depth_c), ptr(warped), ptr(mask), ptr(ws), b, h, w, c)
+        ctx.save_for_backward(img_c, left, right, depth_c)
+        ctx.mark_non_differentiable(mask)
+        return warped, mask
+
+    @staticmethod
+    def backward(ctx, g_warped: Tensor, _gmask):
+        img, left, right, depth = ctx.saved_tensors
+        b, h, w, c = img.shape
+        g = _f32c(g_warped)
+        gdepth = torch.empty_like(depth)
+        gimg = torch.zeros_like(img) if ctx.needs_input_grad[0] else None
+        ws = torch.empty(b, 24, dtype=torch.float32, device=img.device)
+        call("mvs_invwarp_bwd", img, ptr(img), ptr(left), ptr(right), ptr(depth), ptr(g), ptr(gdepth), ptr(gimg), ptr(ws), b, h, w, c)
+        return gimg, None, None, gdepth
+
+
+def inverse_warp(img: Tensor, left_cam: Tensor, right_cam: Tensor, depth: Tensor) -> Tuple[Tensor, Tensor]:
+    """img [B,H,W,C], cams [B,2,4,4], depth [B,H,W] -> (warped [B,H,W,C], mask [B,H,W,1])."""
+    return _InvWarp.apply(img, left_cam, right_cam, depth)
