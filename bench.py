@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — depth-samples/sec of the MVSNet plane-sweep path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp16|bf16|fp32]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU)
+
+A step = one MVSNet.forward (eval) over one synthetic DTU-shaped item per GPU at BASELINE.json configs[1]:
+N=5 views, 512x640 images -> 128x160 maps, C=32, D=192  (3,932,160 depth-samples per item; weak scaling, no
+data-path collective: items are independent).  `value` times it with the inputs resident in HBM, `e2e` through the
+same reference-facing call with pinned HOST inputs and a device->host read of depth + confidence every step.
+`roofline` is measured live with CUDA events for the dominant stage, `cpu_baseline` is the oracle port (the
+reference's own torch-CPU op sequence) on this box's host cores.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+VIEWS, HEIGHT, WIDTH, NDEPTH, CHANNELS = 5, 512, 640, 192, 32
+HF, WF = HEIGHT // 4, WIDTH // 4
+SAMPLES_PER_ITEM = NDEPTH * HF * WF
+WORKLOAD = "MVSNet forward N=5 512x640 D=192 (BASELINE.json configs[1])"
+METRIC = "depth-samples/sec (N=5,D=192,512x640)"
+# algorithmic work per item: warp+variance bytes = s*(C*D*Hf*Wf + N*C*Hf*Wf) + 4*D ; CostRegNet flops
+REG_FLOPS = 20304 * SAMPLES_PER_ITEM
+SOFTARGMIN_BYTES = 4 * SAMPLES_PER_ITEM + 12 * HF * WF
+
+
+def warp_var_bytes(elem: int) -> int:
+    return elem * (CHANNELS * SAMPLES_PER_ITEM + VIEWS * CHANNELS * HF * WF) + 4 * NDEPTH
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_oracle():
+    spec = importlib.util.spec_from_file_location("planesweep_oracle", os.path.join(ROOT, "oracle", "planesweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_model(dtype):
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False, volume_dtype=dtype)
+    with torch.no_grad():
+        model.cost_regularization.prob.weight.mul_(64.0)  # peaky softmax (hazard H11); same work either way
+    return model.eval()
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout.readlines()), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_forward_timer(steps: int, warmup: int):
+    """The reference's CPU path (oracle port: same torch-CPU op sequence as jdacs/models/mvsnet.py:105-155)."""
+    from ssmvs_b200 import synth
+    oracle = load_oracle()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = make_model(torch.float32)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    inp = synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], sd)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times, threads
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    times, threads = cpu_forward_timer(args.steps, min(args.warmup, 1))
+    total = sum(times)
+    val = SAMPLES_PER_ITEM * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "depth-samples/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": 1, "sample": "1 item per step on host cores"},
+            "cpu_baseline": {"value": val, "unit": "depth-samples/s", "cores": threads, "kind": "port",
+                             "sample": "%d full forward passes of 1 item (oracle port of the reference's torch-CPU path, fp32)" % len(times)},
+            "e2e": {"value": val, "unit": "depth-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    import ssmvs_b200
+    from ssmvs_b200 import ops, parallel, synth
+
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+
+    rank, world, local = parallel.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the plane-sweep path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ssmvs_b200._lib.bind()
+    dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
+    elem = 4 if dtype == torch.float32 else 2
+    model = make_model(dtype).to(dev)
+    host = synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=rank)
+    pinned = {k: host[k].pin_memory() for k in ("imgs", "proj_matrices", "depth_values")}
+    res = {k: v.to(dev) for k, v in pinned.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    out_host = {"depth": torch.empty(1, HF, WF).pin_memory(), "conf": torch.empty(1, HF, WF).pin_memory()}
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident():
+        return model(res["imgs"], res["proj_matrices"], res["depth_values"])
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        o = model(d["imgs"], d["proj_matrices"], d["depth_values"])
+        out_host["depth"].copy_(o["depth"], non_blocking=True)
+        out_host["conf"].copy_(o["photometric_confidence"], non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        """per-step CUDA-event pairs on the launching stream, L2 flushed between steps (outside the pairs)."""
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize(dev)
+            parallel.barrier()
+            torch.cuda.synchronize(dev)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            l0 = ssmvs_b200._lib.launches
+            t0 = time.perf_counter()
+            for a, b in ev:
+                flush.zero_()
+                a.record(stream)
+                fn()
+                b.record(stream)
+            torch.cuda.synchronize(dev)
+            parallel.barrier()
+            wall = time.perf_counter() - t0
+            launches = ssmvs_b200._lib.launches - l0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return parallel.max_over_ranks(ms, dev), wall, launches
+
+    with ClockSampler(local) as clk:
+        ms_total, wall, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = clk.summary()
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 3)
+
+    # ---- per-stage timing for the roofline (same inputs, each stage bracketed by events, L2 flushed before each)
+    def stage_times(reps=5):
+        t = {"features": [], "warp_var": [], "reg3d": [], "softargmin": []}
+        mk = lambda: torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            for _ in range(reps):
+                e = [mk() for _ in range(8)]
+                imgs = res["imgs"]
+                flush.zero_(); e[0].record(stream)
+                f = model.feature(imgs.transpose(0, 1).reshape(VIEWS, 3, HEIGHT, WIDTH))
+                feats = list(f.reshape(VIEWS, 1, CHANNELS, HF, WF).unbind(0))
+                e[1].record(stream)
+                rt = ops.compose_proj(res["proj_matrices"])
+                ref8 = ops.pack_c8(feats[0], dtype)
+                src8 = [ops.pack_c8(s, dtype) for s in feats[1:]]
+                var = torch.empty(1, CHANNELS // 8, NDEPTH, HF, WF, 8, dtype=dtype, device=dev)
+                flush.zero_(); e[2].record(stream)
+                ssmvs_b200._lib.call("mvs_warp_var_fwd", ref8, ref8.data_ptr(), ops._ptr_array(src8), len(src8), rt.data_ptr(),
+                                     res["depth_values"].data_ptr(), 0, var.data_ptr(), 1, CHANNELS, NDEPTH, HF, WF,
+                                     ssmvs_b200._lib.dtype_code(dtype), ssmvs_b200._lib.dtype_code(dtype), 0, 0)
+                e[3].record(stream)
+                flush.zero_(); e[4].record(stream)
+                model.cost_regularization.act_dtype = dtype
+                reg = model.cost_regularization(var)
+                e[5].record(stream)
+                flush.zero_(); e[6].record(stream)
+                ops.soft_argmin(reg, res["depth_values"])
+                e[7].record(stream)
+                torch.cuda.synchronize(dev)
+                for k, (i, j) in zip(t, ((0, 1), (2, 3), (4, 5), (6, 7))):
+                    t[k].append(e[i].elapsed_time(e[j]))
+        return {k: statistics.median(v) for k, v in t.items()}
+
+    stages = stage_times()
+    peaks = load_peaks()
+    wv_gbs = warp_var_bytes(elem) / (stages["warp_var"] * 1e-3) / 1e9
+    reg_tfs = REG_FLOPS / (stages["reg3d"] * 1e-3) / 1e12
+    roof_wv = {"kernel": "warp_var_fwd_kernel", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "frac": wv_gbs / peaks["hbm_gbs"], "traffic": None, "ms": stages["warp_var"], "peak_source": peaks["source"]}
+    roof_reg = {"kernel": "CostRegNet conv stack (12 launches)", "bound": "tensor", "achieved": reg_tfs, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": reg_tfs / peaks["bf16_tflops"], "traffic": None, "ms": stages["reg3d"],
+                "peak_source": peaks["source"]}
+    dominant = roof_reg if stages["reg3d"] >= stages["warp_var"] else roof_wv
+
+    if rank == 0:
+        items = world * args.steps
+        value = items * SAMPLES_PER_ITEM / (ms_total * 1e-3)
+        e2e_value = items * SAMPLES_PER_ITEM / (ms_e2e * 1e-3)
+        h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        line = {"metric": METRIC, "value": value, "unit": "depth-samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " storage, f32 accumulate",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world, "per_gpu_batch": 1, "parallelism": "dp%d (items sharded, no collective)" % world,
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
+                           "wall_s_incl_flush": wall},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": "depth-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "roofline": dominant, "roofline_warp_var": roof_wv, "roofline_reg3d": roof_reg, "stage_ms": stages}
+        if world == 1 and not args.no_cpu_baseline:
+            times, threads = cpu_forward_timer(3, 1)
+            line["cpu_baseline"] = {"value": SAMPLES_PER_ITEM * len(times) / sum(times), "unit": "depth-samples/s", "cores": threads,
+                                    "kind": "port", "sample": "3 full forward passes of 1 item after 1 warm-up (oracle port of the reference's torch-CPU path, fp32)"}
+        print(json.dumps(line))
+    parallel.barrier()
+
+
+if __name__ == "__main__":
+    main()

@@ -218,8 +218,8 @@ def gen_jdacs_ms():
     ref_hyp = rmod.calSweepingDepthHypo(kr, ks[:, 0], ci["ref_ex"], ci["src_ex"], ci["depth_min"], ci["depth_max"])
     assert ref_hyp.shape == hyp.shape, "reference torch.range gave %s planes" % (ref_hyp.shape,)
     _close(hyp, ref_hyp, 1e-6, "calSweepingDepthHypo")
-    ref_w = rmod.homo_warping(fea, kr, ks[:, 0], ci["ref_ex"], ci["src_ex"][:, 0], hyp)
-    _close(oracle.homo_warping_ms(fea, kr, ks[:, 0], ci["ref_ex"], ci["src_ex"][:, 0], hyp), ref_w, 1e-5, "homo_warping(K,E)")
+    ref_w = rmod.homo_warping(fea, kr, ks[:, 0], ci["ref_ex"], ci["src_ex"][:, 0], ref_hyp)
+    _close(oracle.homo_warping_ms(fea, kr, ks[:, 0], ci["ref_ex"], ci["src_ex"][:, 0], ref_hyp), ref_w, 1e-5, "homo_warping(K,E)")
 
     # --- a9: calDepthHypo ---------------------------------------------------------------------
     depth_up = synth.plausible_depth(1, 32, 48, seed=8)

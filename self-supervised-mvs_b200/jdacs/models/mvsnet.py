@@ -1,0 +1,159 @@
+"""Mirror of the reference's `models/mvsnet.py` (jdacs/models/mvsnet.py): FeatureNet, CostRegNet, RefineNet,
+MVSNet, mvsnet_loss — same constructor / forward signatures, sub-module names and state-dict keys, so that
+`from models.mvsnet import MVSNet, mvsnet_loss` (jdacs/train.py:28) and reference checkpoints keep working.
+
+What runs where:
+  FeatureNet, RefineNet      2-D convolutions, library (cuDNN) code — outside the plane-sweep path
+  cost volume                ONE fused kernel: homography warp + bilinear gather + running variance
+  CostRegNet                 3x3x3 (transposed) convolutions with BN/ReLU/skip fused in the epilogue
+  softmax / depth / index / confidence   ONE fused kernel
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops, regnet
+from .module import ALIGN_CORNERS, ConvBnReLU, ConvBnReLU3D
+
+
+class FeatureNet(nn.Module):
+    """jdacs/models/mvsnet.py:17-34."""
+
+    def __init__(self):
+        super().__init__()
+        self.inplanes = 32
+        self.conv0 = ConvBnReLU(3, 8, 3, 1, 1)
+        self.conv1 = ConvBnReLU(8, 8, 3, 1, 1)
+        self.conv2 = ConvBnReLU(8, 16, 5, 2, 2)
+        self.conv3 = ConvBnReLU(16, 16, 3, 1, 1)
+        self.conv4 = ConvBnReLU(16, 16, 3, 1, 1)
+        self.conv5 = ConvBnReLU(16, 32, 5, 2, 2)
+        self.conv6 = ConvBnReLU(32, 32, 3, 1, 1)
+        self.feature = nn.Conv2d(32, 32, 3, 1, 1)
+
+    def forward(self, x):
+        x = self.conv1(self.conv0(x))
+        x = self.conv4(self.conv3(self.conv2(x)))
+        return self.feature(self.conv6(self.conv5(x)))
+
+
+class CostRegNet(nn.Module):
+    """jdacs/models/mvsnet.py:37-74.  forward takes the variance volume (C8 or [B,32,D,H,W]) and returns
+    cost_reg: [B,D,H,W] fp32 for a C8 input (internal), [B,1,D,H,W] for a plain input (reference shape).
+    D, H, W must be divisible by 8, as in the reference (three stride-2 levels)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0 = ConvBnReLU3D(32, 8)
+        self.conv1 = ConvBnReLU3D(8, 16, stride=2)
+        self.conv2 = ConvBnReLU3D(16, 16)
+        self.conv3 = ConvBnReLU3D(16, 32, stride=2)
+        self.conv4 = ConvBnReLU3D(32, 32)
+        self.conv5 = ConvBnReLU3D(32, 64, stride=2)
+        self.conv6 = ConvBnReLU3D(64, 64)
+        self.conv7 = nn.Sequential(
+            nn.ConvTranspose3d(64, 32, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+            nn.BatchNorm3d(32), nn.ReLU(inplace=True))
+        self.conv9 = nn.Sequential(
+            nn.ConvTranspose3d(32, 16, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+            nn.BatchNorm3d(16), nn.ReLU(inplace=True))
+        self.conv11 = nn.Sequential(
+            nn.ConvTranspose3d(16, 8, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+            nn.BatchNorm3d(8), nn.ReLU(inplace=True))
+        self.prob = nn.Conv3d(8, 1, 3, stride=1, padding=1)
+        self._cache = regnet.PackCache()
+        self.algo = 0           # 0 auto, 1 SIMT fp32, 2 tcgen05 (mvs_conv3d_desc.algo)
+        self.act_dtype = None   # storage dtype of activations in eval mode; None = dtype of the input volume
+
+    def forward(self, x):
+        plain = x.dim() == 5
+        tr = self.training
+        x = regnet.as_c8(x, torch.float32 if tr else (self.act_dtype or torch.float32))
+        for n in (x.shape[2], x.shape[3], x.shape[4]):
+            if n % 8:
+                raise ValueError("CostRegNet needs D, H, W divisible by 8 (got %s), as the reference does" % (tuple(x.shape[2:5]),))
+        if not tr and self.act_dtype is not None and x.dtype != self.act_dtype:
+            raise ValueError("variance volume is %s but CostRegNet.act_dtype is %s" % (x.dtype, self.act_dtype))
+        a = self.algo
+        conv0 = self.conv0(x, None, a)
+        conv2 = self.conv2(self.conv1(conv0, None, a), None, a)
+        conv4 = self.conv4(self.conv3(conv2, None, a), None, a)
+        y = self.conv6(self.conv5(conv4, None, a), None, a)
+        c = self._cache
+        y = regnet.conv_bn_relu(y, self.conv7[0], self.conv7[1], tr, c, conv4, a)    # conv4 + relu(bn(convT(x)))
+        y = regnet.conv_bn_relu(y, self.conv9[0], self.conv9[1], tr, c, conv2, a)
+        y = regnet.conv_bn_relu(y, self.conv11[0], self.conv11[1], tr, c, conv0, a)
+        out = regnet.conv_bias(y, self.prob, tr, c, a)                                # [B,D,H,W] fp32
+        return out.unsqueeze(1) if plain else out
+
+
+class RefineNet(nn.Module):
+    """jdacs/models/mvsnet.py:77-92 (2-D, library code; off by default in train.py via --refine False)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = ConvBnReLU(4, 32)
+        self.conv2 = ConvBnReLU(32, 32)
+        self.conv3 = ConvBnReLU(32, 32)
+        self.res = ConvBnReLU(32, 1)
+
+    def forward(self, img, depth_init):
+        img = F.interpolate(img, scale_factor=0.25, mode='bilinear')
+        depth_init = depth_init.unsqueeze(dim=1)
+        concat = torch.cat((img, depth_init), dim=1)
+        depth_residual = self.res(self.conv3(self.conv2(self.conv1(concat))))
+        return (depth_init + depth_residual).squeeze(dim=1)
+
+
+class MVSNet(nn.Module):
+    """jdacs/models/mvsnet.py:95-161.
+
+    forward(imgs [B,N,3,H,W], proj_matrices [B,N,4,4], depth_values [B,D])
+        -> {"depth": [B,H/4,W/4], "photometric_confidence": [B,H/4,W/4]}
+
+    Extra, optional knobs (defaults reproduce the reference as it runs on torch >= 1.3):
+      volume_dtype   storage of the cost volume / activations in eval mode (fp32 | fp16 | bf16); training is fp32
+      align_corners  True = the geometry the authors intended on torch 1.1 (hazard H1)
+    """
+
+    def __init__(self, refine=True, volume_dtype=torch.float32, align_corners=ALIGN_CORNERS):
+        super().__init__()
+        self.refine = refine
+        self.feature = FeatureNet()
+        self.cost_regularization = CostRegNet()
+        if self.refine:
+            self.refine_network = RefineNet()
+        self.volume_dtype = volume_dtype
+        self.align_corners = align_corners
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        assert imgs.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
+        b, n = imgs.shape[0], imgs.shape[1]
+        # step 1. feature extraction (library code).  In eval mode all views share one batched call; in training
+        # each view is its own call, because BatchNorm2d statistics are per call in the reference (:115).
+        if self.training:
+            features = [self.feature(imgs[:, v]) for v in range(n)]
+        else:
+            f = self.feature(imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:]))
+            features = list(f.reshape(n, b, *f.shape[1:]).unbind(0))
+        # step 2. plane sweep: warp + variance, fused (:120-136)
+        dt = torch.float32 if self.training else self.volume_dtype
+        rt = ops.compose_proj(proj_matrices)
+        variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
+        # step 3. regularisation (:139-141)
+        self.cost_regularization.act_dtype = None if self.training else dt
+        cost_reg = self.cost_regularization(variance)
+        # softmax + regression + confidence, fused (:142-151)
+        depth, _, photometric_confidence, _ = ops.soft_argmin(cost_reg, depth_values)
+        if not self.refine:
+            return {"depth": depth, "photometric_confidence": photometric_confidence}
+        refined_depth = self.refine_network(imgs[:, 0], depth)
+        return {"depth": refined_depth, "photometric_confidence": photometric_confidence}
+
+
+def mvsnet_loss(depth_est, depth_gt, mask):
+    """jdacs/models/mvsnet.py:164-166 (supervised loss, unused by the self-supervised training)."""
+    mask = mask > 0.5
+    return F.smooth_l1_loss(depth_est[mask], depth_gt[mask], reduction='mean')

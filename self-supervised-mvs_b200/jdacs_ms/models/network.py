@@ -1,0 +1,141 @@
+"""Mirror of the reference's jdacs-ms `models/network.py`: FeaturePyramid, CostRegNet, CVPMVSNet, sL1_loss, MSE_loss.
+
+Same constructor / forward signatures, sub-module names (`featurePyramid`, `cost_reg_refine`) and state-dict keys.
+The coarse sweep and every refinement level use the same three fused kernels as MVSNet (warp+variance with
+shared or per-pixel hypotheses, the 3-D convolutions, soft-argmin); FeaturePyramid stays library code.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops, regnet
+from .modules import (ALIGN_CORNERS, ConvBnReLU3D, calDepthHypo, calSweepingDepthHypo, conditionIntrinsics, conv,
+                      proj_cost)
+
+
+class FeaturePyramid(nn.Module):
+    """jdacs-ms/models/network.py:16-41 (2-D, library code)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0aa = conv(3, 64, kernel_size=3, stride=1)
+        self.conv0ba = conv(64, 64, kernel_size=3, stride=1)
+        self.conv0bb = conv(64, 64, kernel_size=3, stride=1)
+        self.conv0bc = conv(64, 32, kernel_size=3, stride=1)
+        self.conv0bd = conv(32, 32, kernel_size=3, stride=1)
+        self.conv0be = conv(32, 32, kernel_size=3, stride=1)
+        self.conv0bf = conv(32, 16, kernel_size=3, stride=1)
+        self.conv0bg = conv(16, 16, kernel_size=3, stride=1)
+        self.conv0bh = conv(16, 16, kernel_size=3, stride=1)
+
+    def _trunk(self, img):
+        f = self.conv0aa(img)
+        return self.conv0bh(self.conv0bg(self.conv0bf(self.conv0be(self.conv0bd(self.conv0bc(self.conv0bb(self.conv0ba(f))))))))
+
+    def forward(self, img, scales=5):
+        fp = [self._trunk(img)]
+        for _ in range(scales - 1):
+            img = F.interpolate(img, scale_factor=0.5, mode='bilinear', align_corners=None).detach()
+            fp.append(self._trunk(img))
+        return fp
+
+
+class CostRegNet(nn.Module):
+    """jdacs-ms/models/network.py:44-74.  C8 (or [B,16,D,H,W]) in, [B,D,H,W] fp32 out.  D, H, W must be even."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0 = ConvBnReLU3D(16, 16, kernel_size=3, pad=1)
+        self.conv0a = ConvBnReLU3D(16, 16, kernel_size=3, pad=1)
+        self.conv1 = ConvBnReLU3D(16, 32, stride=2, kernel_size=3, pad=1)
+        self.conv2 = ConvBnReLU3D(32, 32, kernel_size=3, pad=1)
+        self.conv2a = ConvBnReLU3D(32, 32, kernel_size=3, pad=1)
+        self.conv3 = ConvBnReLU3D(32, 64, kernel_size=3, pad=1)
+        self.conv4 = ConvBnReLU3D(64, 64, kernel_size=3, pad=1)
+        self.conv4a = ConvBnReLU3D(64, 64, kernel_size=3, pad=1)
+        self.conv5 = nn.Sequential(
+            nn.ConvTranspose3d(64, 32, kernel_size=3, padding=1, output_padding=0, stride=1, bias=False),
+            nn.BatchNorm3d(32), nn.ReLU(inplace=True))
+        self.conv6 = nn.Sequential(
+            nn.ConvTranspose3d(32, 16, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+            nn.BatchNorm3d(16), nn.ReLU(inplace=True))
+        self.prob0 = nn.Conv3d(16, 1, 3, stride=1, padding=1)
+        self._cache = regnet.PackCache()
+        self.algo = 0
+        self.act_dtype = None
+
+    def forward(self, x):
+        tr = self.training
+        x = regnet.as_c8(x, torch.float32 if tr else (self.act_dtype or torch.float32))
+        for n in (x.shape[2], x.shape[3], x.shape[4]):
+            if n % 2:
+                raise ValueError("CVP CostRegNet needs even D, H, W (got %s), as the reference does" % (tuple(x.shape[2:5]),))
+        a, c = self.algo, self._cache
+        conv0 = self.conv0a(self.conv0(x, None, a), None, a)
+        conv2 = self.conv2a(self.conv2(self.conv1(conv0, None, a), None, a), None, a)
+        conv4 = self.conv4a(self.conv4(self.conv3(conv2, None, a), None, a), None, a)
+        conv5 = regnet.conv_bn_relu(conv4, self.conv5[0], self.conv5[1], tr, c, conv2, a)
+        conv6 = regnet.conv_bn_relu(conv5, self.conv6[0], self.conv6[1], tr, c, conv0, a)
+        return regnet.conv_bias(conv6, self.prob0, tr, c, a)
+
+
+class CVPMVSNet(nn.Module):
+    """jdacs-ms/models/network.py:77-199.
+
+    forward(ref_img [B,3,H,W], src_imgs [B,nsrc,3,H,W], ref_in [B,3,3], src_in [B,nsrc,3,3], ref_ex [B,4,4],
+            src_ex [B,nsrc,4,4], depth_min [B], depth_max [B])
+        -> {"depth_est_list": [finest ... coarsest], "prob_confidence": [B,H,W]}
+    args needs .nsrc, .nscale, .mode like the reference's argparse namespace."""
+
+    def __init__(self, args, volume_dtype=torch.float32):
+        super().__init__()
+        self.featurePyramid = FeaturePyramid()
+        self.cost_reg_refine = CostRegNet()
+        self.args = args
+        self.volume_dtype = volume_dtype
+
+    def forward(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max):
+        nsrc, nscale = self.args.nsrc, self.args.nscale
+        depth_est_list = []
+        dt = torch.float32 if self.training else self.volume_dtype
+        self.cost_reg_refine.act_dtype = None if self.training else dt
+
+        ref_pyr = self.featurePyramid(ref_img, nscale)
+        src_pyrs = [self.featurePyramid(src_imgs[:, i], nscale) for i in range(nsrc)]
+        ref_in_ms = conditionIntrinsics(ref_in, ref_img.shape, [f.shape for f in ref_pyr])
+        src_in_ms = torch.stack([conditionIntrinsics(src_in[:, i], ref_img.shape, [f.shape for f in src_pyrs[i]])
+                                 for i in range(nsrc)]).permute(1, 0, 2, 3, 4)  # [B,nsrc,nscale,3,3]
+
+        # coarsest level: fronto-parallel sweep (network.py:110-148)
+        depth_hypos = calSweepingDepthHypo(ref_in_ms[:, -1], src_in_ms[:, 0, -1], ref_ex, src_ex, depth_min, depth_max)
+        rt = ops.compose_proj_ke(ref_in_ms[:, -1], src_in_ms[:, :, -1], ref_ex, src_ex[:, :nsrc], 1.0)
+        cost_volume = ops.warp_variance(ref_pyr[-1], [p[-1] for p in src_pyrs], rt, depth_hypos, dt, ALIGN_CORNERS, True)
+        cost_reg = self.cost_reg_refine(cost_volume)
+        depth, _, conf, _ = ops.soft_argmin(cost_reg, depth_hypos)
+        depth_est_list.append(depth)
+
+        # refinement up the pyramid (network.py:153-180)
+        for level in range(nscale - 2, -1, -1):
+            depth_up = F.interpolate(depth[None, :], size=None, scale_factor=2, mode='bilinear', align_corners=None).squeeze(0)
+            depth_hypos = calDepthHypo(self.args, depth_up, ref_in_ms[:, level], src_in_ms[:, :, level], ref_ex, src_ex,
+                                       depth_min, depth_max, level)
+            cost_volume = proj_cost(self.args, ref_pyr[level], src_pyrs, level, ref_in_ms[:, level],
+                                    src_in_ms[:, :, level], ref_ex, src_ex, depth_hypos, dt, as_c8=True)
+            cost_reg2 = self.cost_reg_refine(cost_volume)
+            depth, _, conf, _ = ops.soft_argmin(cost_reg2, depth_hypos)
+            depth_est_list.append(depth)
+
+        depth_est_list.reverse()  # finest first (network.py:195)
+        return {"depth_est_list": depth_est_list, "prob_confidence": conf}
+
+
+def sL1_loss(depth_est, depth_gt, mask):
+    """jdacs-ms/models/network.py:202-203."""
+    return F.smooth_l1_loss(depth_est[mask], depth_gt[mask], reduction='mean')
+
+
+def MSE_loss(depth_est, depth_gt, mask):
+    """jdacs-ms/models/network.py:206-207."""
+    return F.mse_loss(depth_est[mask], depth_gt[mask], reduction='mean')

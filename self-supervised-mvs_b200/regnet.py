@@ -1,0 +1,109 @@
+"""Runner for the 3-D regularisation U-Nets over C8 volumes.
+
+The parameter-holding modules keep the reference's names and shapes (checkpoint compatibility);
+their arithmetic goes through libmvs_b200:
+  * inference (module.eval(), the headline path): BatchNorm is folded to a per-channel affine and fused,
+    with ReLU and the skip add, into the convolution epilogue -> one kernel per layer, any storage dtype;
+  * training (module.train()): un-activated convolution -> batch statistics -> normalise+ReLU+skip kernels, fp32,
+    differentiable (ops._Conv3d / ops._BnAct), running statistics updated like nn.BatchNorm3d.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+class PackCache:
+    """Packed weights / folded BN affines of frozen (eval-mode) parameters, invalidated by in-place updates."""
+
+    def __init__(self) -> None:
+        self._store: Dict[Tuple, Tuple] = {}
+
+    @staticmethod
+    def _key(*tensors: Tensor) -> Tuple:
+        return tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+
+    def packed(self, weight: Tensor, transposed: bool) -> Tensor:
+        k = ("w", id(weight), transposed)
+        hit = self._store.get(k)
+        ver = self._key(weight)
+        if hit is None or hit[0] != ver:
+            if len(self._store) > 512:  # replicas (nn.DataParallel) come and go: keep the table bounded
+                self._store.clear()
+            hit = (ver, ops.pack_conv3d_weight(weight, transposed))
+            self._store[k] = hit
+        return hit[1]
+
+    def folded(self, bn: nn.modules.batchnorm._BatchNorm) -> Tuple[Tensor, Tensor]:
+        k = ("bn", id(bn))
+        ver = self._key(bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        hit = self._store.get(k)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.fold_bn(bn))
+            self._store[k] = hit
+        return hit[1]
+
+
+def conv_bn_relu(x: Tensor, conv: nn.Module, bn: nn.modules.batchnorm._BatchNorm, training: bool, cache: PackCache,
+                 skip: Optional[Tensor] = None, algo: int = 0) -> Tensor:
+    """relu(bn(conv(x))) + skip for nn.Conv3d or nn.ConvTranspose3d holders (3x3x3, pad 1, stride 1|2)."""
+    transposed = isinstance(conv, nn.ConvTranspose3d)
+    stride = conv.stride[0]
+    cout = conv.out_channels
+    if training:
+        z = ops.conv3d(x, conv.weight, None, stride, transposed)
+        return ops.bn_act_train(z, bn, skip, True)
+    scale, shift = cache.folded(bn)
+    return ops.conv3d_raw(x, cache.packed(conv.weight, transposed), cout, stride, transposed, scale, shift, skip,
+                          relu=True, algo=algo)
+
+
+def conv_bias(x: Tensor, conv: nn.Conv3d, training: bool, cache: PackCache, algo: int = 0) -> Tensor:
+    """The final single-channel `prob` convolution: plain fp32 [B,D,H,W] out."""
+    if training:
+        return ops.conv3d(x, conv.weight, conv.bias, 1, False)
+    bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+    return ops.conv3d_raw(x, cache.packed(conv.weight, False), conv.out_channels, 1, False, None, bias, None, relu=False,
+                          algo=algo)
+
+
+def as_c8(x: Tensor, dtype: torch.dtype) -> Tensor:
+    """Accept either a C8 volume or the reference's [B,C,D,H,W] fp32 tensor (API parity)."""
+    if x.dim() == 6:
+        return x
+    if x.dim() != 5:
+        raise ValueError("expected [B,C,D,H,W] or C8 [B,C/8,D,H,W,8], got %s" % (tuple(x.shape),))
+    if x.requires_grad:
+        return _PackC8.apply(x)
+    return ops.pack_c8(x, dtype)
+
+
+class _PackC8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor) -> Tensor:
+        return ops.pack_c8(x, torch.float32)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        return ops.unpack_c8(g.contiguous())
+
+
+class _UnpackC8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor) -> Tensor:
+        return ops.unpack_c8(x)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        return ops.pack_c8(g, torch.float32)
+
+
+def unpack_c8_grad(x: Tensor) -> Tensor:
+    """C8 -> [B,C,*spatial] fp32, differentiable."""
+    return _UnpackC8.apply(x)

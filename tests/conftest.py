@@ -61,7 +61,7 @@ class Backend:
             return {k: self.to(v) for k, v in t.items()}
         if isinstance(t, (list, tuple)):
             return type(t)(self.to(v) for v in t)
-        return t.to(self.device) if isinstance(t, torch.Tensor) else t
+        return t.detach().clone().to(self.device) if isinstance(t, torch.Tensor) else t
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,71 @@
+"""The C-ABI boundary: header <-> exports <-> ctypes table, error behaviour, no-fallback behaviour.  CPU only."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "mvs_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_matches_ctypes_table():
+    import ssmvs_b200
+    assert sorted(ssmvs_b200._lib.EXPORTS) == _declared()
+
+
+def test_library_exports_every_declared_symbol():
+    """libmvs_b200.so (built by __graft_entry__.build()) must load on a box without a GPU and export the ABI."""
+    import ssmvs_b200
+    path = ssmvs_b200._lib.DEFAULT_PATH
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(path)
+    for name in _declared():
+        assert hasattr(lib, name), name
+    lib.mvs_version.restype = ctypes.c_int
+    assert lib.mvs_version() == 100
+    lib.mvs_is_emulation.restype = ctypes.c_int
+    assert lib.mvs_is_emulation() == 0
+
+
+def test_product_library_refuses_cpu_tensors():
+    """No CPU fallback: with the real library bound, host tensors raise instead of silently computing."""
+    import ssmvs_b200
+    ssmvs_b200._lib.bind()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ssmvs_b200.ops.pack_c8(torch.zeros(1, 8, 4, 4))
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    import ssmvs_b200
+    with pytest.raises(RuntimeError, match="not found"):
+        ssmvs_b200._lib.bind(str(tmp_path / "nope.so"))
+    ssmvs_b200._lib.bind()
+
+
+def test_error_codes_and_messages(emu):
+    import ssmvs_b200
+    from ssmvs_b200 import ops
+    with pytest.raises(ValueError):
+        ops.pack_c8(torch.zeros(1, 7, 4, 4))                      # C % 8
+    lib = ssmvs_b200._lib.lib()
+    rc = lib.mvs_pack_c8(None, None, 1, 8, 16, 0, None)
+    assert rc == -1 and b"null" in lib.mvs_last_error()
+    rc = lib.mvs_compose_proj(1, 1, 1, 12, None)                   # too many views (pointers never dereferenced)
+    assert rc == -2 and b"views" in lib.mvs_last_error()
+    x = ops.pack_c8(torch.zeros(1, 8, 3, 4, 4))
+    g = torch.zeros(27, 8, 8)
+    with pytest.raises(ValueError, match="even"):
+        ops.conv3d_raw(x, g, 8, stride=2)                          # odd extent under stride 2
+    with pytest.raises(RuntimeError, match="emulation"):
+        ops.conv3d_raw(ops.pack_c8(torch.zeros(1, 8, 4, 4, 4)), g, 8, algo=2)

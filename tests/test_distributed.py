@@ -1,0 +1,48 @@
+"""world_size-2 gloo tests of the multi-GPU plumbing (sharding, flat gradient all-reduce, max-over-ranks timing)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import ssmvs_b200
+    from ssmvs_b200 import parallel
+    r, w, _ = parallel.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    items = list(parallel.shard_items(5, r, w))
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    x = torch.full((2, 4), float(rank + 1))
+    lin(x).sum().backward()
+    n = parallel.allreduce_gradients(lin.parameters())
+    t = parallel.max_over_ranks(10.0 + rank)
+    parallel.barrier()
+    out[rank] = (items, n, lin.weight.grad.clone(), t)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_gradient_allreduce():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29611, out), nprocs=world, join=True)
+    (i0, n0, g0, t0), (i1, n1, g1, t1) = out[0], out[1]
+    assert i0 == [0, 1, 2] and i1 == [3, 4]                     # every item exactly once
+    assert n0 == n1 == 15
+    assert torch.allclose(g0, g1) and torch.allclose(g0, torch.full((3, 4), 3.0))  # mean of 2*1 and 2*2
+    assert t0 == t1 == 11.0
+
+
+def test_shard_items_covers_everything():
+    from ssmvs_b200 import parallel
+    for n in (1, 7, 8, 13):
+        for w in (1, 2, 4, 8):
+            got = [i for r in range(w) for i in parallel.shard_items(n, r, w)]
+            assert got == list(range(n))

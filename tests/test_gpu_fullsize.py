@@ -1,0 +1,142 @@
+"""Full-size (BASELINE.json configs[1]: N=5, 128x160 maps, C=32, D=192) checks on the B200.
+
+The oracle is too slow / memory hungry to run at this size inside a test, so parity is established through
+size-independent properties and through plain PyTorch fp32 GPU ops of the same arithmetic (ATen grid_sample,
+conv3d, softmax), which are what the unmodified reference would execute on this GPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg2(gpu):
+    from ssmvs_b200 import ops, synth
+    inp = synth.feature_inputs(1, 5, 32, 128, 160, 192, seed=0)
+    feats = [f.to(gpu.device) for f in inp["features"]]
+    rt = ops.compose_proj(inp["proj_matrices"].to(gpu.device))
+    return {"feats": feats, "rt": rt, "dv": inp["depth_values"].to(gpu.device), "proj": inp["proj_matrices"].to(gpu.device)}
+
+
+def _torch_variance(feats, proj, dv):
+    """The reference's op sequence on the GPU (grid_sample + elementwise), jdacs/models/mvsnet.py:120-136."""
+    b, c, h, w = feats[0].shape
+    d = dv.shape[1]
+    ref = feats[0].unsqueeze(2).expand(b, c, d, h, w)
+    s1, s2 = ref.clone(), ref ** 2
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dv.device), torch.arange(w, dtype=torch.float32, device=dv.device), indexing="ij")
+    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, device=dv.device)))
+    for s in range(1, len(feats)):
+        rel = proj[:, s] @ torch.inverse(proj[:, 0])
+        ray = rel[:, :3, :3] @ pix.unsqueeze(0)
+        pts = ray.unsqueeze(2) * dv.view(b, 1, d, 1) + rel[:, :3, 3].view(b, 3, 1, 1)
+        xy = pts[:, :2] / pts[:, 2:3]
+        grid = torch.stack((xy[:, 0] / ((w - 1) / 2) - 1, xy[:, 1] / ((h - 1) / 2) - 1), dim=3).view(b, d * h, w, 2)
+        wv = F.grid_sample(feats[s], grid, mode="bilinear", padding_mode="zeros", align_corners=False).view(b, c, d, h, w)
+        s1 += wv
+        s2 += wv ** 2
+    n = len(feats)
+    return s2 / n - (s1 / n) ** 2
+
+
+def test_variance_volume_matches_aten_at_full_size(cfg2):
+    from ssmvs_b200 import ops
+    want = _torch_variance(cfg2["feats"], cfg2["proj"], cfg2["dv"])
+    v32 = ops.unpack_c8(ops.warp_variance(cfg2["feats"][0], cfg2["feats"][1:], cfg2["rt"], cfg2["dv"], torch.float32))
+    assert rel_err(v32, want) < 1e-4
+    scale = want.abs().max().item()
+    for dt, tol in ((torch.float16, 2e-3), (torch.bfloat16, 2e-2)):   # storage rounding of inputs and output only
+        v = ops.unpack_c8(ops.warp_variance(cfg2["feats"][0], cfg2["feats"][1:], cfg2["rt"], cfg2["dv"], dt))
+        assert (v - want).abs().max().item() < tol * scale, dt
+
+
+def test_variance_properties(cfg2):
+    from ssmvs_b200 import ops
+    f, rt, dv = cfg2["feats"], cfg2["rt"], cfg2["dv"]
+    v = ops.warp_variance(f[0], f[1:], rt, dv, torch.float32)
+    assert torch.isfinite(v).all() and v.min().item() > -1e-4            # a variance (fp32 cancellation only)
+    v2 = ops.warp_variance(2 * f[0], [2 * s for s in f[1:]], rt, dv, torch.float32)
+    assert torch.equal(v2, 4 * v)                                          # exact: scaling by 2 commutes with fp32 rounding
+    perm = [2, 0, 3, 1]
+    vp = ops.warp_variance(f[0], [f[1 + i] for i in perm], rt[perm].contiguous(), dv, torch.float32)
+    assert rel_err(vp, v) < 1e-5                                           # symmetric in the source views
+    same = ops.warp_variance(f[0], [f[0]], ops.compose_proj(torch.eye(4, device=dv.device).expand(1, 2, 4, 4).contiguous()), dv, torch.float32)
+    assert same.abs().max().item() < 1e-5                                  # identical views at identity pose: zero variance
+
+
+def test_regularisation_matches_cudnn_at_full_size(gpu):
+    """CostRegNet (our kernels) vs the same state_dict run through ATen/cuDNN conv3d in fp32."""
+    from ssmvs_b200 import ops
+    from ssmvs_b200.jdacs.models.mvsnet import CostRegNet
+    torch.manual_seed(0)
+    net = CostRegNet().to(gpu.device).eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        x = torch.randn(1, 32, 48, 64, 80, device=gpu.device).abs()
+        sd = {k: v for k, v in net.state_dict().items()}
+
+        def cbr(t, name, stride):
+            y = F.conv3d(t, sd[name + ".conv.weight"], None, stride, 1)
+            return F.relu(F.batch_norm(y, sd[name + ".bn.running_mean"], sd[name + ".bn.running_var"], sd[name + ".bn.weight"], sd[name + ".bn.bias"], False, 0.1, 1e-5))
+
+        def dbr(t, name):
+            y = F.conv_transpose3d(t, sd[name + ".0.weight"], None, 2, 1, 1)
+            return F.relu(F.batch_norm(y, sd[name + ".1.running_mean"], sd[name + ".1.running_var"], sd[name + ".1.weight"], sd[name + ".1.bias"], False, 0.1, 1e-5))
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        c0 = cbr(x, "conv0", 1); c2 = cbr(cbr(c0, "conv1", 2), "conv2", 1); c4 = cbr(cbr(c2, "conv3", 2), "conv4", 1)
+        y = cbr(cbr(c4, "conv5", 2), "conv6", 1)
+        y = c4 + dbr(y, "conv7"); y = c2 + dbr(y, "conv9"); y = c0 + dbr(y, "conv11")
+        want = F.conv3d(y, sd["prob.weight"], sd["prob.bias"], 1, 1).squeeze(1)
+        torch.backends.cudnn.allow_tf32 = prev[0]
+        net.algo = 1
+        got = net(ops.pack_c8(x))
+        assert rel_err(got, want) < 1e-4
+        net.algo = 0
+        for dt, tol in ((torch.float16, 1e-2), (torch.bfloat16, 5e-2)):
+            net.act_dtype = dt
+            got = net(ops.pack_c8(x, dt))
+            assert (got - want).abs().max().item() < tol * want.abs().max().item(), dt
+
+
+def test_softargmin_matches_aten_at_full_size(gpu):
+    from ssmvs_b200 import ops
+    torch.manual_seed(1)
+    cost = 4.0 * torch.randn(1, 192, 128, 160, device=gpu.device)
+    dv = (425.0 + 2.65 * torch.arange(192.0, device=gpu.device)).unsqueeze(0)
+    depth, index, conf, _ = ops.soft_argmin(cost, dv)
+    p = F.softmax(cost, 1)
+    want = (p * dv.view(1, 192, 1, 1)).sum(1)
+    widx = (p * torch.arange(192.0, device=gpu.device).view(1, 192, 1, 1)).sum(1)
+    assert rel_err(depth, want) < 1e-5
+    # the index is a truncated float sum (hazard H12): it may differ only where the sum sits within 1e-4 of an integer
+    diff = index != widx.long()
+    assert (diff & ((widx - widx.round()).abs() > 1e-4)).sum().item() == 0
+    assert diff.float().mean().item() < 1e-3
+    win = 4 * F.avg_pool3d(F.pad(p.unsqueeze(1), (0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1).squeeze(1)
+    assert rel_err(conf[~diff], torch.gather(win, 1, index.unsqueeze(1)).squeeze(1)[~diff]) < 1e-5
+
+
+def test_mvsnet_half_precision_volume_within_north_star_tolerance(gpu):
+    """Whole MVSNet.forward at the headline size: fp16 / bf16 volume vs fp32 volume, <= 1e-3 relative on depth."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False)
+    with torch.no_grad():
+        model.cost_regularization.prob.weight.mul_(64.0)
+    model = model.to(gpu.device).eval()
+    inp = gpu.to(synth.mvsnet_inputs(1, 5, 512, 640, 192, seed=0))
+    with torch.no_grad():
+        model.volume_dtype = torch.float32
+        d32 = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])["depth"]
+        model.volume_dtype = torch.float16
+        d16 = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])["depth"]
+    assert torch.isfinite(d32).all() and d32.min() > 420 and d32.max() < 940
+    assert ((d16 - d32).abs() / d32).max().item() < 1e-3

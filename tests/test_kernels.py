@@ -1,0 +1,244 @@
+"""Per-kernel parity of the C ABI against the oracle and the golden fixtures.
+
+Every test runs twice: on the host-emulation build of the kernel sources (CPU box, `-m "not gpu"`) and on
+libmvs_b200.so on the B200 (`-m gpu`).  Tolerances are for fp32 storage / fp32 accumulation: coordinates are
+re-derived (fp64 projection inverse instead of the reference's fp32 LU), so samples agree to ~1e-5 relative."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+TOL = 5e-5
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def be(request):
+    return request.getfixturevalue(request.param)
+
+
+def _ops():
+    from ssmvs_b200 import ops
+    return ops
+
+
+def test_c8_roundtrip(be):
+    ops = _ops()
+    x = torch.randn(2, 24, 3, 5, 7)
+    p = ops.pack_c8(be.to(x))
+    assert p.shape == (2, 3, 3, 5, 7, 8)
+    assert torch.equal(p.cpu()[1, 2, 1, 4, 6], x[1, 16:24, 1, 4, 6])
+    assert torch.equal(ops.unpack_c8(p).cpu(), x)
+
+
+def test_compose_proj(be, oracle, golden):
+    ops = _ops()
+    g = golden("jdacs_warp")
+    rt = ops.compose_proj(be.to(torch.stack([g["ref_proj"], g["src_proj"], g["src_proj2"]], 1))).cpu()
+    for s, key in enumerate(("src_proj", "src_proj2")):
+        rot, trans = oracle.relative_projection(g[key], g["ref_proj"])
+        assert rel_err(rt[s, :, :9].reshape(-1, 3, 3), rot) < 1e-6
+        assert rel_err(rt[s, :, 9:], trans.squeeze(-1)) < 1e-6
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_homo_warp_matches_reference(be, oracle, golden, align):
+    ops = _ops()
+    g = golden("jdacs_warp")
+    rt = ops.compose_proj(be.to(torch.stack([g["ref_proj"], g["src_proj"], g["src_proj2"]], 1)))
+    out = ops.homo_warp(be.to(g["src_fea"]), rt[0], be.to(g["depth_values"]), align)
+    want = g["warped"] if not align else oracle.homo_warping(g["src_fea"], g["src_proj"], g["ref_proj"], g["depth_values"], True)
+    assert rel_err(out, want) < TOL
+    far = ops.homo_warp(be.to(g["src_fea"]), rt[1], be.to(g["depth_far"]), align)
+    assert torch.allclose(far.cpu(), oracle.homo_warping(g["src_fea"], g["src_proj2"], g["ref_proj"], g["depth_far"], align), atol=1e-5)
+
+
+def test_homo_warp_degenerate_coordinates(be):
+    """z <= 0, NaN and inf depths must give exact zeros (every tap rejected), like grid_sample's zero padding."""
+    ops = _ops()
+    src = torch.randn(1, 4, 6, 9)
+    P = torch.eye(4).reshape(1, 1, 4, 4).repeat(1, 2, 1, 1)
+    P[0, 1, 2, 3] = -10.0  # source camera: z = depth - 10
+    rt = ops.compose_proj(be.to(P))
+    depth = torch.tensor([[10.0, 5.0, float("nan"), float("inf"), 1e30]])
+    out = ops.homo_warp(be.to(src), rt[0], be.to(depth)).cpu()
+    assert torch.isfinite(out).all()
+    assert torch.count_nonzero(out[:, :, 0]) == 0 and torch.count_nonzero(out[:, :, 2]) == 0
+
+
+@pytest.mark.parametrize("ref_sq,align", [(False, False), (True, False), (False, True)])
+def test_warp_variance_forward_backward(be, oracle, golden, ref_sq, align):
+    ops = _ops()
+    g = golden("jdacs_warp")
+    torch.manual_seed(3)
+    ref = torch.randn(2, 8, 12, 16)
+    srcs = [g["src_fea"], 0.5 * g["src_fea"].flip(0)]
+    projs = [g["src_proj"], g["src_proj2"]]
+    wt = torch.randn(2, 8, 6, 12, 16)
+    rt = ops.compose_proj(be.to(torch.stack([g["ref_proj"]] + projs, 1)))
+    a = [be.to(t).detach().clone().requires_grad_(True) for t in [ref] + srcs]
+    var = ops.warp_variance(a[0], a[1:], rt, be.to(g["depth_values"]), torch.float32, align, ref_sq)
+    (var * ops.pack_c8(be.to(wt))).sum().backward()
+    b = [t.detach().clone().requires_grad_(True) for t in [ref] + srcs]
+    want = oracle.variance_volume(b[0], b[1:], g["ref_proj"], projs, g["depth_values"], ref_sq, align)
+    (want * wt).sum().backward()
+    assert rel_err(ops.unpack_c8(var), want) < TOL
+    for x, y in zip(a, b):
+        assert rel_err(x.grad, y.grad) < TOL
+
+
+def test_warp_variance_per_pixel_hypotheses(be, golden):
+    """proj_cost: per-pixel hypotheses + the CVP variance (hazard H2), against the reference's own output."""
+    ops = _ops()
+    g = golden("ms_warp")
+    rt = ops.compose_proj_ke(*[be.to(g[k]) for k in ("ref_in", "src_in", "ref_ex", "src_ex")], 1.0)
+    v = ops.warp_variance(be.to(g["ref_fea"]), [be.to(g["src_fea0"]), be.to(g["src_fea1"])], rt, be.to(g["refine_hypos"]),
+                          ref_sq_in_sum=True)
+    assert rel_err(ops.unpack_c8(v), g["proj_cost"]) < TOL
+    rt1 = ops.compose_proj_ke(*[be.to(g[k]) for k in ("ref_in", "src_in", "ref_ex", "src_ex")], 2.0)
+    w = ops.homo_warp(be.to(g["src_fea"]), rt1[0], be.to(g["sweep_hypos"]))
+    assert rel_err(w, g["warped"]) < TOL
+
+
+def test_warp_variance_odd_sizes(be, oracle):
+    """Ragged map (odd H, W not a multiple of the block) and a depth count that does not divide the chunking."""
+    ops = _ops()
+    from ssmvs_b200 import synth
+    inp = synth.feature_inputs(1, 3, 16, 7, 13, 5, seed=4)
+    f = inp["features"]
+    rt = ops.compose_proj(be.to(inp["proj_matrices"]))
+    v = ops.warp_variance(be.to(f[0]), [be.to(f[1]), be.to(f[2])], rt, be.to(inp["depth_values"]))
+    P = inp["proj_matrices"]
+    want = oracle.variance_volume(f[0], [f[1], f[2]], P[:, 0], [P[:, 1], P[:, 2]], inp["depth_values"])
+    assert rel_err(ops.unpack_c8(v), want) < TOL
+
+
+def test_soft_argmin(be, oracle, golden):
+    ops = _ops()
+    g = golden("jdacs_mvsnet")
+    cost = be.to(g["cost_reg"]).detach().clone().requires_grad_(True)
+    depth, index, conf, prob = ops.soft_argmin(cost, be.to(g["depth_values"]), True)
+    assert rel_err(depth, g["depth"]) < 1e-6
+    assert rel_err(conf, g["photometric_confidence"]) < 1e-5
+    assert torch.equal(index.cpu(), g["index"])                      # bit-exact index on the reference's own cost_reg
+    wm = torch.randn(1, 16, 24)
+    (depth * be.to(wm)).sum().backward()
+    c2 = g["cost_reg"].clone().requires_grad_(True)
+    p2, d2 = oracle.soft_argmin(c2, g["depth_values"])
+    (d2 * wm).sum().backward()
+    assert rel_err(prob, p2) < 1e-5 and rel_err(cost.grad, c2.grad) < 1e-5
+    dpp = g["depth_values"].view(1, 8, 1, 1) + torch.randn(1, 8, 16, 24)
+    d3, *_ = ops.soft_argmin(be.to(g["cost_reg"]), be.to(dpp))
+    assert rel_err(d3, oracle.soft_argmin(g["cost_reg"], dpp)[1]) < 1e-6
+
+
+def test_soft_argmin_index_exact_on_peaky_columns(be, oracle):
+    """One-hot-like columns: expected index lands on integers; truncation must agree with the oracle everywhere."""
+    ops = _ops()
+    torch.manual_seed(5)
+    cost = torch.randn(2, 32, 9, 11)
+    peak = torch.randint(0, 32, (2, 9, 11))
+    cost.scatter_(1, peak.unsqueeze(1), 60.0)
+    dv = (425.0 + 2.65 * torch.arange(32.0)).unsqueeze(0).repeat(2, 1)
+    _, index, conf, _ = ops.soft_argmin(be.to(cost), be.to(dv))
+    oi, oc = oracle.photometric_confidence(F.softmax(cost, 1))
+    assert torch.equal(index.cpu(), oi) and rel_err(conf, oc) < 1e-5
+
+
+CONVS = [(32, 8, 1, False), (8, 16, 2, False), (16, 16, 1, False), (64, 32, 2, True), (16, 8, 2, True), (8, 1, 1, False),
+         (64, 32, 1, True)]
+
+
+@pytest.mark.parametrize("cin,cout,stride,tr", CONVS)
+def test_conv3d_forward_and_gradients(be, cin, cout, stride, tr):
+    ops = _ops()
+    torch.manual_seed(cin + cout)
+    x = torch.randn(2, cin, 4, 6, 8)
+    w = 0.1 * (torch.randn(cin, cout, 3, 3, 3) if tr else torch.randn(cout, cin, 3, 3, 3))
+    bias = torch.randn(cout) if cout == 1 else None
+
+    def ref(xx, ww, bb):
+        return F.conv_transpose3d(xx, ww, bb, stride, 1, stride - 1) if tr else F.conv3d(xx, ww, bb, stride, 1)
+    xa, wa = ops.pack_c8(be.to(x)).requires_grad_(True), be.to(w).requires_grad_(True)
+    ba = be.to(bias).requires_grad_(True) if bias is not None else None
+    ya = ops.conv3d(xa, wa, ba, stride, tr)
+    xb, wb = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    bb = bias.clone().requires_grad_(True) if bias is not None else None
+    yb = ref(xb, wb, bb)
+    wt = torch.randn_like(yb)
+    (ya * (be.to(wt.squeeze(1)) if cout == 1 else ops.pack_c8(be.to(wt)))).sum().backward()
+    (yb * wt).sum().backward()
+    got = ya.detach().unsqueeze(1) if cout == 1 else ops.unpack_c8(ya)
+    assert rel_err(got, yb) < 1e-5
+    assert rel_err(ops.unpack_c8(xa.grad), xb.grad) < 1e-5
+    assert rel_err(wa.grad, wb.grad) < 1e-5
+    if bias is not None:
+        assert rel_err(ba.grad, bb.grad) < 1e-5
+
+
+def test_conv3d_fused_epilogue(be):
+    """Inference form: relu(conv * scale + shift) + skip in one kernel."""
+    ops = _ops()
+    torch.manual_seed(1)
+    x, w = torch.randn(1, 16, 4, 4, 8), 0.1 * torch.randn(8, 16, 3, 3, 3)
+    scale, shift, skip = torch.rand(8) + 0.5, torch.randn(8), torch.randn(1, 8, 4, 4, 8)
+    y = ops.conv3d_raw(ops.pack_c8(be.to(x)), ops.pack_conv3d_weight(be.to(w), False), 8, 1, False, be.to(scale), be.to(shift),
+                       ops.pack_c8(be.to(skip)), relu=True, algo=1)
+    want = F.relu(F.conv3d(x, w, None, 1, 1) * scale.view(1, 8, 1, 1, 1) + shift.view(1, 8, 1, 1, 1)) + skip
+    assert rel_err(ops.unpack_c8(y), want) < 1e-5
+
+
+def test_batch_norm_training(be):
+    ops = _ops()
+    torch.manual_seed(2)
+    bn = torch.nn.BatchNorm3d(16)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    bn2 = torch.nn.BatchNorm3d(16)
+    bn2.load_state_dict(bn.state_dict())
+    bn = bn.to(be.device)
+    x, skip, wt = torch.randn(2, 16, 4, 6, 8) * 2 + 0.5, torch.randn(2, 16, 4, 6, 8), torch.randn(2, 16, 4, 6, 8)
+    xa, sk = ops.pack_c8(be.to(x)).requires_grad_(True), ops.pack_c8(be.to(skip)).requires_grad_(True)
+    ya = ops.bn_act_train(xa, bn, sk, True)
+    (ya * ops.pack_c8(be.to(wt))).sum().backward()
+    xb, sb = x.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    yb = F.relu(bn2(xb)) + sb
+    (yb * wt).sum().backward()
+    assert rel_err(ops.unpack_c8(ya), yb) < 1e-5
+    assert rel_err(ops.unpack_c8(xa.grad), xb.grad) < 1e-4 and rel_err(ops.unpack_c8(sk.grad), sb.grad) < 1e-6
+    assert rel_err(bn.weight.grad, bn2.weight.grad) < 1e-4 and rel_err(bn.bias.grad, bn2.bias.grad) < 1e-4
+    assert rel_err(bn.running_mean, bn2.running_mean) < 1e-5 and rel_err(bn.running_var, bn2.running_var) < 1e-5
+
+
+def test_inverse_warp(be, golden):
+    ops = _ops()
+    g = golden("jdacs_invwarp")
+    d = be.to(g["depth"]).detach().clone().requires_grad_(True)
+    w, m = ops.inverse_warp(be.to(g["img"]), be.to(g["cams"][:, 0]), be.to(g["cams"][:, 2]), d)
+    (w * be.to(g["weight"])).sum().backward()
+    assert rel_err(w, g["warped"]) < TOL and torch.equal(m.cpu(), g["mask"])
+    assert rel_err(d.grad, g["grad_depth"]) < TOL
+    w, m = ops.inverse_warp(be.to(g["img"]), be.to(g["cams"][:, 0]), be.to(g["cams"][:, 1]), be.to(g["depth_far"]))
+    bad = (m.cpu() != g["mask_far"]).sum().item()
+    assert bad <= 2                                       # a mask bit may flip only where floor() sits on an integer
+    both = (m.cpu() * g["mask_far"])
+    assert rel_err(w.cpu() * both, g["warped_far"] * both) < TOL
+
+
+def test_inverse_warp_image_gradient(be, oracle, golden):
+    ops = _ops()
+    g = golden("jdacs_invwarp")
+    img = be.to(g["img"]).detach().clone().requires_grad_(True)
+    w, _ = ops.inverse_warp(img, be.to(g["cams"][:, 0]), be.to(g["cams"][:, 2]), be.to(g["depth"]))
+    (w * be.to(g["weight"])).sum().backward()
+    i2 = g["img"].clone().requires_grad_(True)
+    w2, _ = oracle.inverse_warping(i2, g["cams"][:, 0], g["cams"][:, 2], g["depth"])
+    (w2 * g["weight"]).sum().backward()
+    assert rel_err(img.grad, i2.grad) < TOL
+
+
+def test_depth_hypotheses(be, golden):
+    ops = _ops()
+    g = golden("ms_warp")
+    h = ops.depth_hypo_refine(*[be.to(t) for t in (g["depth_up"], g["ref_in"], g["src_in"][:, 0], g["ref_ex"], g["src_ex"][:, 0])])
+    assert rel_err(h, g["refine_hypos"]) < 1e-6

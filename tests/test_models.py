@@ -1,0 +1,103 @@
+"""The reference-facing modules (same names / signatures / state-dict keys) against outputs of the reference itself."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import rel_err, state_dict_of
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def be(request):
+    return request.getfixturevalue(request.param)
+
+
+def test_mvsnet_eval_and_train(be, golden):
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    g = golden("jdacs_mvsnet")
+    model = MVSNet(refine=False)
+    res = model.load_state_dict(state_dict_of(g), strict=False)
+    assert not res.unexpected_keys and all("num_batches_tracked" in k for k in res.missing_keys)
+    model = model.to(be.device).eval()
+    args = [be.to(g[k]) for k in ("imgs", "proj_matrices", "depth_values")]
+    with torch.no_grad():
+        out = model(*args)
+    assert set(out) == {"depth", "photometric_confidence"}
+    assert rel_err(out["depth"], g["depth"]) < 1e-4            # north_star: <= 1e-3 relative on depth maps
+    assert rel_err(out["photometric_confidence"], g["photometric_confidence"]) < 1e-3
+    model.train()
+    out = model(*args)
+    assert rel_err(out["depth"], g["train_depth"]) < 1e-4
+    (out["depth"] * be.to(g["loss_weight"])).sum().backward()
+    params = dict(model.named_parameters())
+    for k, v in g.items():
+        if k.startswith("grad."):
+            assert rel_err(params[k[5:]].grad, v) < 2e-3, k
+
+
+def test_mvsnet_stage_taps(be, golden):
+    """Variance volume and cost_reg of the eval forward, stage by stage, against the reference's tensors."""
+    from ssmvs_b200 import ops
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    g = golden("jdacs_mvsnet")
+    model = MVSNet(refine=False)
+    model.load_state_dict(state_dict_of(g), strict=False)
+    model = model.to(be.device).eval()
+    with torch.no_grad():
+        feats = be.to(g["features"])
+        rt = ops.compose_proj(be.to(g["proj_matrices"]))
+        var = ops.warp_variance(feats[0], [feats[1], feats[2]], rt, be.to(g["depth_values"]))
+        assert rel_err(ops.unpack_c8(var), g["variance"]) < 5e-5
+        reg = model.cost_regularization(ops.pack_c8(be.to(g["variance"])))
+        assert rel_err(reg, g["cost_reg"]) < 1e-4
+        assert rel_err(model.cost_regularization(be.to(g["variance"])).squeeze(1), g["cost_reg"]) < 1e-4  # reference-shaped input
+        _, index, _, _ = ops.soft_argmin(reg, be.to(g["depth_values"]))
+        assert (index.cpu() != g["index"]).sum().item() == 0
+
+
+def test_state_dict_keys_match_reference(golden):
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    mine = {k for k in MVSNet(refine=False).state_dict() if "num_batches_tracked" not in k}
+    assert mine == set(state_dict_of(golden("jdacs_mvsnet")))
+    mine = {k for k in CVPMVSNet(SimpleNamespace(nsrc=2, nscale=2, mode="test")).state_dict() if "num_batches_tracked" not in k}
+    assert mine == set(state_dict_of(golden("ms_cvp")))
+    assert {k for k in MVSNet(refine=True).state_dict()} >= {"refine_network.res.conv.weight"}
+
+
+def test_cvpmvsnet(be, golden):
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    g = golden("ms_cvp")
+    model = CVPMVSNet(SimpleNamespace(nsrc=2, nscale=2, mode="test"))
+    model.load_state_dict(state_dict_of(g), strict=False)
+    model = model.to(be.device).eval()
+    args = [be.to(g[k]) for k in ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")]
+    with torch.no_grad():
+        out = model(*args)
+    assert len(out["depth_est_list"]) == 2 and out["depth_est_list"][0].shape == (1, 32, 48)
+    for i, d in enumerate(out["depth_est_list"]):
+        assert rel_err(d, g["depth_est_list.%d" % i]) < 1e-4
+    assert rel_err(out["prob_confidence"], g["prob_confidence"]) < 1e-3
+    model.train()
+    out = model(*args)
+    sum(d.sum() for d in out["depth_est_list"]).backward()
+    assert model.cost_reg_refine.conv0.conv.weight.grad.abs().sum() > 0
+    assert model.featurePyramid.conv0aa[0].weight.grad.abs().sum() > 0
+
+
+def test_unsup_loss(be, golden):
+    from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs_ms.losses.unsup_loss import UnSupLoss as UnSupLossMS
+    for name, cls in (("jdacs_unsup_loss", UnSupLoss), ("ms_unsup_loss", UnSupLossMS)):
+        g = golden(name)
+        d = be.to(g["depth"]).detach().clone().requires_grad_(True)
+        crit = cls()
+        total = crit(be.to(g["imgs"]), be.to(g["cams"]), d)
+        total.backward()
+        assert rel_err(total, g["total"]) < 1e-5
+        assert rel_err(crit.reconstr_loss, g["reconstr"]) < 1e-5 and rel_err(crit.ssim_loss, g["ssim"]) < 1e-5
+        assert rel_err(crit.smooth_loss, g["smooth"]) < 1e-5
+        assert rel_err(d.grad, g["grad_depth"]) < 1e-4
+    with pytest.raises(RuntimeError):                          # hazard H5: top-3 needs >= 3 source views
+        g = golden("jdacs_unsup_loss")
+        UnSupLoss()(be.to(g["imgs"][:, :3]), be.to(g["cams"][:, :3]), be.to(g["depth"]))
