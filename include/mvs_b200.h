@@ -100,7 +100,10 @@ int mvs_pack_conv3d_weight(const float* w, float* g, int Cin, int Cout, int tran
  * Replaces ConvBnReLU3D / ConvTranspose3d+BN+ReLU / prob: jdacs/models/module.py:35-42, mvsnet.py:37-74,
  * jdacs-ms/models/network.py:44-74. */
 int mvs_conv3d_fwd(const mvs_conv3d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
-                   const void* skip, void* y, void* stream);
+                   const void* skip, void* y, void* ws, void* stream);
+/* bytes of caller-owned scratch `ws` mvs_conv3d_fwd needs for this descriptor (0 for the SIMT path; the tcgen05
+ * path re-packs the 27 weight tap tiles into it on every call, so in-place weight updates are always seen). */
+int64_t mvs_conv3d_workspace_bytes(const mvs_conv3d_desc* d);
 /* training: gradient w.r.t. the torch-layout weight ([Cout][Cin][27] or, transposed, [Cin][Cout][27]; zero-initialised
  * by the caller).  x: C8 volume (dtype_in), grad_y: C8 fp32 volume of the un-activated convolution output.
  * (The gradient w.r.t. x needs no entry point of its own: it is mvs_conv3d_fwd of grad_y with the same torch weight

@@ -40,7 +40,8 @@ _SIGS = {
     "mvs_warp_var_fwd": ([_P, C.POINTER(_P), _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "mvs_warp_var_bwd": ([_P, _P, C.POINTER(_P), _I, _P, _P, _I, _P, C.POINTER(_P), _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "mvs_pack_conv3d_weight": ([_P, _P, _I, _I, _I, _P], _I),
-    "mvs_conv3d_fwd": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P, _P, _P, _P], _I),
+    "mvs_conv3d_fwd": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "mvs_conv3d_workspace_bytes": ([C.POINTER(Conv3dDesc)], _L),
     "mvs_conv3d_bwd_weight": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P], _I),
     "mvs_bn_stats": ([_P, _P, _I, _I, _L, _P], _I),
     "mvs_bn_act_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P], _I),

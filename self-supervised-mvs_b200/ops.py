@@ -192,7 +192,9 @@ def conv3d_raw(x: Tensor, g: Tensor, cout: int, stride: int = 1, transposed: boo
         skip = skip.contiguous()
         if skip.shape != y.shape or skip.dtype != y.dtype:
             raise ValueError("skip tensor must match the output (%s %s vs %s %s)" % (tuple(skip.shape), skip.dtype, tuple(y.shape), y.dtype))
-    call("mvs_conv3d_fwd", x, C.byref(d), ptr(x), ptr(g), ptr(scale), ptr(shift), ptr(skip), ptr(y))
+    nws = _lib.lib().mvs_conv3d_workspace_bytes(C.byref(d))
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
+    call("mvs_conv3d_fwd", x, C.byref(d), ptr(x), ptr(g), ptr(scale), ptr(shift), ptr(skip), ptr(y), ptr(ws))
     return y
 
 
