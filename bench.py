@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -200,12 +201,16 @@ def main():
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
             l0 = ssmvs_b200._lib.launches
             t0 = time.perf_counter()
+            if args.ncu_range and fn is step_resident:
+                torch.cuda.profiler.start()
             for a, b in ev:
                 flush.zero_()
                 a.record(stream)
                 fn()
                 b.record(stream)
             torch.cuda.synchronize(dev)
+            if args.ncu_range and fn is step_resident:
+                torch.cuda.profiler.stop()
             parallel.barrier()
             wall = time.perf_counter() - t0
             launches = ssmvs_b200._lib.launches - l0
@@ -216,6 +221,8 @@ def main():
         ms_total, wall, launches = timed(step_resident, args.steps, args.warmup)
     clocks = clk.summary()
     ms_e2e, _, _ = timed(step_e2e, args.steps, 3)
+    if args.ncu_range:
+        return
 
     # ---- per-stage timing for the roofline (same inputs, each stage bracketed by events, L2 flushed before each)
     def stage_times(reps=5):

@@ -1,11 +1,12 @@
 #!/bin/bash
-# One GPU-box round: parity tests, smoke, bench, ncu launch list.  Usage (under gpurun): bash tools_gpu_round.sh [tag]
-TAG=${1:-r1}
+# One GPU-box round: parity tests, smoke, bench, ncu launch list.  Usage (under gpurun): bash tools_gpu_round.sh [tag] [steps...]
+TAG=${1:-r1}; shift
+STEPS=${@:-tc tests smoke bench ncu}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
-nproc > gpurun_out/${TAG}_nproc.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/${TAG}_nproc.txt
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
-tail -5 gpurun_out/${TAG}_pytest.log; tail -3 gpurun_out/${TAG}_smoke.log; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+for S in $STEPS; do case $S in
+ tc)    timeout 600 python -m pytest tests/test_conv3d_tc.py -q -m gpu --timeout 120 -x > gpurun_out/${TAG}_tc.log 2>&1; echo "tc rc=$?" >> gpurun_out/${TAG}_tc.log; tail -25 gpurun_out/${TAG}_tc.log;;
+ tests) timeout 1200 python -m pytest tests -q -m gpu --timeout 300 --deselect tests/test_conv3d_tc.py > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; tail -25 gpurun_out/${TAG}_pytest.log;;
+ smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log; tail -4 gpurun_out/${TAG}_smoke.log;;
+ bench) timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err;;
+ ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ncu-range > gpurun_out/${TAG}_ncu_bench.log 2>&1; tail -2 gpurun_out/${TAG}_ncu_bench.log;;
+esac; done
