@@ -6,6 +6,7 @@
 // Reference arithmetic: jdacs/models/module.py:105-140, mvsnet.py:120-136; jdacs-ms/models/modules.py:62-104,
 // 209-261, network.py:114-137.  Sampler semantics: ATen grid_sampler_2d bilinear / zeros padding.
 #include "mvs_rt.h"
+#include <stdlib.h>
 
 struct SrcPtrs { const void* p[MVS_MAX_SRC]; };
 struct GradPtrs { float* p[MVS_MAX_SRC]; };
@@ -217,6 +218,134 @@ warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, Src
     }
 }
 
+#ifndef MVS_CPU_EMU
+// ------------------------------------------------------------------------------------------------ fused forward, 16-bit storage
+// Same arithmetic as warp_var_fwd_kernel, arranged for instruction throughput (the kernel is issue-bound long before
+// it is HBM-bound): a thread owns CPT channel blocks of its pixel so the homography runs once per CPT*8 channels;
+// the four taps are blended with packed half2 / bfloat162 FMAs (one rounding to the storage type per FMA, the same
+// size as the storage rounding of the inputs); running sum / sum of squares / variance stay fp32 but use the packed
+// f32x2 pipe (FFMA2); projective divide by reciprocal; the reference's normalise / un-normalise pair is folded into one FMA.
+template <typename T> struct Pack2;
+template <> struct Pack2<__half> {
+    typedef __half2 type;
+    static __device__ __forceinline__ __half2 splat(float w) { return __float2half2_rn(w); }
+    static __device__ __forceinline__ float2 to_f2(__half2 v) { return __half22float2(v); }
+    static __device__ __forceinline__ __half2 from_f2(float2 v) { return __float22half2_rn(v); }
+};
+template <> struct Pack2<__nv_bfloat16> {
+    typedef __nv_bfloat162 type;
+    static __device__ __forceinline__ __nv_bfloat162 splat(float w) { return __float2bfloat162_rn(w); }
+    static __device__ __forceinline__ float2 to_f2(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+    static __device__ __forceinline__ __nv_bfloat162 from_f2(float2 v) { return __float22bfloat162_rn(v); }
+};
+
+template <typename T, int CPT>
+__global__ void __launch_bounds__(128)
+warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
+                         const float* __restrict__ depth, int per_pixel, T* __restrict__ var, int B, int CB, int D, int H,
+                         int W, int dper, int align_corners, int ref_sq_in_sum) {
+    typedef typename Pack2<T>::type T2;
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int nchunk = (D + dper - 1) / dper;
+    const int CG = CB / CPT;
+    int y = blockIdx.y;
+    const int dc = y % nchunk; y /= nchunk;
+    const int cg = y % CG;
+    const int b = y / CG;
+    const float fx = (float)(p % W), fy = (float)(p / W);
+    const int64_t plane = (int64_t)HW * 8;                       // elements per channel block of a map
+    const int64_t map_off = ((int64_t)b * CB + (int64_t)cg * CPT) * plane;
+
+    float2 r[CPT][4], r2[CPT][4];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ref + map_off + c * plane + (int64_t)p * 8));
+        const T2* h = reinterpret_cast<const T2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { r[c][j] = Pack2<T>::to_f2(h[j]); r2[c][j] = __fmul2_rn(r[c][j], r[c][j]); }
+    }
+    float ray[MVS_MAX_SRC][3], tr[MVS_MAX_SRC][3];
+#pragma unroll
+    for (int s = 0; s < MVS_MAX_SRC; ++s)
+        if (s < nsrc) {
+            const float* m = rt + ((int64_t)s * B + b) * 12;
+            pixel_ray(m, fx, fy, ray[s]);
+            tr[s][0] = __ldg(m + 9); tr[s][1] = __ldg(m + 10); tr[s][2] = __ldg(m + 11);
+        }
+    // ix = u * sx + ox : align_corners ? u : u * W/(W-1) - 0.5
+    const float sx = align_corners ? 1.f : (float)W / (float)(W - 1), sy = align_corners ? 1.f : (float)H / (float)(H - 1);
+    const float oxy = align_corners ? 0.f : -0.5f;
+    const float inv_n = 1.f / (float)(nsrc + 1);
+    const float2 inv_n2 = make_float2(inv_n, inv_n);
+
+    const int d_end = min(D, (dc + 1) * dper);
+    for (int d = dc * dper; d < d_end; ++d) {
+        const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+        float2 s1[CPT][4], s2[CPT][4];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[c][j] = ref_sq_in_sum ? r2[c][j] : r[c][j]; s2[c][j] = r2[c][j]; }
+#pragma unroll
+        for (int s = 0; s < MVS_MAX_SRC; ++s) {
+            if (s < nsrc) {
+                const float pz = ray[s][2] * dv + tr[s][2];
+                const float iz = 1.f / pz;                       // pz == 0 -> inf -> NaN/inf coordinates -> every tap rejected
+                const float ix = (ray[s][0] * dv + tr[s][0]) * iz * sx + oxy;
+                const float iy = (ray[s][1] * dv + tr[s][1]) * iz * sy + oxy;
+                const float x0 = floorf(ix), y0 = floorf(iy);
+                const float x1 = x0 + 1.f, y1 = y0 + 1.f;
+                const bool vx0 = (x0 >= 0.f) && (x0 <= (float)(W - 1)), vx1 = (x1 >= 0.f) && (x1 <= (float)(W - 1));
+                const bool vy0 = (y0 >= 0.f) && (y0 <= (float)(H - 1)), vy1 = (y1 >= 0.f) && (y1 <= (float)(H - 1));
+                const float wx0 = x1 - ix, wx1 = ix - x0, wy0 = y1 - iy, wy1 = iy - y0;
+                // invalid taps read pixel (clamped) with weight exactly 0, so there is no divergent load
+                const int xa = vx0 ? (int)x0 : 0, xb = vx1 ? (int)x1 : 0, ya = vy0 ? (int)y0 : 0, yb = vy1 ? (int)y1 : 0;
+                const int o0 = ya * W + xa, o1 = ya * W + xb, o2 = yb * W + xa, o3 = yb * W + xb;
+                const T2 w0 = Pack2<T>::splat((vx0 && vy0) ? wx0 * wy0 : 0.f), w1 = Pack2<T>::splat((vx1 && vy0) ? wx1 * wy0 : 0.f);
+                const T2 w2 = Pack2<T>::splat((vx0 && vy1) ? wx0 * wy1 : 0.f), w3 = Pack2<T>::splat((vx1 && vy1) ? wx1 * wy1 : 0.f);
+                const T* base = reinterpret_cast<const T*>(srcs.p[s]) + map_off;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const T* m = base + c * plane;
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)o0 * 8));
+                    const uint4 bq = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)o1 * 8));
+                    const uint4 cq = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)o2 * 8));
+                    const uint4 dq = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)o3 * 8));
+                    const T2* ha = reinterpret_cast<const T2*>(&a);
+                    const T2* hb = reinterpret_cast<const T2*>(&bq);
+                    const T2* hc = reinterpret_cast<const T2*>(&cq);
+                    const T2* hd = reinterpret_cast<const T2*>(&dq);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        T2 v = __hmul2(ha[j], w0);
+                        v = __hfma2(hb[j], w1, v);
+                        v = __hfma2(hc[j], w2, v);
+                        v = __hfma2(hd[j], w3, v);
+                        const float2 f = Pack2<T>::to_f2(v);
+                        s1[c][j] = __fadd2_rn(s1[c][j], f);
+                        s2[c][j] = __ffma2_rn(f, f, s2[c][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            uint4 out;
+            T2* ho = reinterpret_cast<T2*>(&out);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 m = __fmul2_rn(s1[c][j], inv_n2);
+                const float2 q = __fmul2_rn(s2[c][j], inv_n2);
+                ho[j] = Pack2<T>::from_f2(__ffma2_rn(make_float2(-m.x, -m.y), m, q));
+            }
+            *reinterpret_cast<uint4*>(var + ((((int64_t)b * CB + cg * CPT + c) * D + d) * HW + p) * 8) = out;
+        }
+    }
+}
+#endif  // !MVS_CPU_EMU
+
 static int depth_chunk(int D, int HW, int B, int CB) {
     // enough (pixel-tile x chunk) blocks for >= ~4 waves of 148 SMs x 8 resident blocks, chunks of >= 8 planes
     int dper = D;
@@ -245,6 +374,23 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     SrcPtrs sp;
     for (int s = 0; s < MVS_MAX_SRC; ++s) sp.p[s] = s < nsrc ? srcs[s] : nullptr;
     const int CB = C / 8, HW = H * W;
+#ifndef MVS_CPU_EMU
+    if (dtype_in == dtype_out && dtype_in != MVS_F32 && CB % 2 == 0) {
+        // 16-bit storage: packed-math kernel, CPT channel blocks per thread
+        static const int cpt_env = getenv("MVS_WARP_CPT") ? atoi(getenv("MVS_WARP_CPT")) : 0;
+        const int cpt = (cpt_env == 4 && CB % 4 == 0) ? 4 : 2;
+        const int dperf = depth_chunk(D, HW, B, CB / cpt);
+        const dim3 gridf(mvs_cdiv(HW, 128), (unsigned)(B * (CB / cpt) * ((D + dperf - 1) / dperf)));
+        if (dtype_in == MVS_F16) {
+            if (cpt == 4) warp_var_fwd_fast_kernel<__half, 4><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __half*)ref, sp, nsrc, rt, depth, per_pixel, (__half*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
+            else warp_var_fwd_fast_kernel<__half, 2><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __half*)ref, sp, nsrc, rt, depth, per_pixel, (__half*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
+        } else {
+            if (cpt == 4) warp_var_fwd_fast_kernel<__nv_bfloat16, 4><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)ref, sp, nsrc, rt, depth, per_pixel, (__nv_bfloat16*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
+            else warp_var_fwd_fast_kernel<__nv_bfloat16, 2><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)ref, sp, nsrc, rt, depth, per_pixel, (__nv_bfloat16*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
+        }
+        return MVS_CHECK_LAUNCH("mvs_warp_var_fwd");
+    }
+#endif
     const int dper = depth_chunk(D, HW, B, CB);
     const dim3 grid(mvs_cdiv(HW, 128), (unsigned)(B * CB * ((D + dper - 1) / dper)));
     MVS_DISPATCH_DTYPE(dtype_in, TI, MVS_DISPATCH_DTYPE(dtype_out, TO,
