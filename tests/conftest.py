@@ -83,6 +83,9 @@ def gpu():
         pytest.skip("no CUDA device")
     ssmvs_b200._lib.bind()
     assert not ssmvs_b200._lib.is_emulation()
+    # parity tests compare fp32 with fp32: keep the library (cuDNN / cuBLAS) parts of the models off TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return Backend("cuda:0")
 
 
