@@ -233,7 +233,12 @@ def main():
                 e = [mk() for _ in range(8)]
                 imgs = res["imgs"]
                 flush.zero_(); e[0].record(stream)
-                f = model.feature(imgs.transpose(0, 1).reshape(VIEWS, 3, HEIGHT, WIDTH))
+                xin = imgs.transpose(0, 1).reshape(VIEWS, 3, HEIGHT, WIDTH)
+                if dtype != torch.float32:   # same library path MVSNet.forward takes in eval mode
+                    with torch.autocast("cuda", dtype=dtype):
+                        f = model.feature(xin.contiguous(memory_format=torch.channels_last))
+                else:
+                    f = model.feature(xin)
                 feats = list(f.reshape(VIEWS, 1, CHANNELS, HF, WF).unbind(0))
                 e[1].record(stream)
                 rt = ops.compose_proj(res["proj_matrices"])

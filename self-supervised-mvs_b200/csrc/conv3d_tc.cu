@@ -1,40 +1,64 @@
-// conv3d_tc.cu — 3x3x3 stride-1 convolution as an implicit GEMM on the 5th-generation tensor cores (algo = 2).
+// conv3d_tc.cu — 3x3x3 (transposed) convolutions of the regularisation U-Nets as implicit GEMMs on the 5th-generation
+// tensor cores (algo = 2):
 //
-//   D[128 voxels x N couts] (fp32, TMEM)  +=  A[128 voxels x 16 cin] (smem)  .  B[N couts x 16 cin]^T (smem)
+//   D[128 positions x N] (fp32, TMEM)  +=  A[128 positions x 16 cin] (smem)  .  B[N x 16 cin]^T (smem)
 //
-// No im2col: a CTA owns a (16 or 8) x 30 output tile in (h, w) and marches along depth.  Every input plane of the tile
-// (with its 1-voxel halo, zero-filled by TMA outside the volume) is staged ONCE in shared memory as
-//     [cin block][row = hh * 32 + ww][8 cin]                      (hh < PH = TH + 2, ww < 32 = TW + 2)
-// which is exactly the canonical no-swizzle K-major UMMA operand with SBO = 128 B: rows are 16 bytes apart, so the A
-// operand of tap (kd, kh, kw) is the SAME buffer addressed at (plane + kd, row + kh * 32 + kw) — 27 descriptors
-// over one tile instead of 27 gathered copies.  Rows whose ww >= 30 (or hh >= TH) are junk outputs that are never stored.
-// The C8 activation layout makes the TMA box {32 w x 8 cin, PH, 1, 1} a run of 512-byte rows.
+// No im2col.  A CTA owns a (4 nM) x 30 tile of positions in (h, w) and marches along depth.  Every input plane of the tile
+// (with its halo, zero-filled by TMA outside the volume) is staged ONCE in shared memory as
+//     [cin block][row = hh * 32 + ww][8 cin]
+// which is the canonical no-swizzle K-major UMMA operand with SBO = 128 B: rows are 16 bytes apart, so the A operand of
+// a filter tap is the SAME buffer addressed at (plane slot, row + shift) — a list of shifted descriptors over one tile
+// instead of gathered copies.  The C8 activation layout makes the TMA box {32 w x 8 cin, PH, 1, 1} a run of 512-byte rows.
+// Rows with ww >= 30 or hh >= TH are junk accumulator rows that are never stored.
 //
-// Warp roles (224 threads): 0 = TMA producer of input planes (4-stage ring over depth), 1 = MMA issuer (one elected
-// lane) + TMEM owner, 2 = weight-tile loader (resident when the 27 tap tiles fit, else a ring streamed per plane),
-// 3..6 = epilogue (tcgen05.ld -> folded-BN affine, ReLU, skip add -> C8 store), double-buffered against the MMAs.
+// One kernel, three tap programs built on the host (struct Entry):
+//   S1  stride-1 Conv3d / ConvTranspose3d : slots = planes d-1, d, d+1; 27 entries (row shift kh*32+kw).
+//   S2  stride-2 Conv3d                   : the input is staged de-interleaved by (h, w) parity (4 strided tensor maps),
+//                                           so tap k reads parity (k != 1) at shift {0,1,1}[k]; two input planes per step.
+//   T2  stride-2 ConvTranspose3d          : positions are INPUT voxels; 4 accumulator groups = output (d, h) parities, the
+//                                           w parity is folded into N (= 2 Cout) so each lane stores two adjacent voxels.
+//   Cin = 8 layers pair two taps into one K = 16 step: the descriptor's LBO is the row distance between the two taps.
+//
+// Warp roles (224 threads): 0 = TMA producer of input planes (ring over depth), 1 = MMA issuer (one elected lane) +
+// TMEM owner, 2 = weight-tile loader (resident when all tiles fit, else a ring streamed per step), 3..6 = epilogue
+// (tcgen05.ld -> folded-BN affine, ReLU, skip add -> C8 store), double-buffered against the MMAs through TMEM.
 #include "mvs_rt.h"
 #include <cuda.h>
 
 namespace {
 
 constexpr int kThreads = 224;
-constexpr int kPW = 32;          // padded tile width (30 outputs + 2 halo columns)
+constexpr int kPW = 32;          // staged tile width (30 positions + halo)
 constexpr int kTW = 30;
-constexpr int kStages = 4;       // input-plane ring
 constexpr int kBStages = 4;      // weight-tile ring (streaming mode)
+constexpr int kMaxStages = 6;    // input-slot ring
+constexpr int kMaxEntries = 27;
 constexpr int kSmemLimit = 227 * 1024;
+enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2 };
+
+struct Entry {
+    int16_t row_shift;     // rows added to the A start address
+    uint16_t lbo_rows;     // 0: K halves are consecutive cin blocks (LBO = chunk stride); else paired taps, LBO = rows * 16 B
+    uint8_t slot_off;      // input slot relative to the first live slot of the step
+    uint8_t sub;           // parity sub-plane (S2)
+    uint8_t group;         // accumulator group (T2: output (d, h) parity)
+    uint8_t first;         // first entry of its group: overwrite instead of accumulate
+};
 
 struct TcParams {
-    const void* w;        // [27][CiB][N][8] storage dtype
-    const float* scale;   // [Cout] or null
-    const float* shift;   // [Cout] or null
-    const void* skip;     // y's layout or null
+    const void* w;         // [entry][kchunk][N][8] storage dtype
+    const float* scale;    // [Cout] or null
+    const float* shift;    // [Cout] or null
+    const void* skip;      // y's layout or null
     void* y;
-    int B, CiB, Cout, N, D, H, W;
-    int TH, PH, nM, rows_alloc, nwt, nht, LD, nseg;
-    int b_resident, relu, flip, is_bf16;
-    uint32_t chunk_bytes, plane_bytes, btile_bytes, tmem_cols;
+    int mode, B, CiB, Cout, N, ksteps, kchunks;
+    int Di, Hi, Wi, Do, Ho, Wo;      // input / output grids
+    int Dt, Ht, Wt;                  // grid the tiles walk (S1/S2: output, T2: input)
+    int TH, PH, nM, nwt, nht, LD, nseg;
+    int nsub, stages, sps, live, groups, nentries;
+    int b_resident, relu, is_bf16;
+    uint32_t chunk_bytes, sub_bytes, slot_bytes, btile_bytes, tmem_cols;
+    Entry prog[kMaxEntries];
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -60,6 +84,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -91,21 +119,23 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);  // version = 1 (sm_100), layout = SWIZZLE_NONE
 }
 
+struct TensorMaps { CUtensorMap m[4]; };
+
 // ------------------------------------------------------------------------------------------------ kernel
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* planes = smem;
-    uint8_t* bsm = planes + (size_t)kStages * p.plane_bytes;
-    const uint32_t b_bytes = p.b_resident ? 27u * p.btile_bytes : (uint32_t)kBStages * p.btile_bytes;
+    uint8_t* slots = smem;
+    uint8_t* bsm = slots + (size_t)p.stages * p.slot_bytes;
+    const uint32_t b_bytes = p.b_resident ? (uint32_t)p.nentries * p.btile_bytes : (uint32_t)kBStages * p.btile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + b_bytes);
-    uint64_t* plane_full = bars;                  // [kStages]
-    uint64_t* plane_empty = bars + kStages;       // [kStages]
-    uint64_t* b_full = bars + 2 * kStages;        // [kBStages]
-    uint64_t* b_empty = b_full + kBStages;        // [kBStages]
-    uint64_t* acc_full = b_empty + kBStages;      // [2]
-    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint64_t* slot_full = bars;                    // [kMaxStages]
+    uint64_t* slot_empty = bars + kMaxStages;      // [kMaxStages]
+    uint64_t* b_full = bars + 2 * kMaxStages;      // [kBStages]
+    uint64_t* b_empty = b_full + kBStages;         // [kBStages]
+    uint64_t* acc_full = b_empty + kBStages;       // [2]
+    uint64_t* acc_empty = acc_full + 2;            // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,11 +145,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const int seg = t % p.nseg;
     const int b = t / p.nseg;
     const int w0 = wt * kTW, h0 = ht * p.TH, d0 = seg * p.LD;
-    const int nout = min(p.LD, p.D - d0);          // output planes of this CTA
-    const int nplanes = nout + 2;                  // input planes d0-1 .. d0+nout
+    const int nsteps = min(p.LD, p.Dt - d0);                   // depth steps of this CTA
+    const int nslots = (nsteps - 1) * p.sps + p.live;          // input slots it consumes
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(plane_full + i, 1); mbar_init(plane_empty + i, 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(slot_full + i, 1); mbar_init(slot_empty + i, 1); }
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,33 +165,37 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== input planes: one TMA box per cin block per plane =====================
+        // ===================== input slots: one TMA box per (sub-plane, cin block) =====================
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            for (int s = 0; s < p.nsub; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[s]) : "memory");
             const uint32_t box_bytes = (uint32_t)p.PH * kPW * 16u;
-            for (int j = 0; j < nplanes; ++j) {
-                const int s = j % kStages;
-                mbar_wait(plane_empty + s, ((j / kStages) & 1) ^ 1);
-                mbar_expect_tx(plane_full + s, box_bytes * (uint32_t)p.CiB);
-                for (int cb = 0; cb < p.CiB; ++cb)
-                    tma_load_4d(&tmap, plane_full + s, planes + (size_t)s * p.plane_bytes + (size_t)cb * p.chunk_bytes,
-                                (w0 - 1) * 8, h0 - 1, d0 - 1 + j, b * p.CiB + cb);
+            for (int j = 0; j < nslots; ++j) {
+                const int st = j % p.stages;
+                mbar_wait(slot_empty + st, ((j / p.stages) & 1) ^ 1);
+                mbar_expect_tx(slot_full + st, box_bytes * (uint32_t)(p.CiB * p.nsub));
+                uint8_t* dst = slots + (size_t)st * p.slot_bytes;
+                for (int s = 0; s < p.nsub; ++s)
+                    for (int cb = 0; cb < p.CiB; ++cb, dst += p.chunk_bytes) {
+                        if (p.mode == MODE_S1) tma_load_4d(&maps.m[0], slot_full + st, dst, (w0 - 1) * 8, h0 - 1, d0 - 1 + j, b * p.CiB + cb);
+                        else if (p.mode == MODE_T2) tma_load_4d(&maps.m[0], slot_full + st, dst, w0 * 8, h0, d0 + j, b * p.CiB + cb);
+                        else tma_load_5d(&maps.m[s], slot_full + st, dst, 0, w0 - 1, h0 - 1, 2 * d0 - 1 + j, b * p.CiB + cb);
+                    }
             }
         }
     } else if (warp == 2) {
-        // ===================== weight tap tiles =====================
+        // ===================== weight tiles (one per program entry) =====================
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
             if (p.b_resident) {
-                mbar_expect_tx(b_full, 27u * p.btile_bytes);
-                for (int tap = 0; tap < 27; ++tap) bulk_load(bsm + (size_t)tap * p.btile_bytes, wsrc + (size_t)tap * p.btile_bytes, p.btile_bytes, b_full);
+                mbar_expect_tx(b_full, (uint32_t)p.nentries * p.btile_bytes);
+                for (int e = 0; e < p.nentries; ++e) bulk_load(bsm + (size_t)e * p.btile_bytes, wsrc + (size_t)e * p.btile_bytes, p.btile_bytes, b_full);
             } else {
-                for (int i = 0, u = 0; i < nout; ++i)
-                    for (int tap = 0; tap < 27; ++tap, ++u) {
-                        const int s = u % kBStages;
-                        mbar_wait(b_empty + s, ((u / kBStages) & 1) ^ 1);
-                        mbar_expect_tx(b_full + s, p.btile_bytes);
-                        bulk_load(bsm + (size_t)s * p.btile_bytes, wsrc + (size_t)tap * p.btile_bytes, p.btile_bytes, b_full + s);
+                for (int i = 0, u = 0; i < nsteps; ++i)
+                    for (int e = 0; e < p.nentries; ++e, ++u) {
+                        const int st = u % kBStages;
+                        mbar_wait(b_empty + st, ((u / kBStages) & 1) ^ 1);
+                        mbar_expect_tx(b_full + st, p.btile_bytes);
+                        bulk_load(bsm + (size_t)st * p.btile_bytes, wsrc + (size_t)e * p.btile_bytes, p.btile_bytes, b_full + st);
                     }
             }
         }
@@ -171,39 +205,39 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             // instruction descriptor: D = f32, A/B = f16|bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t fmt = p.is_bf16 ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t planes_addr = smem_u32(planes), b_addr = smem_u32(bsm);
-            const int ksteps = p.CiB / 2;
+            const uint32_t slots_addr = smem_u32(slots), b_addr = smem_u32(bsm);
             if (p.b_resident) mbar_wait(b_full, 0);
-            for (int i = 0, u = 0; i < nout; ++i) {
+            for (int i = 0, u = 0; i < nsteps; ++i) {
                 const int buf = i & 1;
                 mbar_wait(acc_empty + buf, ((i >> 1) & 1) ^ 1);
-                for (int j = (i == 0 ? 0 : i + 2); j <= i + 2; ++j) mbar_wait(plane_full + (j % kStages), (j / kStages) & 1);
+                const int jlo = i * p.sps, jhi = jlo + p.live;             // live slots [jlo, jhi)
+                for (int j = (i == 0 ? 0 : jhi - p.sps); j < jhi; ++j) mbar_wait(slot_full + (j % p.stages), (j / p.stages) & 1);
                 tc_fence_after();
-                for (int tap = 0; tap < 27; ++tap, ++u) {
-                    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-                    // gather form: Conv3d reads x[o - 1 + k]; stride-1 ConvTranspose3d reads x[o + 1 - k]
-                    const int od = p.flip ? 2 - kd : kd, oh = p.flip ? 2 - kh : kh, ow = p.flip ? 2 - kw : kw;
+                for (int e = 0; e < p.nentries; ++e, ++u) {
+                    const Entry en = p.prog[e];
                     uint32_t btile;
                     if (p.b_resident) {
-                        btile = b_addr + (uint32_t)tap * p.btile_bytes;
+                        btile = b_addr + (uint32_t)e * p.btile_bytes;
                     } else {
-                        const int s = u % kBStages;
-                        mbar_wait(b_full + s, (u / kBStages) & 1);
+                        const int st = u % kBStages;
+                        mbar_wait(b_full + st, (u / kBStages) & 1);
                         tc_fence_after();
-                        btile = b_addr + (uint32_t)s * p.btile_bytes;
+                        btile = b_addr + (uint32_t)st * p.btile_bytes;
                     }
-                    const uint32_t a_plane = planes_addr + (uint32_t)((i + od) % kStages) * p.plane_bytes + (uint32_t)(oh * kPW + ow) * 16u;
+                    const uint32_t a_base = slots_addr + (uint32_t)((jlo + en.slot_off) % p.stages) * p.slot_bytes +
+                                            (uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16);
+                    const uint32_t a_lbo = en.lbo_rows ? (uint32_t)en.lbo_rows * 16u : p.chunk_bytes;
                     for (int m = 0; m < p.nM; ++m) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t ad = smem_desc(a_plane + (uint32_t)(2 * ks) * p.chunk_bytes + (uint32_t)m * 128u * 16u, p.chunk_bytes, 128u);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(((buf * p.groups + en.group) * p.nM + m) * p.N);
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
+                            const uint64_t ad = smem_desc(a_base + (uint32_t)(2 * ks) * p.chunk_bytes + (uint32_t)m * 128u * 16u, a_lbo, 128u);
                             const uint64_t bd = smem_desc(btile + (uint32_t)(2 * ks) * (uint32_t)p.N * 16u, (uint32_t)p.N * 16u, 128u);
-                            umma_f16(d_tmem, ad, bd, idesc, (tap | ks) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, ad, bd, idesc, (en.first && ks == 0) ? 0u : 1u);
                         }
                     }
                     if (!p.b_resident) umma_commit(b_empty + (u % kBStages));
                 }
-                umma_commit(plane_empty + (i % kStages));   // plane i is the oldest of the three: free once these MMAs retire
+                for (int j = jlo; j < jlo + p.sps; ++j) umma_commit(slot_empty + (j % p.stages));  // oldest slots retire with these MMAs
                 umma_commit(acc_full + buf);
             }
         }
@@ -211,54 +245,61 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         // ===================== epilogue: TMEM -> affine / ReLU / skip -> C8 store =====================
         const int quad = warp & 3;                 // TMEM lanes [32 quad, 32 quad + 32) belong to this warp
         const int CoB = (p.Cout + 7) / 8;
-        const int64_t HW = (int64_t)p.H * p.W;
-        for (int i = 0; i < nout; ++i) {
+        const int64_t HWo = (int64_t)p.Ho * p.Wo;
+        const int npw = p.mode == MODE_T2 ? 2 : 1;
+        for (int i = 0; i < nsteps; ++i) {
             const int buf = i & 1;
             mbar_wait(acc_full + buf, (i >> 1) & 1);
             tc_fence_after();
-            const int q = d0 + i;
-            for (int m = 0; m < p.nM; ++m) {
-                const int r = m * 128 + quad * 32 + lane;
-                const int hh = r >> 5, ww = r & 31;
-                const int h = h0 + hh, w = w0 + ww;
-                const bool valid = (hh < p.TH) && (ww < kTW) && (h < p.H) && (w < p.W);
-                for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N + c0), v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (!valid) continue;
-                    if (p.Cout == 1) {
-                        float o = __uint_as_float(v[0]);
-                        if (p.scale) o *= __ldg(p.scale);
-                        if (p.shift) o += __ldg(p.shift);
-                        if (p.relu) o = fmaxf(o, 0.f);
-                        const int64_t off = ((int64_t)b * p.D + q) * HW + (int64_t)h * p.W + w;
-                        if (p.skip) o += reinterpret_cast<const float*>(p.skip)[off];
-                        reinterpret_cast<float*>(p.y)[off] = o;
-                        continue;
-                    }
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int cb = c0 / 8 + half;
-                        if (cb >= CoB) break;
-                        float o[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int co = cb * 8 + k;
-                            float x = __uint_as_float(v[half * 8 + k]);
-                            if (p.scale) x *= __ldg(p.scale + co);
-                            if (p.shift) x += __ldg(p.shift + co);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            o[k] = x;
+            for (int g = 0; g < p.groups; ++g) {
+                for (int m = 0; m < p.nM; ++m) {
+                    const int r = m * 128 + quad * 32 + lane;
+                    const int hh = r >> 5, ww = r & 31;
+                    const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+                    int od, oh, ow;            // output voxel of column block 0
+                    if (p.mode == MODE_T2) { od = 2 * (d0 + i) + (g >> 1); oh = 2 * (h0 + hh) + (g & 1); ow = 2 * (w0 + ww); }
+                    else { od = d0 + i; oh = h0 + hh; ow = w0 + ww; }
+                    const uint32_t tcol = (uint32_t)(((buf * p.groups + g) * p.nM + m) * p.N);
+                    for (int c0 = 0; c0 < npw * p.Cout; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + tcol + (uint32_t)c0, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (!valid) continue;
+                        if (p.Cout == 1) {
+                            float o = __uint_as_float(v[0]);
+                            if (p.scale) o *= __ldg(p.scale);
+                            if (p.shift) o += __ldg(p.shift);
+                            if (p.relu) o = fmaxf(o, 0.f);
+                            const int64_t off = ((int64_t)b * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow;
+                            if (p.skip) o += reinterpret_cast<const float*>(p.skip)[off];
+                            reinterpret_cast<float*>(p.y)[off] = o;
+                            continue;
                         }
-                        const int64_t off = ((((int64_t)b * CoB + cb) * p.D + q) * HW + (int64_t)h * p.W + w) * 8;
-                        if (p.skip) {
-                            float sv[8];
-                            V8<T>::load(reinterpret_cast<const T*>(p.skip) + off, sv);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) o[k] += sv[k];
+                        for (int half = 0; half < 2; ++half) {
+                            const int col = c0 + half * 8;          // column of the accumulator row
+                            if (col >= npw * p.Cout) break;
+                            const int pw = col / p.Cout;              // T2: which of the two adjacent output voxels
+                            const int cb = (col - pw * p.Cout) / 8;   // output channel block
+                            float o[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int co = cb * 8 + k;
+                                float x = __uint_as_float(v[half * 8 + k]);
+                                if (p.scale) x *= __ldg(p.scale + co);
+                                if (p.shift) x += __ldg(p.shift + co);
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                o[k] = x;
+                            }
+                            const int64_t off = ((((int64_t)b * CoB + cb) * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow + pw) * 8;
+                            if (p.skip) {
+                                float sv[8];
+                                V8<T>::load(reinterpret_cast<const T*>(p.skip) + off, sv);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) o[k] += sv[k];
+                            }
+                            V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
                         }
-                        V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
                     }
                 }
             }
@@ -276,17 +317,30 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------ weights: G fp32 -> tap tiles
-// wtc[tap][cib][n][8] = G[tap][cib*8 + k][n]  (zero for n >= CoutPad)
+// ------------------------------------------------------------------------------------------------ weight tiles
+// One tile per program entry: wt[entry][kchunk][n][8].  `src` lists, per (entry, kchunk, column block of Cout), which
+// tap of the gather form G[27][Cin][CoutPad] (and which 8 input channels) it holds; -1 = zeros.
+struct TileSrc { int8_t tap[kMaxEntries][8][2]; int8_t cib[kMaxEntries][8]; };
+
 template <typename T>
-__global__ void pack_weight_tc_kernel(const float* __restrict__ g, T* __restrict__ w, int Cin, int CoutPad, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 27 * CiB * N
-    const int CiB = Cin / 8;
-    if (i >= 27 * CiB * N) return;
-    const int n = i % N, cib = (i / N) % CiB, tap = i / (N * CiB);
+__global__ void pack_tiles_kernel(const float* __restrict__ g, T* __restrict__ w, const __grid_constant__ TileSrc src, int nentries,
+                                  int kchunks, int N, int Cin, int Cout, int CoutPad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nentries * kchunks * N
+    if (i >= nentries * kchunks * N) return;
+    const int n = i % N, kc = (i / N) % kchunks, e = i / (N * kchunks);
+    const int pw = Cout > 1 ? n / Cout : 0;                // column block (T2 folds the w parity into N)
+    const int co = Cout > 1 ? n - pw * Cout : n;
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = n < CoutPad ? g[((int64_t)tap * Cin + cib * 8 + k) * CoutPad + n] : 0.f;
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (pw < 2 && co < Cout) {
+        const int tap = src.tap[e][kc][pw];
+        if (tap >= 0) {
+            const int ci0 = src.cib[e][kc] * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = g[((int64_t)tap * Cin + ci0 + k) * CoutPad + co];
+        }
+    }
     V8<T>::store(w + (int64_t)i * 8, v);
 }
 
@@ -305,89 +359,220 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-int n_pad(int cout) { return cout <= 16 ? 16 : (cout + 15) / 16 * 16; }
+// ------------------------------------------------------------------------------------------------ tap programs
+struct Plan { TcParams p; TileSrc src; size_t smem; };
+
+int mode_of(const mvs_conv3d_desc* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
+
+int n_of(const mvs_conv3d_desc* d) {
+    const int cols = (mode_of(d) == MODE_T2 ? 2 : 1) * d->Cout;
+    return cols <= 16 ? 16 : (cols + 15) / 16 * 16;
+}
+
+struct Tap { int slot, sub, shift, tap; };  // where a filter tap reads, and its index in the gather form
+
+// Build the entry list + weight-tile sources.  Returns the number of entries.
+int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
+    const int mode = mode_of(d);
+    const bool paired = d->Cin == 8;
+    memset(&src, -1, sizeof(src));
+    int ne = 0;
+    auto add = [&](int slot, int sub, int shift, int lbo_rows, int group, bool first) {
+        Entry& e = p.prog[ne];
+        e.row_shift = (int16_t)shift; e.lbo_rows = (uint16_t)lbo_rows; e.slot_off = (uint8_t)slot; e.sub = (uint8_t)sub;
+        e.group = (uint8_t)group; e.first = first ? 1 : 0;
+        return ne++;
+    };
+    if (mode == MODE_T2) {
+        // output parity 0 <- (offset 0, k = 1); parity 1 <- (offset 0, k = 2), (offset 1, k = 0)
+        const int noff[2] = {1, 2}, off[2][2] = {{0, 0}, {0, 1}}, kk[2][2] = {{1, 1}, {2, 0}};
+        for (int pd = 0; pd < 2; ++pd)
+            for (int ph = 0; ph < 2; ++ph) {
+                bool first = true;
+                for (int a = 0; a < noff[pd]; ++a)
+                    for (int c = 0; c < noff[ph]; ++c)
+                        for (int ow = 0; ow < 2; ++ow) {
+                            const int e = add(off[pd][a], 0, off[ph][c] * kPW + ow, 0, pd * 2 + ph, first);
+                            first = false;
+                            const int kd = kk[pd][a], kh = kk[ph][c];
+                            const int tap0 = ow == 0 ? (kd * 3 + kh) * 3 + 1 : -1;      // pw = 0: kw = 1 at offset 0 only
+                            const int tap1 = (kd * 3 + kh) * 3 + (ow == 0 ? 2 : 0);     // pw = 1: kw = 2 at offset 0, kw = 0 at offset 1
+                            for (int kc = 0; kc < d->Cin / 8; ++kc) { src.tap[e][kc][0] = (int8_t)tap0; src.tap[e][kc][1] = (int8_t)tap1; src.cib[e][kc] = (int8_t)kc; }
+                        }
+            }
+        return ne;
+    }
+    // S1 / S2: collect the 27 taps
+    Tap taps[27];
+    for (int tp = 0; tp < 27; ++tp) {
+        const int k[3] = {tp / 9, (tp / 3) % 3, tp % 3};
+        Tap& t = taps[tp];
+        t.tap = tp;
+        if (mode == MODE_S1) {
+            // gather form: Conv3d reads x[o - 1 + k]; stride-1 ConvTranspose3d reads x[o + 1 - k]
+            const int o[3] = {d->transposed ? 2 - k[0] : k[0], d->transposed ? 2 - k[1] : k[1], d->transposed ? 2 - k[2] : k[2]};
+            t.slot = o[0]; t.sub = 0; t.shift = o[1] * kPW + o[2];
+        } else {
+            // x[2o - 1 + k]: k = 1 -> even parity at index o (shift 1 from the tile origin o-1), k = 0 / 2 -> odd parity at o-1 / o
+            const int sh[3] = {0, 1, 1};
+            t.slot = k[0]; t.sub = (k[1] == 1 ? 0 : 1) * 2 + (k[2] == 1 ? 0 : 1); t.shift = sh[k[1]] * kPW + sh[k[2]];
+        }
+    }
+    if (!paired) {
+        for (int tp = 0; tp < 27; ++tp) {
+            const int e = add(taps[tp].slot, taps[tp].sub, taps[tp].shift, 0, 0, tp == 0);
+            for (int kc = 0; kc < d->Cin / 8; ++kc) { src.tap[e][kc][0] = (int8_t)tp; src.cib[e][kc] = (int8_t)kc; }
+        }
+        return ne;
+    }
+    // Cin = 8: two taps of the same (slot, sub-plane) share one K = 16 step; LBO = their row distance
+    bool used[27] = {false};
+    for (int a = 0; a < 27; ++a) {
+        if (used[a]) continue;
+        used[a] = true;
+        int best = -1;
+        for (int c = a + 1; c < 27; ++c)
+            if (!used[c] && taps[c].slot == taps[a].slot && taps[c].sub == taps[a].sub && taps[c].shift != taps[a].shift &&
+                (best < 0 || abs(taps[c].shift - taps[a].shift) < abs(taps[best].shift - taps[a].shift))) best = c;
+        int lo = a, hi = best;
+        if (best >= 0) { used[best] = true; if (taps[hi].shift < taps[lo].shift) { lo = best; hi = a; } }
+        int e;
+        if (best >= 0) {
+            e = add(taps[lo].slot, taps[lo].sub, taps[lo].shift, taps[hi].shift - taps[lo].shift, 0, ne == 0);
+            src.tap[e][0][0] = (int8_t)taps[lo].tap; src.tap[e][1][0] = (int8_t)taps[hi].tap;
+        } else if (taps[a].shift > 0) {   // lone tap: zero weights on the row before it
+            e = add(taps[a].slot, taps[a].sub, taps[a].shift - 1, 1, 0, ne == 0);
+            src.tap[e][1][0] = (int8_t)taps[a].tap;
+        } else {                           // lone tap at shift 0: zero weights on the row after it
+            e = add(taps[a].slot, taps[a].sub, 0, 1, 0, ne == 0);
+            src.tap[e][0][0] = (int8_t)taps[a].tap;
+        }
+        src.cib[e][0] = 0; src.cib[e][1] = 0;
+    }
+    return ne;
+}
+
+bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
+    TcParams& p = pl.p;
+    memset(&p, 0, sizeof(p));
+    p.mode = mode_of(d);
+    p.B = d->B; p.CiB = d->Cin / 8; p.Cout = d->Cout; p.N = n_of(d);
+    p.ksteps = d->Cin == 8 ? 1 : d->Cin / 16;
+    p.kchunks = 2 * p.ksteps;
+    p.Di = d->Din; p.Hi = d->Hin; p.Wi = d->Win; p.Do = d->Dout; p.Ho = d->Hout; p.Wo = d->Wout;
+    if (p.mode == MODE_T2) { p.Dt = p.Di; p.Ht = p.Hi; p.Wt = p.Wi; } else { p.Dt = p.Do; p.Ht = p.Ho; p.Wt = p.Wo; }
+    p.relu = d->relu; p.is_bf16 = d->dtype_in == MVS_BF16;
+    p.nsub = p.mode == MODE_S2 ? 4 : 1;
+    p.sps = p.mode == MODE_S2 ? 2 : 1;
+    p.live = p.mode == MODE_T2 ? 2 : 3;
+    p.groups = p.mode == MODE_T2 ? 4 : 1;
+    // ring depth = live slots + the slots of one step prefetched while the current step computes
+    p.stages = p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 5);
+    p.nentries = build_program(d, p, pl.src);
+    p.btile_bytes = (uint32_t)p.kchunks * p.N * 16;
+    int max_reach = 0;   // furthest row an A descriptor touches beyond its 128-row window
+    for (int e = 0; e < p.nentries; ++e) max_reach = max(max_reach, (int)p.prog[e].row_shift + (int)p.prog[e].lbo_rows);
+    const int halo = p.mode == MODE_S1 ? 2 : 1;
+    const uint32_t all_b = (uint32_t)p.nentries * p.btile_bytes;
+    for (int nM = 4; nM >= 1; --nM) {   // largest tile whose slot ring fits beside the weights, 2 accumulator sets in TMEM
+        if (2 * p.groups * nM * p.N > 512) continue;
+        p.nM = nM; p.TH = 4 * nM; p.PH = p.TH + halo;
+        const int rows = max(nM * 128 + max_reach + 1, p.PH * kPW);
+        p.chunk_bytes = (uint32_t)((rows + 7) / 8 * 8) * 16u;
+        p.sub_bytes = p.chunk_bytes * (uint32_t)p.CiB;
+        p.slot_bytes = p.sub_bytes * (uint32_t)p.nsub;
+        const size_t ring = (size_t)p.stages * p.slot_bytes;
+        for (int res = 1; res >= 0; --res) {
+            const size_t need = ring + (res ? all_b : (size_t)kBStages * p.btile_bytes) + 512;
+            if (need <= (size_t)kSmemLimit) { p.b_resident = res; pl.smem = need; goto fits; }
+        }
+    }
+    return false;
+fits:
+    uint32_t cols = 32;
+    while ((int)cols < 2 * p.groups * p.nM * p.N) cols <<= 1;
+    p.tmem_cols = cols;
+    p.nwt = (p.Wt + kTW - 1) / kTW;
+    p.nht = (p.Ht + p.TH - 1) / p.TH;
+    // depth segments: enough CTAs for >= ~3 waves of 148 SMs, but >= 8 steps each (halo slots are reloaded per segment)
+    const int64_t tiles = (int64_t)p.B * p.nwt * p.nht;
+    int LD = p.Dt;
+    while (LD > 8 && tiles * ((p.Dt + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
+    p.LD = LD; p.nseg = (p.Dt + LD - 1) / LD;
+    return tiles * p.nseg < (1ll << 31);
+}
 
 }  // namespace
 
 int mvs_conv3d_tc_supported(const mvs_conv3d_desc* d) {
-    if (d->stride != 1) return 0;
     if (d->dtype_in != MVS_F16 && d->dtype_in != MVS_BF16) return 0;
     if (d->Cout != 1 && d->dtype_out != d->dtype_in) return 0;
-    if (d->Cin % 16 != 0 || d->Cin > 64) return 0;
+    if (d->Cin != 8 && (d->Cin % 16 != 0 || d->Cin > 64)) return 0;
     if (d->Cout != 1 && (d->Cout % 8 != 0 || d->Cout > 64)) return 0;
+    if (mode_of(d) == MODE_T2 && (d->Cout == 1 || 2 * d->Cout > 64)) return 0;
+    if (mode_of(d) == MODE_S2 && ((d->Win & 1) || (d->Hin & 1) || (d->Din & 1))) return 0;
     return 1;
 }
 
 int64_t mvs_conv3d_tc_workspace_bytes(const mvs_conv3d_desc* d) {
     if (!mvs_conv3d_tc_supported(d)) return 0;
-    return (int64_t)27 * (d->Cin / 8) * n_pad(d->Cout) * 16;  // tap tiles [27][Cin/8][N][8] in the storage dtype
+    const int kchunks = d->Cin == 8 ? 2 : d->Cin / 8;
+    return (int64_t)kMaxEntries * kchunks * n_of(d) * 16;  // weight tiles [entry][kchunk][N][8] in the storage dtype
 }
 
 int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
                       const void* skip, void* y, void* ws, void* stream) {
     MVS_REQUIRE(mvs_conv3d_tc_supported(d), MVS_E_UNSUPPORTED,
-                "mvs_conv3d_fwd: tcgen05 path needs stride 1, fp16/bf16 storage, Cin in {16,32,48,64}, Cout in {1,8..64}");
+                "mvs_conv3d_fwd: tcgen05 path needs fp16/bf16 storage, Cin in {8,16,32,48,64}, Cout in {1,8..64} (<= 32 transposed stride 2)");
+    MVS_REQUIRE(ws, MVS_E_ARG, "mvs_conv3d_fwd: the tcgen05 path needs a workspace of mvs_conv3d_workspace_bytes() bytes");
     EncodeTiledFn enc = encode_tiled();
     MVS_REQUIRE(enc, MVS_E_LAUNCH, "mvs_conv3d_fwd: cuTensorMapEncodeTiled is not available from this driver");
-    const int N = n_pad(d->Cout), CiB = d->Cin / 8, CoutPad = (d->Cout + 7) / 8 * 8;
+    static thread_local Plan pl;
+    MVS_REQUIRE(make_plan(d, pl), MVS_E_UNSUPPORTED, "mvs_conv3d_fwd: no tcgen05 tiling fits shared memory for Cin=%d Cout=%d", d->Cin, d->Cout);
+    TcParams& p = pl.p;
+    p.w = ws; p.scale = scale; p.shift = shift; p.skip = skip; p.y = y;
     cudaStream_t st = (cudaStream_t)stream;
+    const int CoutPad = (d->Cout + 7) / 8 * 8;
 
-    // ---- tap tiles, re-packed from the gather form into the caller's workspace on every call
-    MVS_REQUIRE(ws, MVS_E_ARG, "mvs_conv3d_fwd: the tcgen05 path needs a workspace of mvs_conv3d_workspace_bytes() bytes");
-    void* wt = ws;
+    // ---- weight tiles, re-packed from the gather form into the caller's workspace on every call
     // (<= 110 K elements: negligible next to the convolution, and always coherent with in-place weight updates)
-    if (d->dtype_in == MVS_F16) pack_weight_tc_kernel<__half><<<mvs_cdiv(27 * CiB * N, 256), 256, 0, st>>>(g, (__half*)wt, d->Cin, CoutPad, N);
-    else pack_weight_tc_kernel<__nv_bfloat16><<<mvs_cdiv(27 * CiB * N, 256), 256, 0, st>>>(g, (__nv_bfloat16*)wt, d->Cin, CoutPad, N);
+    const int nvec = p.nentries * p.kchunks * p.N;
+    if (p.is_bf16) pack_tiles_kernel<__nv_bfloat16><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__nv_bfloat16*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
+    else pack_tiles_kernel<__half><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__half*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
 
-    // ---- tiling plan
-    TcParams p;
-    p.w = wt; p.scale = scale; p.shift = shift; p.skip = skip; p.y = y;
-    p.B = d->B; p.CiB = CiB; p.Cout = d->Cout; p.N = N; p.D = d->Din; p.H = d->Hin; p.W = d->Win;
-    p.relu = d->relu; p.flip = d->transposed; p.is_bf16 = d->dtype_in == MVS_BF16;
-    p.btile_bytes = (uint32_t)CiB * N * 16;
-    p.b_resident = 27u * p.btile_bytes <= 56u * 1024u;
-    const uint32_t b_bytes = p.b_resident ? 27u * p.btile_bytes : (uint32_t)kBStages * p.btile_bytes;
-    int nM = 4;
-    for (;; --nM) {  // largest M-tile count whose 4-stage plane ring fits beside the weights and 2 accumulator sets fit TMEM
-        p.nM = nM; p.TH = 4 * nM; p.PH = p.TH + 2;
-        p.rows_alloc = (nM * 128 + 2 * kPW + 2 + 7) / 8 * 8;
-        p.chunk_bytes = (uint32_t)p.rows_alloc * 16u;
-        p.plane_bytes = p.chunk_bytes * (uint32_t)CiB;
-        const size_t need = (size_t)kStages * p.plane_bytes + b_bytes + 256;
-        if ((need <= (size_t)kSmemLimit && 2 * nM * N <= 512) || nM == 1) break;
-    }
-    const size_t smem = (size_t)kStages * p.plane_bytes + b_bytes + 256;
-    MVS_REQUIRE(smem <= (size_t)kSmemLimit, MVS_E_UNSUPPORTED, "mvs_conv3d_fwd: tcgen05 tile does not fit shared memory (%zu bytes)", smem);
-    uint32_t cols = 32;
-    while ((int)cols < 2 * p.nM * N) cols <<= 1;
-    p.tmem_cols = cols;
-    p.nwt = (p.W + kTW - 1) / kTW;
-    p.nht = (p.H + p.TH - 1) / p.TH;
-    // depth segments: enough CTAs for >= ~3 waves of 148 SMs, but >= 8 planes each (2 halo planes per segment)
-    const int64_t tiles = (int64_t)p.B * p.nwt * p.nht;
-    int LD = p.D;
-    while (LD > 8 && tiles * ((p.D + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
-    p.LD = LD; p.nseg = (p.D + LD - 1) / LD;
-    const int64_t nblocks = tiles * p.nseg;
-    MVS_REQUIRE(nblocks < (1ll << 31), MVS_E_SHAPE, "mvs_conv3d_fwd: too many tiles");
-
-    // ---- tensor map over x: dims (innermost first) {W*8, H, D, B*CiB}, box {256, PH, 1, 1}, zero fill outside
-    CUtensorMap tmap;
-    const cuuint64_t gdim[4] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * CiB};
-    const cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)p.D * p.H * p.W * 16};
-    const cuuint32_t box[4] = {(cuuint32_t)kPW * 8, (cuuint32_t)p.PH, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult cr = enc(&tmap, p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim,
-                            gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_conv3d_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
-
-    if (p.is_bf16) {
-        cudaFuncSetAttribute(conv3d_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_tc_kernel<__nv_bfloat16><<<(unsigned)nblocks, kThreads, smem, st>>>(tmap, p);
+    // ---- tensor maps over x (zero fill outside the volume)
+    TensorMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const cuuint64_t W = p.Wi, H = p.Hi, D = p.Di, NB = (cuuint64_t)p.B * p.CiB;
+    if (p.mode != MODE_S2) {
+        // dims (innermost first) {W*8, H, D, B*CiB}, box {256, PH, 1, 1}
+        const cuuint64_t gdim[4] = {W * 8, H, D, NB};
+        const cuuint64_t gstr[3] = {W * 16, H * W * 16, D * H * W * 16};
+        const cuuint32_t box[4] = {(cuuint32_t)kPW * 8, (cuuint32_t)p.PH, 1, 1}, estr[4] = {1, 1, 1, 1};
+        const CUresult cr = enc(&maps.m[0], dt, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_conv3d_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
     } else {
-        cudaFuncSetAttribute(conv3d_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_tc_kernel<__half><<<(unsigned)nblocks, kThreads, smem, st>>>(tmap, p);
+        // one map per (h, w) parity: dims {8, W/2, H/2, D, B*CiB} with doubled h / w strides, box {8, 32, PH, 1, 1}
+        for (int s = 0; s < 4; ++s) {
+            const int ph = s >> 1, pw = s & 1;
+            const cuuint64_t gdim[5] = {8, W / 2, H / 2, D, NB};
+            const cuuint64_t gstr[4] = {32, 2 * W * 16, H * W * 16, D * H * W * 16};
+            const cuuint32_t box[5] = {8, (cuuint32_t)kPW, (cuuint32_t)p.PH, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+            void* base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(x)) + ((size_t)ph * W + pw) * 16;
+            const CUresult cr = enc(&maps.m[s], dt, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_conv3d_fwd: cuTensorMapEncodeTiled (parity %d) failed (%d)", s, (int)cr);
+        }
+    }
+    const unsigned nblocks = (unsigned)((int64_t)p.B * p.nwt * p.nht * p.nseg);
+    if (p.is_bf16) {
+        cudaFuncSetAttribute(conv3d_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        conv3d_tc_kernel<__nv_bfloat16><<<nblocks, kThreads, pl.smem, st>>>(maps, p);
+    } else {
+        cudaFuncSetAttribute(conv3d_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        conv3d_tc_kernel<__half><<<nblocks, kThreads, pl.smem, st>>>(maps, p);
     }
     return MVS_CHECK_LAUNCH("mvs_conv3d_fwd (tcgen05)");
 }

@@ -127,19 +127,26 @@ class MVSNet(nn.Module):
             self.refine_network = RefineNet()
         self.volume_dtype = volume_dtype
         self.align_corners = align_corners
+        self.feature_autocast = True   # eval + 16-bit volume: FeatureNet (library code) runs under torch.autocast
 
     def forward(self, imgs, proj_matrices, depth_values):
         assert imgs.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
         b, n = imgs.shape[0], imgs.shape[1]
         # step 1. feature extraction (library code).  In eval mode all views share one batched call; in training
         # each view is its own call, because BatchNorm2d statistics are per call in the reference (:115).
+        dt = torch.float32 if self.training else self.volume_dtype
         if self.training:
             features = [self.feature(imgs[:, v]) for v in range(n)]
         else:
-            f = self.feature(imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:]))
+            x = imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:])
+            if dt != torch.float32 and x.is_cuda and self.feature_autocast:
+                # the features are stored in `dt` by the sweep anyway: let the library run its tensor-core kernels
+                with torch.autocast("cuda", dtype=dt):
+                    f = self.feature(x.contiguous(memory_format=torch.channels_last))
+            else:
+                f = self.feature(x)
             features = list(f.reshape(n, b, *f.shape[1:]).unbind(0))
         # step 2. plane sweep: warp + variance, fused (:120-136)
-        dt = torch.float32 if self.training else self.volume_dtype
         rt = ops.compose_proj(proj_matrices)
         variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
         # step 3. regularisation (:139-141)
