@@ -19,18 +19,21 @@
 //                                           w parity is folded into N (= 2 Cout) so each lane stores two adjacent voxels.
 //   Cin = 8 layers pair two taps into one K = 16 step: the descriptor's LBO is the row distance between the two taps.
 //
-// Warp roles (224 threads): 0 = TMA producer of input planes (ring over depth), 1 = MMA issuer (one elected lane) +
-// TMEM owner, 2 = weight-tile loader (resident when all tiles fit, else a ring streamed per step), 3..6 = epilogue
-// (tcgen05.ld -> folded-BN affine, ReLU, skip add -> C8 store), double-buffered against the MMAs through TMEM.
+// Warp roles (320 threads): 0 = TMA producer of input planes (ring over depth); 1..4 = MMA issuers, one elected lane each,
+// issuer k owns the accumulators of M-tile k (these MMAs are only N = 16..64 wide, so ONE issuing thread is the
+// bottleneck: measured 225 cycles per MMA against ~36 cycles of operand reads) and warp 1 also owns TMEM; 5 = weight-tile
+// loader (resident when all tiles fit, else a ring streamed per step); 6..9 = epilogue (tcgen05.ld -> folded-BN affine,
+// ReLU, skip add -> C8 store), double-buffered against the MMAs through TMEM.
 #include "mvs_rt.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int kThreads = 224;
+constexpr int kThreads = 320;     // producer | 4 MMA issuers | weight loader | 4 epilogue warps
 constexpr int kPW = 32;          // staged tile width (30 positions + halo)
 constexpr int kTW = 30;
-constexpr int kBStages = 4;      // weight-tile ring (streaming mode)
+constexpr int kBStages = 16;     // max depth of the weight-tile ring (streaming mode; p.bstages are used)
 constexpr int kMaxStages = 6;    // input-slot ring
 constexpr int kMaxEntries = 27;
 constexpr int kSmemLimit = 227 * 1024;
@@ -55,7 +58,7 @@ struct TcParams {
     int Di, Hi, Wi, Do, Ho, Wo;      // input / output grids
     int Dt, Ht, Wt;                  // grid the tiles walk (S1/S2: output, T2: input)
     int TH, PH, nM, nwt, nht, LD, nseg;
-    int nsub, stages, sps, live, groups, nentries;
+    int nsub, stages, sps, live, groups, nentries, bstages;
     int b_resident, relu, is_bf16;
     uint32_t chunk_bytes, sub_bytes, slot_bytes, btile_bytes, tmem_cols;
     Entry prog[kMaxEntries];
@@ -112,12 +115,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row core matrices of 16-byte rows,
-// SBO = distance between 8-row groups, LBO = distance between the two 8-element K halves of one K=16 step.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);  // version = 1 (sm_100), layout = SWIZZLE_NONE
-}
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), no-swizzle K-major: 8-row core matrices of 16-byte rows;
+// lo word = start >> 4 | (LBO >> 4) << 16 with LBO = distance between the two 8-element K halves of one K = 16 step,
+// hi word = SBO >> 4 (distance between 8-row groups = 128 B) | version 1 (sm_100) at bit 46; layout type 0 = SWIZZLE_NONE.
+// They are assembled inline by the MMA issuers (one add per K step).
 
 struct TensorMaps { CUtensorMap m[4]; };
 
@@ -128,7 +129,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* slots = smem;
     uint8_t* bsm = slots + (size_t)p.stages * p.slot_bytes;
-    const uint32_t b_bytes = p.b_resident ? (uint32_t)p.nentries * p.btile_bytes : (uint32_t)kBStages * p.btile_bytes;
+    const uint32_t b_bytes = p.b_resident ? (uint32_t)p.nentries * p.btile_bytes : (uint32_t)p.bstages * p.btile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + b_bytes);
     uint64_t* slot_full = bars;                    // [kMaxStages]
     uint64_t* slot_empty = bars + kMaxStages;      // [kMaxStages]
@@ -149,9 +150,10 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     const int nslots = (nsteps - 1) * p.sps + p.live;          // input slots it consumes
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(slot_full + i, 1); mbar_init(slot_empty + i, 1); }
-        for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        // every issuer commits its own MMAs, so the barriers the MMAs release count one arrival per issuer
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(slot_full + i, 1); mbar_init(slot_empty + i, (uint32_t)p.nM); }
+        for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, (uint32_t)p.nM); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, (uint32_t)p.nM); mbar_init(acc_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -182,7 +184,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == 5) {
         // ===================== weight tiles (one per program entry) =====================
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
@@ -192,20 +194,24 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
             } else {
                 for (int i = 0, u = 0; i < nsteps; ++i)
                     for (int e = 0; e < p.nentries; ++e, ++u) {
-                        const int st = u % kBStages;
-                        mbar_wait(b_empty + st, ((u / kBStages) & 1) ^ 1);
+                        const int st = u % p.bstages;
+                        mbar_wait(b_empty + st, ((u / p.bstages) & 1) ^ 1);
                         mbar_expect_tx(b_full + st, p.btile_bytes);
                         bulk_load(bsm + (size_t)st * p.btile_bytes, wsrc + (size_t)e * p.btile_bytes, p.btile_bytes, b_full + st);
                     }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+    } else if (warp >= 1 && warp <= 4) {
+        // ===================== MMA issuers: issuer m accumulates M-tile m =====================
+        const int m = warp - 1;
+        if (lane == 0 && m < p.nM) {
             // instruction descriptor: D = f32, A/B = f16|bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t fmt = p.is_bf16 ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t slots_addr = smem_u32(slots), b_addr = smem_u32(bsm);
+            const uint32_t slots_addr = smem_u32(slots) + (uint32_t)m * 128u * 16u, b_addr = smem_u32(bsm);
+            // descriptor words: lo = start >> 4 | (LBO >> 4) << 16 ; hi = SBO >> 4 (128 B) | version 1 at bit 46
+            const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
+            const uint32_t a_kstep = (2u * p.chunk_bytes) >> 4, b_kstep = 2u * (uint32_t)p.N, b_lbo = (uint32_t)p.N << 16;
             if (p.b_resident) mbar_wait(b_full, 0);
             for (int i = 0, u = 0; i < nsteps; ++i) {
                 const int buf = i & 1;
@@ -213,29 +219,27 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 const int jlo = i * p.sps, jhi = jlo + p.live;             // live slots [jlo, jhi)
                 for (int j = (i == 0 ? 0 : jhi - p.sps); j < jhi; ++j) mbar_wait(slot_full + (j % p.stages), (j / p.stages) & 1);
                 tc_fence_after();
+                const uint32_t d_base = tmem_base + (uint32_t)((buf * p.groups * p.nM + m) * p.N);
                 for (int e = 0; e < p.nentries; ++e, ++u) {
                     const Entry en = p.prog[e];
                     uint32_t btile;
                     if (p.b_resident) {
                         btile = b_addr + (uint32_t)e * p.btile_bytes;
                     } else {
-                        const int st = u % kBStages;
-                        mbar_wait(b_full + st, (u / kBStages) & 1);
+                        const int st = u % p.bstages;
+                        mbar_wait(b_full + st, (u / p.bstages) & 1);
                         tc_fence_after();
                         btile = b_addr + (uint32_t)st * p.btile_bytes;
                     }
-                    const uint32_t a_base = slots_addr + (uint32_t)((jlo + en.slot_off) % p.stages) * p.slot_bytes +
+                    const uint32_t a_addr = slots_addr + (uint32_t)((jlo + en.slot_off) % p.stages) * p.slot_bytes +
                                             (uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16);
-                    const uint32_t a_lbo = en.lbo_rows ? (uint32_t)en.lbo_rows * 16u : p.chunk_bytes;
-                    for (int m = 0; m < p.nM; ++m) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(((buf * p.groups + en.group) * p.nM + m) * p.N);
-                        for (int ks = 0; ks < p.ksteps; ++ks) {
-                            const uint64_t ad = smem_desc(a_base + (uint32_t)(2 * ks) * p.chunk_bytes + (uint32_t)m * 128u * 16u, a_lbo, 128u);
-                            const uint64_t bd = smem_desc(btile + (uint32_t)(2 * ks) * (uint32_t)p.N * 16u, (uint32_t)p.N * 16u, 128u);
-                            umma_f16(d_tmem, ad, bd, idesc, (en.first && ks == 0) ? 0u : 1u);
-                        }
-                    }
-                    if (!p.b_resident) umma_commit(b_empty + (u % kBStages));
+                    uint32_t a_lo = (a_addr >> 4) | ((en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16);
+                    uint32_t b_lo = (btile >> 4) | b_lbo;
+                    const uint32_t d_tmem = d_base + (uint32_t)(en.group * p.nM * p.N);
+                    uint32_t acc = en.first ? 0u : 1u;
+                    for (int ks = 0; ks < p.ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
+                        umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
+                    if (!p.b_resident) umma_commit(b_empty + (u % p.bstages));
                 }
                 for (int j = jlo; j < jlo + p.sps; ++j) umma_commit(slot_empty + (j % p.stages));  // oldest slots retire with these MMAs
                 umma_commit(acc_full + buf);
@@ -243,7 +247,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         }
     } else {
         // ===================== epilogue: TMEM -> affine / ReLU / skip -> C8 store =====================
-        const int quad = warp & 3;                 // TMEM lanes [32 quad, 32 quad + 32) belong to this warp
+        const int quad = warp & 3;                 // warps 6..9 -> quads 2,3,0,1; TMEM lanes [32 quad, 32 quad + 32) belong to this warp
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
         const int npw = p.mode == MODE_T2 ? 2 : 1;
@@ -474,30 +478,38 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     for (int e = 0; e < p.nentries; ++e) max_reach = max(max_reach, (int)p.prog[e].row_shift + (int)p.prog[e].lbo_rows);
     const int halo = p.mode == MODE_S1 ? 2 : 1;
     const uint32_t all_b = (uint32_t)p.nentries * p.btile_bytes;
-    for (int nM = 4; nM >= 1; --nM) {   // largest tile whose slot ring fits beside the weights, 2 accumulator sets in TMEM
+    // largest tile (nM M-tiles of 128 rows = 4 nM x 30 positions) whose slot ring fits beside the weights with 2 accumulator
+    // sets in TMEM -- but small volumes take smaller tiles so that at least ~2 waves of CTAs exist
+    bool found = false;
+    const char* force = getenv("MVS_TC_NM");          // test knob: force the M-tile count (when it fits)
+    const int forced = force ? atoi(force) : 0;
+    for (int nM = 4; nM >= 1 && !found; --nM) {
         if (2 * p.groups * nM * p.N > 512) continue;
+        if (forced >= 1 && forced <= 4 && nM > forced) continue;
         p.nM = nM; p.TH = 4 * nM; p.PH = p.TH + halo;
         const int rows = max(nM * 128 + max_reach + 1, p.PH * kPW);
         p.chunk_bytes = (uint32_t)((rows + 7) / 8 * 8) * 16u;
         p.sub_bytes = p.chunk_bytes * (uint32_t)p.CiB;
         p.slot_bytes = p.sub_bytes * (uint32_t)p.nsub;
         const size_t ring = (size_t)p.stages * p.slot_bytes;
-        for (int res = 1; res >= 0; --res) {
-            const size_t need = ring + (res ? all_b : (size_t)kBStages * p.btile_bytes) + 512;
-            if (need <= (size_t)kSmemLimit) { p.b_resident = res; pl.smem = need; goto fits; }
-        }
+        const size_t room = ring + 512 <= (size_t)kSmemLimit ? (size_t)kSmemLimit - ring - 512 : 0;
+        if (room >= all_b) { p.b_resident = 1; p.bstages = 1; pl.smem = ring + all_b + 512; }
+        else if (room >= 4 * (size_t)p.btile_bytes) {
+            p.b_resident = 0; p.bstages = (int)min((size_t)kBStages, room / p.btile_bytes); pl.smem = ring + (size_t)p.bstages * p.btile_bytes + 512;
+        } else continue;
+        p.nwt = (p.Wt + kTW - 1) / kTW;
+        p.nht = (p.Ht + p.TH - 1) / p.TH;
+        const int64_t tiles_nm = (int64_t)p.B * p.nwt * p.nht;
+        found = nM == 1 || nM == forced || tiles_nm * ((p.Dt + 3) / 4) >= 2 * 148;
     }
-    return false;
-fits:
+    if (!found) return false;
     uint32_t cols = 32;
     while ((int)cols < 2 * p.groups * p.nM * p.N) cols <<= 1;
     p.tmem_cols = cols;
-    p.nwt = (p.Wt + kTW - 1) / kTW;
-    p.nht = (p.Ht + p.TH - 1) / p.TH;
-    // depth segments: enough CTAs for >= ~3 waves of 148 SMs, but >= 8 steps each (halo slots are reloaded per segment)
+    // depth segments: enough CTAs for >= ~3 waves of 148 SMs, but >= 4 steps each (halo slots are reloaded per segment)
     const int64_t tiles = (int64_t)p.B * p.nwt * p.nht;
     int LD = p.Dt;
-    while (LD > 8 && tiles * ((p.Dt + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
+    while (LD > 4 && tiles * ((p.Dt + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
     p.LD = LD; p.nseg = (p.Dt + LD - 1) / LD;
     return tiles * p.nseg < (1ll << 31);
 }

@@ -31,10 +31,14 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dtype,force_nm", [(torch.float16, 0), (torch.bfloat16, 0), (torch.float16, 4), (torch.float16, 2)])
 @pytest.mark.parametrize("cin,cout,stride,tr,shape", CASES)
-def test_tc_matches_simt_and_aten(gpu, cin, cout, stride, tr, shape, dtype):
+def test_tc_matches_simt_and_aten(gpu, monkeypatch, cin, cout, stride, tr, shape, dtype, force_nm):
     from ssmvs_b200 import ops
+    if force_nm:
+        monkeypatch.setenv("MVS_TC_NM", str(force_nm))     # library test knob: M-tiles per CTA (default: by volume size)
+    else:
+        monkeypatch.delenv("MVS_TC_NM", raising=False)
     torch.manual_seed(cin * 100 + cout + stride)
     b, d, h, w = shape
     dev = gpu.device
