@@ -246,8 +246,7 @@ def main():
                 flush.zero_(); e[0].record(stream)
                 xin = imgs.transpose(0, 1).reshape(VIEWS, 3, HEIGHT, WIDTH)
                 if dtype != torch.float32:   # same library path MVSNet.forward takes in eval mode
-                    with torch.autocast("cuda", dtype=dtype):
-                        f = model.feature(xin.contiguous(memory_format=torch.channels_last))
+                    f = model.feature.forward_folded(xin, dtype)
                 else:
                     f = model.feature(xin)
                 feats = list(f.reshape(VIEWS, 1, CHANNELS, HF, WF).unbind(0))

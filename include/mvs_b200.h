@@ -43,6 +43,8 @@ int mvs_is_emulation(void);
 /* ---- layout ------------------------------------------------------------------------------------------- */
 /* fp32 [B][C][S] (S = H*W or D*H*W) -> C8 [B][C/8][S][8] in `dtype`.  C % 8 == 0. */
 int mvs_pack_c8(const float* src, void* dst, int B, int C, int64_t S, int dtype, void* stream);
+/* channels-last [B][S][C] in `dtype` (the layout the library 2-D feature extractor emits) -> C8 [B][C/8][S][8], same dtype */
+int mvs_nhwc_to_c8(const void* src, void* dst, int B, int C, int64_t S, int dtype, void* stream);
 /* inverse of mvs_pack_c8 */
 int mvs_unpack_c8(const void* src, float* dst, int B, int C, int64_t S, int dtype, void* stream);
 

@@ -33,6 +33,7 @@ _SIGS = {
     "mvs_is_emulation": ([], _I),
     "mvs_pack_c8": ([_P, _P, _I, _I, _L, _I, _P], _I),
     "mvs_unpack_c8": ([_P, _P, _I, _I, _L, _I, _P], _I),
+    "mvs_nhwc_to_c8": ([_P, _P, _I, _I, _L, _I, _P], _I),
     "mvs_compose_proj": ([_P, _P, _I, _I, _P], _I),
     "mvs_compose_proj_ke": ([_P, _P, _P, _P, _F, _P, _I, _I, _P], _I),
     "mvs_homo_warp_fwd": ([_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),

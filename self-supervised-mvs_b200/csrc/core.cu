@@ -60,6 +60,28 @@ __global__ void unpack_c8_kernel(const T* __restrict__ src, float* __restrict__ 
     for (int k = 0; k < 8; ++k) p[(int64_t)k * S] = v[k];
 }
 
+// channels-last [B][S][C] (what the library feature extractor emits) -> C8 [B][C/8][S][8], same storage type: each
+// thread moves one 16/32-byte channel block, consecutive threads walk the channel blocks of one pixel (coalesced read).
+template <typename T>
+__global__ void nhwc_to_c8_kernel(const T* __restrict__ src, T* __restrict__ dst, int CB, int64_t S, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // i = (b * S + s) * CB + cb
+    if (i >= total) return;
+    const int cb = (int)(i % CB);
+    const int64_t bs = i / CB;
+    const int64_t s = bs % S, b = bs / S;
+    float v[8];
+    V8<T>::load(src + i * 8, v);
+    V8<T>::store(dst + ((b * CB + cb) * S + s) * 8, v);
+}
+
+extern "C" int mvs_nhwc_to_c8(const void* src, void* dst, int B, int C, int64_t S, int dtype, void* stream) {
+    MVS_REQUIRE(src && dst, MVS_E_ARG, "mvs_nhwc_to_c8: null pointer");
+    MVS_REQUIRE(B > 0 && C > 0 && S > 0 && C % 8 == 0, MVS_E_SHAPE, "mvs_nhwc_to_c8: C=%d must be a positive multiple of 8", C);
+    const int64_t total = (int64_t)B * S * (C / 8);
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(nhwc_to_c8_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, (const T*)src, (T*)dst, C / 8, S, total));
+    return MVS_CHECK_LAUNCH("mvs_nhwc_to_c8");
+}
+
 extern "C" int mvs_pack_c8(const float* src, void* dst, int B, int C, int64_t S, int dtype, void* stream) {
     MVS_REQUIRE(src && dst, MVS_E_ARG, "mvs_pack_c8: null pointer");
     MVS_REQUIRE(B > 0 && C > 0 && S > 0 && C % 8 == 0, MVS_E_SHAPE, "mvs_pack_c8: C=%d must be a positive multiple of 8", C);

@@ -38,6 +38,30 @@ class FeatureNet(nn.Module):
         x = self.conv4(self.conv3(self.conv2(x)))
         return self.feature(self.conv6(self.conv5(x)))
 
+    def forward_folded(self, x, dtype):
+        """Eval-mode fast path (library code): BatchNorm folded into the convolution weights, `dtype` channels-last
+        activations, so each layer is one cuDNN tensor-core convolution + ReLU.  Same arithmetic as forward() in eval
+        mode up to the rounding of `dtype`."""
+        key = (dtype, x.device)
+        sig = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        hit = getattr(self, "_folded", {}).get(key)
+        if hit is None or hit[0] != sig:
+            layers = []
+            for blk in (self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6):
+                scale, shift = ops.fold_bn(blk.bn)
+                w = (blk.conv.weight.detach().float() * scale.view(-1, 1, 1, 1)).to(dtype).contiguous(memory_format=torch.channels_last)
+                layers.append((w, shift.to(dtype), blk.conv.stride, blk.conv.padding, True))
+            layers.append((self.feature.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last),
+                           self.feature.bias.detach().to(dtype), self.feature.stride, self.feature.padding, False))
+            hit = (sig, layers)
+            self.__dict__.setdefault("_folded", {})[key] = hit
+        y = x.to(dtype).contiguous(memory_format=torch.channels_last)
+        for w, b, stride, pad, relu in hit[1]:
+            y = F.conv2d(y, w, b, stride, pad)
+            if relu:
+                y = F.relu_(y)
+        return y
+
 
 class CostRegNet(nn.Module):
     """jdacs/models/mvsnet.py:37-74.  forward takes the variance volume (C8 or [B,32,D,H,W]) and returns
@@ -141,8 +165,7 @@ class MVSNet(nn.Module):
             x = imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:])
             if dt != torch.float32 and x.is_cuda and self.feature_autocast:
                 # the features are stored in `dt` by the sweep anyway: let the library run its tensor-core kernels
-                with torch.autocast("cuda", dtype=dt):
-                    f = self.feature(x.contiguous(memory_format=torch.channels_last))
+                f = self.feature.forward_folded(x, dt)
             else:
                 f = self.feature(x)
             features = list(f.reshape(n, b, *f.shape[1:]).unbind(0))

@@ -23,7 +23,13 @@ def _f32c(t: Tensor) -> Tensor:
 
 # ------------------------------------------------------------------------------------------------ layout
 def pack_c8(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
-    """fp32 [B,C,*spatial] -> C8 [B,C/8,*spatial,8] in `dtype`."""
+    """[B,C,*spatial] -> C8 [B,C/8,*spatial,8] in `dtype` (from fp32 NCHW, or directly from a channels-last tensor of `dtype`)."""
+    if x.dim() == 4 and x.dtype == dtype and x.shape[1] % 8 == 0 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+        x = x.detach()
+        b, c, h, w = x.shape
+        out = torch.empty(b, c // 8, h, w, 8, dtype=dtype, device=x.device)
+        call("mvs_nhwc_to_c8", x, ptr(x), ptr(out), b, c, h * w, dtype_code(dtype))
+        return out
     x = _f32c(x)
     b, c = x.shape[0], x.shape[1]
     if c % 8:

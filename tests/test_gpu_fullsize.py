@@ -143,3 +143,23 @@ def test_mvsnet_half_precision_volume_within_north_star_tolerance(gpu):
         d16 = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])["depth"]
     assert torch.isfinite(d32).all() and d32.min() > 420 and d32.max() < 940
     assert ((d16 - d32).abs() / d32).max().item() < 1e-3
+
+
+def test_feature_net_folded_fast_path(gpu):
+    """Library-side eval fast path (BN folded, fp16 channels-last) against the plain fp32 FeatureNet, and its hand-off
+    to the sweep (channels-last -> C8 repack kernel)."""
+    from ssmvs_b200 import ops
+    from ssmvs_b200.jdacs.models.mvsnet import FeatureNet
+    torch.manual_seed(0)
+    net = FeatureNet().to(gpu.device).eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        x = torch.randn(3, 3, 128, 160, device=gpu.device)
+        want = net(x)
+        got = net.forward_folded(x, torch.float16)
+        assert got.dtype == torch.float16 and got.is_contiguous(memory_format=torch.channels_last)
+        assert (got.float() - want).abs().max().item() < 2e-2 * want.abs().max().item()
+        assert torch.equal(ops.unpack_c8(ops.pack_c8(got, torch.float16)), got.float())
