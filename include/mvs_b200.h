@@ -91,7 +91,7 @@ typedef struct {
     int transposed;        /* 0: Conv3d(k=3,pad=1,stride)   1: ConvTranspose3d(k=3,pad=1,stride,output_padding=stride-1) */
     int dtype_in, dtype_out;
     int relu;              /* apply ReLU after the affine */
-    int algo;              /* 0 auto, 1 SIMT fp32 direct, 2 tcgen05 implicit GEMM */
+    int algo;              /* 0 auto, 1 SIMT fp32 direct, 2 tcgen05 implicit GEMM, 3 tcgen05 with `ws` already packed by an earlier algo-2 call */
 } mvs_conv3d_desc;
 
 /* torch weight ([Cout][Cin][27] for Conv3d, [Cin][Cout][27] for ConvTranspose3d) -> gather form
@@ -103,8 +103,9 @@ int mvs_pack_conv3d_weight(const float* w, float* g, int Cin, int Cout, int tran
  * jdacs-ms/models/network.py:44-74. */
 int mvs_conv3d_fwd(const mvs_conv3d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
                    const void* skip, void* y, void* ws, void* stream);
-/* bytes of caller-owned scratch `ws` mvs_conv3d_fwd needs for this descriptor (0 for the SIMT path; the tcgen05
- * path re-packs the 27 weight tap tiles into it on every call, so in-place weight updates are always seen). */
+/* bytes of caller-owned scratch `ws` mvs_conv3d_fwd needs for this descriptor (0 for the SIMT path).  The tcgen05
+ * path packs the weight tap tiles into it (algo 0 / 2); the tiles depend only on g, Cin, Cout, stride, transposed and
+ * the storage dtype, so a caller with frozen weights may keep `ws` and pass algo = 3 to skip the re-pack. */
 int64_t mvs_conv3d_workspace_bytes(const mvs_conv3d_desc* d);
 /* training: gradient w.r.t. the torch-layout weight ([Cout][Cin][27] or, transposed, [Cin][Cout][27]; zero-initialised
  * by the caller).  x: C8 volume (dtype_in), grad_y: C8 fp32 volume of the un-activated convolution output.

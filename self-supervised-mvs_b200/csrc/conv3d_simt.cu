@@ -148,7 +148,7 @@ int64_t mvs_conv3d_tc_workspace_bytes(const mvs_conv3d_desc* d);
 
 extern "C" int64_t mvs_conv3d_workspace_bytes(const mvs_conv3d_desc* d) {
 #ifndef MVS_CPU_EMU
-    if (d && (d->algo == 2 || d->algo == 0)) return mvs_conv3d_tc_workspace_bytes(d);
+    if (d && d->algo != 1) return mvs_conv3d_tc_workspace_bytes(d);
 #endif
     (void)d;
     return 0;
@@ -159,12 +159,12 @@ extern "C" int mvs_conv3d_fwd(const mvs_conv3d_desc* d, const void* x, const flo
     int rc = check_conv_desc(d, "mvs_conv3d_fwd");
     if (rc) return rc;
     MVS_REQUIRE(x && g && y, MVS_E_ARG, "mvs_conv3d_fwd: null pointer");
-    MVS_REQUIRE(d->algo >= 0 && d->algo <= 2, MVS_E_ARG, "mvs_conv3d_fwd: unknown algo %d", d->algo);
+    MVS_REQUIRE(d->algo >= 0 && d->algo <= 3, MVS_E_ARG, "mvs_conv3d_fwd: unknown algo %d", d->algo);
     MVS_REQUIRE(d->Cout != 1 || d->dtype_out == MVS_F32, MVS_E_ARG, "mvs_conv3d_fwd: single-channel output is plain fp32");
 #ifndef MVS_CPU_EMU
-    if (d->algo == 2 || (d->algo == 0 && mvs_conv3d_tc_supported(d))) return mvs_conv3d_fwd_tc(d, x, g, scale, shift, skip, y, ws, stream);
+    if (d->algo >= 2 || (d->algo == 0 && mvs_conv3d_tc_supported(d))) return mvs_conv3d_fwd_tc(d, x, g, scale, shift, skip, y, ws, stream);
 #else
-    MVS_REQUIRE(d->algo != 2, MVS_E_UNSUPPORTED, "mvs_conv3d_fwd: the tcgen05 path does not exist in the emulation build");
+    MVS_REQUIRE(d->algo < 2, MVS_E_UNSUPPORTED, "mvs_conv3d_fwd: the tcgen05 path does not exist in the emulation build");
 #endif
     const int64_t Vout = (int64_t)d->Dout * d->Hout * d->Wout;
     const int CoB = ((d->Cout + 7) / 8);

@@ -546,10 +546,11 @@ int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, c
     cudaStream_t st = (cudaStream_t)stream;
     const int CoutPad = (d->Cout + 7) / 8 * 8;
 
-    // ---- weight tiles, re-packed from the gather form into the caller's workspace on every call
-    // (<= 110 K elements: negligible next to the convolution, and always coherent with in-place weight updates)
+    // ---- weight tiles, packed from the gather form into the caller's workspace (skipped when algo = 3 says they are there)
     const int nvec = p.nentries * p.kchunks * p.N;
-    if (p.is_bf16) pack_tiles_kernel<__nv_bfloat16><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__nv_bfloat16*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
+    if (d->algo == 3) {
+        // the caller kept the tiles of a frozen weight from an earlier algo = 2 call on the same workspace
+    } else if (p.is_bf16) pack_tiles_kernel<__nv_bfloat16><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__nv_bfloat16*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
     else pack_tiles_kernel<__half><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__half*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
 
     // ---- tensor maps over x (zero fill outside the volume)

@@ -185,7 +185,8 @@ def _desc(x: Tensor, cout: int, stride: int, transposed: bool, out_dtype: torch.
 
 def conv3d_raw(x: Tensor, g: Tensor, cout: int, stride: int = 1, transposed: bool = False,
                scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, skip: Optional[Tensor] = None,
-               relu: bool = False, out_dtype: Optional[torch.dtype] = None, algo: int = 0) -> Tensor:
+               relu: bool = False, out_dtype: Optional[torch.dtype] = None, algo: int = 0,
+               tile_cache: Optional[dict] = None) -> Tensor:
     """y = [relu](conv(x) * scale + shift) + skip on C8 volumes (no autograd).  cout == 1 gives plain fp32 [B,D,H,W]."""
     x = x.contiguous()
     out_dtype = torch.float32 if cout == 1 else (out_dtype or x.dtype)
@@ -199,7 +200,19 @@ def conv3d_raw(x: Tensor, g: Tensor, cout: int, stride: int = 1, transposed: boo
         if skip.shape != y.shape or skip.dtype != y.dtype:
             raise ValueError("skip tensor must match the output (%s %s vs %s %s)" % (tuple(skip.shape), skip.dtype, tuple(y.shape), y.dtype))
     nws = _lib.lib().mvs_conv3d_workspace_bytes(C.byref(d))
-    ws = torch.empty(nws, dtype=torch.uint8, device=x.device) if nws > 0 else None
+    ws = None
+    if nws > 0:
+        # tcgen05 path: weight tap tiles live in a workspace; with frozen weights (tile_cache) they are packed once
+        key = (g.data_ptr(), g._version, d.dtype_in, stride, int(transposed), str(x.device))
+        ws = tile_cache.get(key) if tile_cache is not None else None
+        if ws is not None:
+            d.algo = 3
+        else:
+            ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+            if tile_cache is not None:
+                if len(tile_cache) > 256:
+                    tile_cache.clear()
+                tile_cache[key] = ws
     call("mvs_conv3d_fwd", x, C.byref(d), ptr(x), ptr(g), ptr(scale), ptr(shift), ptr(skip), ptr(y), ptr(ws))
     return y
 

@@ -24,6 +24,7 @@ class PackCache:
 
     def __init__(self) -> None:
         self._store: Dict[Tuple, Tuple] = {}
+        self.tiles: Dict[Tuple, Tensor] = {}   # tcgen05 weight tap tiles, keyed by the packed weight (ops.conv3d_raw)
 
     @staticmethod
     def _key(*tensors: Tensor) -> Tuple:
@@ -38,6 +39,7 @@ class PackCache:
                 self._store.clear()
             hit = (ver, ops.pack_conv3d_weight(weight, transposed))
             self._store[k] = hit
+            self.tiles.clear()   # a repacked weight may land on a recycled address: never trust old tap tiles
         return hit[1]
 
     def folded(self, bn: nn.modules.batchnorm._BatchNorm) -> Tuple[Tensor, Tensor]:
@@ -61,7 +63,7 @@ def conv_bn_relu(x: Tensor, conv: nn.Module, bn: nn.modules.batchnorm._BatchNorm
         return ops.bn_act_train(z, bn, skip, True)
     scale, shift = cache.folded(bn)
     return ops.conv3d_raw(x, cache.packed(conv.weight, transposed), cout, stride, transposed, scale, shift, skip,
-                          relu=True, algo=algo)
+                          relu=True, algo=algo, tile_cache=cache.tiles)
 
 
 def conv_bias(x: Tensor, conv: nn.Conv3d, training: bool, cache: PackCache, algo: int = 0) -> Tensor:
@@ -70,7 +72,7 @@ def conv_bias(x: Tensor, conv: nn.Conv3d, training: bool, cache: PackCache, algo
         return ops.conv3d(x, conv.weight, conv.bias, 1, False)
     bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
     return ops.conv3d_raw(x, cache.packed(conv.weight, False), conv.out_channels, 1, False, None, bias, None, relu=False,
-                          algo=algo)
+                          algo=algo, tile_cache=cache.tiles)
 
 
 def as_c8(x: Tensor, dtype: torch.dtype) -> Tensor:
