@@ -11,12 +11,15 @@
 // instead of gathered copies.  The C8 activation layout makes the TMA box {32 w x 8 cin, PH, 1, 1} a run of 512-byte rows.
 // Rows with ww >= 30 or hh >= TH are junk accumulator rows that are never stored.
 //
-// One kernel, three tap programs built on the host (struct Entry):
-//   S1  stride-1 Conv3d / ConvTranspose3d : slots = planes d-1, d, d+1; 27 entries (row shift kh*32+kw).
+// A tcgen05.mma costs ~100 cycles of A-operand fetch per 128 x 16 tile whatever N is (measured: N = 16 and N = 32 take the
+// same time, and the kernel time is #MMAs x ~97 cycles), so filter taps that read the SAME A rows are folded into N:
+// one kernel, three tap programs built on the host (struct Entry), each MMA writing `nblk` column blocks of Cout:
+//   S1  stride-1 Conv3d / ConvTranspose3d : slots = planes d-1, d, d+1; 9 entries (kd, kh) with row shift kh*32; the three
+//                                           kw taps are the 3 column blocks and the epilogue adds lanes l, l+1, l+2 (shuffles).
 //   S2  stride-2 Conv3d                   : the input is staged de-interleaved by (h, w) parity (4 strided tensor maps),
-//                                           so tap k reads parity (k != 1) at shift {0,1,1}[k]; two input planes per step.
-//   T2  stride-2 ConvTranspose3d          : positions are INPUT voxels; 4 accumulator groups = output (d, h) parities, the
-//                                           w parity is folded into N (= 2 Cout) so each lane stores two adjacent voxels.
+//                                           so tap k reads parity (k != 1) at shift {0,1,1}[k]; 27 entries, one block.
+//   T2  stride-2 ConvTranspose3d          : positions are INPUT voxels; 8 entries = input offsets (od, oh, ow) in {0,1}^3 and
+//                                           8 column blocks = output parities, so each lane stores a 2x2x2 block of voxels.
 //   Cin = 8 layers pair two taps into one K = 16 step: the descriptor's LBO is the row distance between the two taps.
 //
 // Warp roles (320 threads): 0 = TMA producer of input planes (ring over depth); 1..4 = MMA issuers, one elected lane each,
@@ -44,7 +47,7 @@ struct Entry {
     uint16_t lbo_rows;     // 0: K halves are consecutive cin blocks (LBO = chunk stride); else paired taps, LBO = rows * 16 B
     uint8_t slot_off;      // input slot relative to the first live slot of the step
     uint8_t sub;           // parity sub-plane (S2)
-    uint8_t group;         // accumulator group (T2: output (d, h) parity)
+    uint8_t group;         // accumulator group (always 0 now: parities are column blocks)
     uint8_t first;         // first entry of its group: overwrite instead of accumulate
 };
 
@@ -54,7 +57,7 @@ struct TcParams {
     const float* shift;    // [Cout] or null
     const void* skip;      // y's layout or null
     void* y;
-    int mode, B, CiB, Cout, N, ksteps, kchunks;
+    int mode, B, CiB, Cout, CoP, nblk, N, ksteps, kchunks;   // CoP = columns per block, nblk blocks folded into N
     int Di, Hi, Wi, Do, Ho, Wo;      // input / output grids
     int Dt, Ht, Wt;                  // grid the tiles walk (S1/S2: output, T2: input)
     int TH, PH, nM, nwt, nht, LD, nseg;
@@ -110,6 +113,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -250,60 +258,70 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         const int quad = warp & 3;                 // warps 6..9 -> quads 2,3,0,1; TMEM lanes [32 quad, 32 quad + 32) belong to this warp
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
-        const int npw = p.mode == MODE_T2 ? 2 : 1;
+        const bool kwfold = p.mode == MODE_S1;
+        const int nov = p.mode == MODE_T2 ? 8 : 1;  // output voxels per accumulator row
         for (int i = 0; i < nsteps; ++i) {
             const int buf = i & 1;
             mbar_wait(acc_full + buf, (i >> 1) & 1);
             tc_fence_after();
-            for (int g = 0; g < p.groups; ++g) {
-                for (int m = 0; m < p.nM; ++m) {
-                    const int r = m * 128 + quad * 32 + lane;
-                    const int hh = r >> 5, ww = r & 31;
-                    const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
-                    int od, oh, ow;            // output voxel of column block 0
-                    if (p.mode == MODE_T2) { od = 2 * (d0 + i) + (g >> 1); oh = 2 * (h0 + hh) + (g & 1); ow = 2 * (w0 + ww); }
-                    else { od = d0 + i; oh = h0 + hh; ow = w0 + ww; }
-                    const uint32_t tcol = (uint32_t)(((buf * p.groups + g) * p.nM + m) * p.N);
-                    for (int c0 = 0; c0 < npw * p.Cout; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + tcol + (uint32_t)c0, v);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int m = 0; m < p.nM; ++m) {
+                const int r = m * 128 + quad * 32 + lane;
+                const int hh = r >> 5, ww = r & 31;     // a warp is one h-row of the tile: lane = w position
+                const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N);
+                for (int cb = 0; cb < CoB; ++cb) {
+                    for (int ov = 0; ov < nov; ++ov) {
+                        float o[8];
+                        if (kwfold) {
+                            // blocks 0,1,2 hold the taps that read input column (lane), for outputs lane, lane-1, lane-2:
+                            // output column j = block0[j] + block1[j+1] + block2[j+2]
+                            uint32_t v0[8], v1[8], v2[8];
+                            tmem_ld8(trow + (uint32_t)(cb * 8), v0);
+                            tmem_ld8(trow + (uint32_t)(p.CoP + cb * 8), v1);
+                            tmem_ld8(trow + (uint32_t)(2 * p.CoP + cb * 8), v2);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                o[k] = __uint_as_float(v0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1) +
+                                       __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2);
+                        } else {
+                            uint32_t v0[8];
+                            tmem_ld8(trow + (uint32_t)(ov * p.CoP + cb * 8), v0);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v0[k]);
+                        }
                         if (!valid) continue;
+                        int od, oh, ow;
+                        if (p.mode == MODE_T2) { od = 2 * (d0 + i) + (ov >> 2); oh = 2 * (h0 + hh) + ((ov >> 1) & 1); ow = 2 * (w0 + ww) + (ov & 1); }
+                        else { od = d0 + i; oh = h0 + hh; ow = w0 + ww; }
                         if (p.Cout == 1) {
-                            float o = __uint_as_float(v[0]);
-                            if (p.scale) o *= __ldg(p.scale);
-                            if (p.shift) o += __ldg(p.shift);
-                            if (p.relu) o = fmaxf(o, 0.f);
+                            float x = o[0];
+                            if (p.scale) x *= __ldg(p.scale);
+                            if (p.shift) x += __ldg(p.shift);
+                            if (p.relu) x = fmaxf(x, 0.f);
                             const int64_t off = ((int64_t)b * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow;
-                            if (p.skip) o += reinterpret_cast<const float*>(p.skip)[off];
-                            reinterpret_cast<float*>(p.y)[off] = o;
+                            if (p.skip) x += reinterpret_cast<const float*>(p.skip)[off];
+                            reinterpret_cast<float*>(p.y)[off] = x;
                             continue;
                         }
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const int col = c0 + half * 8;          // column of the accumulator row
-                            if (col >= npw * p.Cout) break;
-                            const int pw = col / p.Cout;              // T2: which of the two adjacent output voxels
-                            const int cb = (col - pw * p.Cout) / 8;   // output channel block
-                            float o[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int co = cb * 8 + k;
-                                float x = __uint_as_float(v[half * 8 + k]);
-                                if (p.scale) x *= __ldg(p.scale + co);
-                                if (p.shift) x += __ldg(p.shift + co);
-                                if (p.relu) x = fmaxf(x, 0.f);
-                                o[k] = x;
-                            }
-                            const int64_t off = ((((int64_t)b * CoB + cb) * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow + pw) * 8;
-                            if (p.skip) {
-                                float sv[8];
-                                V8<T>::load(reinterpret_cast<const T*>(p.skip) + off, sv);
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) o[k] += sv[k];
-                            }
-                            V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
+                        for (int k = 0; k < 8; ++k) {
+                            const int co = cb * 8 + k;
+                            float x = o[k];
+                            if (p.scale) x *= __ldg(p.scale + co);
+                            if (p.shift) x += __ldg(p.shift + co);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            o[k] = x;
                         }
+                        const int64_t off = ((((int64_t)b * CoB + cb) * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow) * 8;
+                        if (p.skip) {
+                            float sv[8];
+                            V8<T>::load(reinterpret_cast<const T*>(p.skip) + off, sv);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) o[k] += sv[k];
+                        }
+                        V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
                     }
                 }
             }
@@ -322,23 +340,22 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ weight tiles
-// One tile per program entry: wt[entry][kchunk][n][8].  `src` lists, per (entry, kchunk, column block of Cout), which
-// tap of the gather form G[27][Cin][CoutPad] (and which 8 input channels) it holds; -1 = zeros.
-struct TileSrc { int8_t tap[kMaxEntries][8][2]; int8_t cib[kMaxEntries][8]; };
+// One tile per program entry: wt[entry][kchunk][n][8], n = block * CoP + co.  `src` lists, per (entry, kchunk, column
+// block), which tap of the gather form G[27][Cin][CoutPad] (and which 8 input channels) it holds; -1 = zeros.
+struct TileSrc { int8_t tap[kMaxEntries][8][8]; int8_t cib[kMaxEntries][8]; };
 
 template <typename T>
 __global__ void pack_tiles_kernel(const float* __restrict__ g, T* __restrict__ w, const __grid_constant__ TileSrc src, int nentries,
-                                  int kchunks, int N, int Cin, int Cout, int CoutPad) {
+                                  int kchunks, int N, int Cin, int Cout, int CoutPad, int CoP, int nblk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over nentries * kchunks * N
     if (i >= nentries * kchunks * N) return;
     const int n = i % N, kc = (i / N) % kchunks, e = i / (N * kchunks);
-    const int pw = Cout > 1 ? n / Cout : 0;                // column block (T2 folds the w parity into N)
-    const int co = Cout > 1 ? n - pw * Cout : n;
+    const int blk = n / CoP, co = n % CoP;
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = 0.f;
-    if (pw < 2 && co < Cout) {
-        const int tap = src.tap[e][kc][pw];
+    if (blk < nblk && co < Cout) {
+        const int tap = src.tap[e][kc][blk];
         if (tap >= 0) {
             const int ci0 = src.cib[e][kc] * 8;
 #pragma unroll
@@ -368,88 +385,85 @@ struct Plan { TcParams p; TileSrc src; size_t smem; };
 
 int mode_of(const mvs_conv3d_desc* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
 
-int n_of(const mvs_conv3d_desc* d) {
-    const int cols = (mode_of(d) == MODE_T2 ? 2 : 1) * d->Cout;
-    return cols <= 16 ? 16 : (cols + 15) / 16 * 16;
-}
+int cop_of(const mvs_conv3d_desc* d) { return d->Cout == 1 ? 8 : d->Cout; }
+int nblk_of(const mvs_conv3d_desc* d) { return mode_of(d) == MODE_S1 ? 3 : (mode_of(d) == MODE_T2 ? 8 : 1); }
+int n_of(const mvs_conv3d_desc* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 
-struct Tap { int slot, sub, shift, tap; };  // where a filter tap reads, and its index in the gather form
+// A "fold tap": one A view (slot, sub-plane, row shift) and, per column block, the filter tap it multiplies (-1 = none).
+struct FoldTap { int slot, sub, shift, tap[8]; };
 
 // Build the entry list + weight-tile sources.  Returns the number of entries.
 int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
     const int mode = mode_of(d);
-    const bool paired = d->Cin == 8;
     memset(&src, -1, sizeof(src));
+    FoldTap ft[27];
+    int nft = 0;
+    if (mode == MODE_S1) {
+        // gather form: Conv3d reads x[o - 1 + k]; stride-1 ConvTranspose3d reads x[o + 1 - k].  Block c = input column offset c.
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh) {
+                FoldTap& t = ft[nft++];
+                t.slot = d->transposed ? 2 - kd : kd; t.sub = 0; t.shift = (d->transposed ? 2 - kh : kh) * kPW;
+                for (int c = 0; c < 8; ++c) t.tap[c] = c < 3 ? (kd * 3 + kh) * 3 + (d->transposed ? 2 - c : c) : -1;
+            }
+    } else if (mode == MODE_S2) {
+        // x[2o - 1 + k]: k = 1 -> even parity at index o (shift 1 from the tile origin o-1), k = 0 / 2 -> odd parity at o-1 / o
+        const int sh[3] = {0, 1, 1};
+        for (int tp = 0; tp < 27; ++tp) {
+            const int k[3] = {tp / 9, (tp / 3) % 3, tp % 3};
+            FoldTap& t = ft[nft++];
+            t.slot = k[0]; t.sub = (k[1] == 1 ? 0 : 1) * 2 + (k[2] == 1 ? 0 : 1); t.shift = sh[k[1]] * kPW + sh[k[2]];
+            for (int c = 0; c < 8; ++c) t.tap[c] = c == 0 ? tp : -1;
+        }
+    } else {
+        // output parity 0 <- (offset 0, k = 1); parity 1 <- (offset 0, k = 2), (offset 1, k = 0); block c = (pd, ph, pw)
+        const int kk[2][2] = {{1, -1}, {2, 0}};   // kk[parity][offset]
+        for (int od = 0; od < 2; ++od)
+            for (int oh = 0; oh < 2; ++oh)
+                for (int ow = 0; ow < 2; ++ow) {
+                    FoldTap& t = ft[nft++];
+                    t.slot = od; t.sub = 0; t.shift = oh * kPW + ow;
+                    for (int c = 0; c < 8; ++c) {
+                        const int kd = kk[c >> 2][od], kh = kk[(c >> 1) & 1][oh], kw = kk[c & 1][ow];
+                        t.tap[c] = (kd < 0 || kh < 0 || kw < 0) ? -1 : (kd * 3 + kh) * 3 + kw;
+                    }
+                }
+    }
     int ne = 0;
-    auto add = [&](int slot, int sub, int shift, int lbo_rows, int group, bool first) {
+    auto add = [&](const FoldTap& t, int shift, int lbo_rows) {
         Entry& e = p.prog[ne];
-        e.row_shift = (int16_t)shift; e.lbo_rows = (uint16_t)lbo_rows; e.slot_off = (uint8_t)slot; e.sub = (uint8_t)sub;
-        e.group = (uint8_t)group; e.first = first ? 1 : 0;
+        e.row_shift = (int16_t)shift; e.lbo_rows = (uint16_t)lbo_rows; e.slot_off = (uint8_t)t.slot; e.sub = (uint8_t)t.sub;
+        e.group = 0; e.first = ne == 0 ? 1 : 0;
         return ne++;
     };
-    if (mode == MODE_T2) {
-        // output parity 0 <- (offset 0, k = 1); parity 1 <- (offset 0, k = 2), (offset 1, k = 0)
-        const int noff[2] = {1, 2}, off[2][2] = {{0, 0}, {0, 1}}, kk[2][2] = {{1, 1}, {2, 0}};
-        for (int pd = 0; pd < 2; ++pd)
-            for (int ph = 0; ph < 2; ++ph) {
-                bool first = true;
-                for (int a = 0; a < noff[pd]; ++a)
-                    for (int c = 0; c < noff[ph]; ++c)
-                        for (int ow = 0; ow < 2; ++ow) {
-                            const int e = add(off[pd][a], 0, off[ph][c] * kPW + ow, 0, pd * 2 + ph, first);
-                            first = false;
-                            const int kd = kk[pd][a], kh = kk[ph][c];
-                            const int tap0 = ow == 0 ? (kd * 3 + kh) * 3 + 1 : -1;      // pw = 0: kw = 1 at offset 0 only
-                            const int tap1 = (kd * 3 + kh) * 3 + (ow == 0 ? 2 : 0);     // pw = 1: kw = 2 at offset 0, kw = 0 at offset 1
-                            for (int kc = 0; kc < d->Cin / 8; ++kc) { src.tap[e][kc][0] = (int8_t)tap0; src.tap[e][kc][1] = (int8_t)tap1; src.cib[e][kc] = (int8_t)kc; }
-                        }
-            }
-        return ne;
-    }
-    // S1 / S2: collect the 27 taps
-    Tap taps[27];
-    for (int tp = 0; tp < 27; ++tp) {
-        const int k[3] = {tp / 9, (tp / 3) % 3, tp % 3};
-        Tap& t = taps[tp];
-        t.tap = tp;
-        if (mode == MODE_S1) {
-            // gather form: Conv3d reads x[o - 1 + k]; stride-1 ConvTranspose3d reads x[o + 1 - k]
-            const int o[3] = {d->transposed ? 2 - k[0] : k[0], d->transposed ? 2 - k[1] : k[1], d->transposed ? 2 - k[2] : k[2]};
-            t.slot = o[0]; t.sub = 0; t.shift = o[1] * kPW + o[2];
-        } else {
-            // x[2o - 1 + k]: k = 1 -> even parity at index o (shift 1 from the tile origin o-1), k = 0 / 2 -> odd parity at o-1 / o
-            const int sh[3] = {0, 1, 1};
-            t.slot = k[0]; t.sub = (k[1] == 1 ? 0 : 1) * 2 + (k[2] == 1 ? 0 : 1); t.shift = sh[k[1]] * kPW + sh[k[2]];
-        }
-    }
-    if (!paired) {
-        for (int tp = 0; tp < 27; ++tp) {
-            const int e = add(taps[tp].slot, taps[tp].sub, taps[tp].shift, 0, 0, tp == 0);
-            for (int kc = 0; kc < d->Cin / 8; ++kc) { src.tap[e][kc][0] = (int8_t)tp; src.cib[e][kc] = (int8_t)kc; }
+    if (d->Cin != 8) {
+        for (int i = 0; i < nft; ++i) {
+            const int e = add(ft[i], ft[i].shift, 0);
+            for (int kc = 0; kc < d->Cin / 8; ++kc) { for (int c = 0; c < 8; ++c) src.tap[e][kc][c] = (int8_t)ft[i].tap[c]; src.cib[e][kc] = (int8_t)kc; }
         }
         return ne;
     }
-    // Cin = 8: two taps of the same (slot, sub-plane) share one K = 16 step; LBO = their row distance
+    // Cin = 8: two fold taps of the same (slot, sub-plane) share one K = 16 step; LBO = their row distance
     bool used[27] = {false};
-    for (int a = 0; a < 27; ++a) {
+    for (int a = 0; a < nft; ++a) {
         if (used[a]) continue;
         used[a] = true;
         int best = -1;
-        for (int c = a + 1; c < 27; ++c)
-            if (!used[c] && taps[c].slot == taps[a].slot && taps[c].sub == taps[a].sub && taps[c].shift != taps[a].shift &&
-                (best < 0 || abs(taps[c].shift - taps[a].shift) < abs(taps[best].shift - taps[a].shift))) best = c;
-        int lo = a, hi = best;
-        if (best >= 0) { used[best] = true; if (taps[hi].shift < taps[lo].shift) { lo = best; hi = a; } }
+        for (int c = a + 1; c < nft; ++c)
+            if (!used[c] && ft[c].slot == ft[a].slot && ft[c].sub == ft[a].sub && ft[c].shift != ft[a].shift &&
+                (best < 0 || abs(ft[c].shift - ft[a].shift) < abs(ft[best].shift - ft[a].shift))) best = c;
         int e;
         if (best >= 0) {
-            e = add(taps[lo].slot, taps[lo].sub, taps[lo].shift, taps[hi].shift - taps[lo].shift, 0, ne == 0);
-            src.tap[e][0][0] = (int8_t)taps[lo].tap; src.tap[e][1][0] = (int8_t)taps[hi].tap;
-        } else if (taps[a].shift > 0) {   // lone tap: zero weights on the row before it
-            e = add(taps[a].slot, taps[a].sub, taps[a].shift - 1, 1, 0, ne == 0);
-            src.tap[e][1][0] = (int8_t)taps[a].tap;
-        } else {                           // lone tap at shift 0: zero weights on the row after it
-            e = add(taps[a].slot, taps[a].sub, 0, 1, 0, ne == 0);
-            src.tap[e][0][0] = (int8_t)taps[a].tap;
+            used[best] = true;
+            const int lo = ft[best].shift < ft[a].shift ? best : a, hi = lo == a ? best : a;
+            e = add(ft[lo], ft[lo].shift, ft[hi].shift - ft[lo].shift);
+            for (int c = 0; c < 8; ++c) { src.tap[e][0][c] = (int8_t)ft[lo].tap[c]; src.tap[e][1][c] = (int8_t)ft[hi].tap[c]; }
+        } else if (ft[a].shift > 0) {      // lone tap: zero weights on the row before it
+            e = add(ft[a], ft[a].shift - 1, 1);
+            for (int c = 0; c < 8; ++c) src.tap[e][1][c] = (int8_t)ft[a].tap[c];
+        } else {                            // lone tap at shift 0: zero weights on the row after it
+            e = add(ft[a], 0, 1);
+            for (int c = 0; c < 8; ++c) src.tap[e][0][c] = (int8_t)ft[a].tap[c];
         }
         src.cib[e][0] = 0; src.cib[e][1] = 0;
     }
@@ -460,7 +474,7 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     TcParams& p = pl.p;
     memset(&p, 0, sizeof(p));
     p.mode = mode_of(d);
-    p.B = d->B; p.CiB = d->Cin / 8; p.Cout = d->Cout; p.N = n_of(d);
+    p.B = d->B; p.CiB = d->Cin / 8; p.Cout = d->Cout; p.CoP = cop_of(d); p.nblk = nblk_of(d); p.N = n_of(d);
     p.ksteps = d->Cin == 8 ? 1 : d->Cin / 16;
     p.kchunks = 2 * p.ksteps;
     p.Di = d->Din; p.Hi = d->Hin; p.Wi = d->Win; p.Do = d->Dout; p.Ho = d->Hout; p.Wo = d->Wout;
@@ -469,7 +483,7 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     p.nsub = p.mode == MODE_S2 ? 4 : 1;
     p.sps = p.mode == MODE_S2 ? 2 : 1;
     p.live = p.mode == MODE_T2 ? 2 : 3;
-    p.groups = p.mode == MODE_T2 ? 4 : 1;
+    p.groups = 1;
     // ring depth = live slots + the slots of one step prefetched while the current step computes
     p.stages = p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 5);
     p.nentries = build_program(d, p, pl.src);
@@ -521,7 +535,7 @@ int mvs_conv3d_tc_supported(const mvs_conv3d_desc* d) {
     if (d->Cout != 1 && d->dtype_out != d->dtype_in) return 0;
     if (d->Cin != 8 && (d->Cin % 16 != 0 || d->Cin > 64)) return 0;
     if (d->Cout != 1 && (d->Cout % 8 != 0 || d->Cout > 64)) return 0;
-    if (mode_of(d) == MODE_T2 && (d->Cout == 1 || 2 * d->Cout > 64)) return 0;
+    if (mode_of(d) == MODE_T2 && (d->Cout == 1 || 8 * d->Cout > 256)) return 0;
     if (mode_of(d) == MODE_S2 && ((d->Win & 1) || (d->Hin & 1) || (d->Din & 1))) return 0;
     return 1;
 }
@@ -529,7 +543,8 @@ int mvs_conv3d_tc_supported(const mvs_conv3d_desc* d) {
 int64_t mvs_conv3d_tc_workspace_bytes(const mvs_conv3d_desc* d) {
     if (!mvs_conv3d_tc_supported(d)) return 0;
     const int kchunks = d->Cin == 8 ? 2 : d->Cin / 8;
-    return (int64_t)kMaxEntries * kchunks * n_of(d) * 16;  // weight tiles [entry][kchunk][N][8] in the storage dtype
+    const int nentries = mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27);   // upper bounds (Cin = 8 pairs need fewer)
+    return (int64_t)nentries * kchunks * n_of(d) * 16;  // weight tiles [entry][kchunk][N][8] in the storage dtype
 }
 
 int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
@@ -550,8 +565,8 @@ int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, c
     const int nvec = p.nentries * p.kchunks * p.N;
     if (d->algo == 3) {
         // the caller kept the tiles of a frozen weight from an earlier algo = 2 call on the same workspace
-    } else if (p.is_bf16) pack_tiles_kernel<__nv_bfloat16><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__nv_bfloat16*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
-    else pack_tiles_kernel<__half><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__half*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad);
+    } else if (p.is_bf16) pack_tiles_kernel<__nv_bfloat16><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__nv_bfloat16*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad, p.CoP, p.nblk);
+    else pack_tiles_kernel<__half><<<mvs_cdiv(nvec, 256), 256, 0, st>>>(g, (__half*)ws, pl.src, p.nentries, p.kchunks, p.N, d->Cin, d->Cout, CoutPad, p.CoP, p.nblk);
 
     // ---- tensor maps over x (zero fill outside the volume)
     TensorMaps maps;

@@ -15,12 +15,17 @@ softargmin_fwd_kernel(const float* __restrict__ cost, const float* __restrict__ 
     const int b = (int)(i / HW);
     const float* col = cost + (int64_t)b * D * HW + p;
     // sweep 1: max and sum of exponentials (as ATen's softmax: exp(x - max) / sum)
+    // only B*H*W threads exist (20 k at the headline size), so latency is hidden with memory-level parallelism:
+    // every sweep is unrolled to keep 16 independent loads in flight; the accumulation ORDER stays sequential in d.
     float mx = -INFINITY;
+#pragma unroll 16
     for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(col + (int64_t)d * HW));
     float sum = 0.f;
+#pragma unroll 16
     for (int d = 0; d < D; ++d) sum += expf(__ldg(col + (int64_t)d * HW) - mx);
     // sweep 2: expectations, ascending d, fp32 (hazard H12: the index is a truncated float sum)
     float e_depth = 0.f, e_index = 0.f;
+#pragma unroll 8
     for (int d = 0; d < D; ++d) {
         const float pd = expf(__ldg(col + (int64_t)d * HW) - mx) / sum;
         const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
