@@ -82,7 +82,8 @@ extern "C" int mvs_softargmin_fwd(const float* cost, const float* depth, int per
     MVS_REQUIRE(cost && depth, MVS_E_ARG, "mvs_softargmin_fwd: null pointer");
     MVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, MVS_E_SHAPE, "mvs_softargmin_fwd: bad dims");
     const int64_t total = (int64_t)B * H * W;
-    MVS_LAUNCH(softargmin_fwd_kernel, dim3(mvs_cdiv(total, 128)), dim3(128), stream, cost, depth, per_pixel, depth_out,
+    const int bs = total < 148 * 1024 ? 32 : 128;   // few pixel columns: one warp per block spreads them over all SMs
+    MVS_LAUNCH(softargmin_fwd_kernel, dim3(mvs_cdiv(total, bs)), dim3(bs), stream, cost, depth, per_pixel, depth_out,
                index_out, conf_out, prob_out, B, D, H * W);
     return MVS_CHECK_LAUNCH("mvs_softargmin_fwd");
 }

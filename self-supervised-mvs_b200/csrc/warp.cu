@@ -239,8 +239,8 @@ template <> struct Pack2<__nv_bfloat16> {
     static __device__ __forceinline__ __nv_bfloat162 from_f2(float2 v) { return __float22bfloat162_rn(v); }
 };
 
-template <typename T, int CPT>
-__global__ void __launch_bounds__(128)
+template <typename T, int CPT, int NS>   // NS = compile-time bound on the source count (register arrays are sized by it)
+__global__ void __launch_bounds__(128, NS <= 4 ? 5 : 3)
 warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
                          const float* __restrict__ depth, int per_pixel, T* __restrict__ var, int B, int CB, int D, int H,
                          int W, int dper, int align_corners, int ref_sq_in_sum) {
@@ -258,17 +258,17 @@ warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, cons
     const int64_t plane = (int64_t)HW * 8;                       // elements per channel block of a map
     const int64_t map_off = ((int64_t)b * CB + (int64_t)cg * CPT) * plane;
 
-    float2 r[CPT][4], r2[CPT][4];
+    float2 r[CPT][4];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ref + map_off + c * plane + (int64_t)p * 8));
         const T2* h = reinterpret_cast<const T2*>(&raw);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { r[c][j] = Pack2<T>::to_f2(h[j]); r2[c][j] = __fmul2_rn(r[c][j], r[c][j]); }
+        for (int j = 0; j < 4; ++j) r[c][j] = Pack2<T>::to_f2(h[j]);
     }
-    float ray[MVS_MAX_SRC][3], tr[MVS_MAX_SRC][3];
+    float ray[NS][3], tr[NS][3];
 #pragma unroll
-    for (int s = 0; s < MVS_MAX_SRC; ++s)
+    for (int s = 0; s < NS; ++s)
         if (s < nsrc) {
             const float* m = rt + ((int64_t)s * B + b) * 12;
             pixel_ray(m, fx, fy, ray[s]);
@@ -287,21 +287,26 @@ warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, cons
 #pragma unroll
         for (int c = 0; c < CPT; ++c)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { s1[c][j] = ref_sq_in_sum ? r2[c][j] : r[c][j]; s2[c][j] = r2[c][j]; }
+            for (int j = 0; j < 4; ++j) { s2[c][j] = __fmul2_rn(r[c][j], r[c][j]); s1[c][j] = ref_sq_in_sum ? s2[c][j] : r[c][j]; }
 #pragma unroll
-        for (int s = 0; s < MVS_MAX_SRC; ++s) {
+        for (int s = 0; s < NS; ++s) {
             if (s < nsrc) {
                 const float pz = ray[s][2] * dv + tr[s][2];
                 const float iz = 1.f / pz;                       // pz == 0 -> inf -> NaN/inf coordinates -> every tap rejected
                 const float ix = (ray[s][0] * dv + tr[s][0]) * iz * sx + oxy;
                 const float iy = (ray[s][1] * dv + tr[s][1]) * iz * sy + oxy;
-                const float x0 = floorf(ix), y0 = floorf(iy);
+                // floor and float->int without the conversion (XU) pipe: adding 1.5 * 2^23 with round-down leaves floor(ix)
+                // in the low mantissa bits (exact for |ix| < 2^22; larger or NaN coordinates fail the range tests below)
+                const float kMagic = 12582912.f;
+                const float tx = __fadd_rd(ix, kMagic), ty = __fadd_rd(iy, kMagic);
+                const float x0 = tx - kMagic, y0 = ty - kMagic;
                 const float x1 = x0 + 1.f, y1 = y0 + 1.f;
                 const bool vx0 = (x0 >= 0.f) && (x0 <= (float)(W - 1)), vx1 = (x1 >= 0.f) && (x1 <= (float)(W - 1));
                 const bool vy0 = (y0 >= 0.f) && (y0 <= (float)(H - 1)), vy1 = (y1 >= 0.f) && (y1 <= (float)(H - 1));
                 const float wx0 = x1 - ix, wx1 = ix - x0, wy0 = y1 - iy, wy1 = iy - y0;
                 // invalid taps read pixel (clamped) with weight exactly 0, so there is no divergent load
-                const int xa = vx0 ? (int)x0 : 0, xb = vx1 ? (int)x1 : 0, ya = vy0 ? (int)y0 : 0, yb = vy1 ? (int)y1 : 0;
+                const int xi = __float_as_int(tx) - 0x4B400000, yi = __float_as_int(ty) - 0x4B400000;
+                const int xa = vx0 ? xi : 0, xb = vx1 ? xi + 1 : 0, ya = vy0 ? yi : 0, yb = vy1 ? yi + 1 : 0;
                 const int o0 = ya * W + xa, o1 = ya * W + xb, o2 = yb * W + xa, o3 = yb * W + xb;
                 const T2 w0 = Pack2<T>::splat((vx0 && vy0) ? wx0 * wy0 : 0.f), w1 = Pack2<T>::splat((vx1 && vy0) ? wx1 * wy0 : 0.f);
                 const T2 w2 = Pack2<T>::splat((vx0 && vy1) ? wx0 * wy1 : 0.f), w3 = Pack2<T>::splat((vx1 && vy1) ? wx1 * wy1 : 0.f);
@@ -376,18 +381,16 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     const int CB = C / 8, HW = H * W;
 #ifndef MVS_CPU_EMU
     if (dtype_in == dtype_out && dtype_in != MVS_F32 && CB % 2 == 0) {
-        // 16-bit storage: packed-math kernel, CPT channel blocks per thread
-        static const int cpt_env = getenv("MVS_WARP_CPT") ? atoi(getenv("MVS_WARP_CPT")) : 0;
-        const int cpt = (cpt_env == 4 && CB % 4 == 0) ? 4 : 2;
-        const int dperf = depth_chunk(D, HW, B, CB / cpt);
-        const dim3 gridf(mvs_cdiv(HW, 128), (unsigned)(B * (CB / cpt) * ((D + dperf - 1) / dperf)));
-        if (dtype_in == MVS_F16) {
-            if (cpt == 4) warp_var_fwd_fast_kernel<__half, 4><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __half*)ref, sp, nsrc, rt, depth, per_pixel, (__half*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
-            else warp_var_fwd_fast_kernel<__half, 2><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __half*)ref, sp, nsrc, rt, depth, per_pixel, (__half*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
-        } else {
-            if (cpt == 4) warp_var_fwd_fast_kernel<__nv_bfloat16, 4><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)ref, sp, nsrc, rt, depth, per_pixel, (__nv_bfloat16*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
-            else warp_var_fwd_fast_kernel<__nv_bfloat16, 2><<<gridf, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)ref, sp, nsrc, rt, depth, per_pixel, (__nv_bfloat16*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum);
-        }
+        // 16-bit storage: packed-math kernel, 2 channel blocks per thread, source-count bound in {2,4,6,8}
+        const int dperf = depth_chunk(D, HW, B, CB / 2);
+        const dim3 gridf(mvs_cdiv(HW, 128), (unsigned)(B * (CB / 2) * ((D + dperf - 1) / dperf)));
+#define MVS_WV_LAUNCH(T, NS) warp_var_fwd_fast_kernel<T, 2, NS><<<gridf, 128, 0, (cudaStream_t)stream>>>( \
+            (const T*)ref, sp, nsrc, rt, depth, per_pixel, (T*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum)
+#define MVS_WV_BY_NS(T) do { if (nsrc <= 2) MVS_WV_LAUNCH(T, 2); else if (nsrc <= 4) MVS_WV_LAUNCH(T, 4); \
+                             else if (nsrc <= 6) MVS_WV_LAUNCH(T, 6); else MVS_WV_LAUNCH(T, 8); } while (0)
+        if (dtype_in == MVS_F16) MVS_WV_BY_NS(__half); else MVS_WV_BY_NS(__nv_bfloat16);
+#undef MVS_WV_BY_NS
+#undef MVS_WV_LAUNCH
         return MVS_CHECK_LAUNCH("mvs_warp_var_fwd");
     }
 #endif
