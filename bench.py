@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16")
+    ap.add_argument("--batch", type=int, default=4, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
@@ -175,11 +176,12 @@ def main():
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
     elem = 4 if dtype == torch.float32 else 2
     model = make_model(dtype).to(dev)
-    host = synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=rank)
+    PB = args.batch
+    host = synth.mvsnet_inputs(PB, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=rank)
     pinned = {k: host[k].pin_memory() for k in ("imgs", "proj_matrices", "depth_values")}
     res = {k: v.to(dev) for k, v in pinned.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    out_host = {"depth": torch.empty(1, HF, WF).pin_memory(), "conf": torch.empty(1, HF, WF).pin_memory()}
+    out_host = {"depth": torch.empty(PB, HF, WF).pin_memory(), "conf": torch.empty(PB, HF, WF).pin_memory()}
     stream = torch.cuda.current_stream(dev)
 
     graphed = None
@@ -244,20 +246,20 @@ def main():
                 e = [mk() for _ in range(8)]
                 imgs = res["imgs"]
                 flush.zero_(); e[0].record(stream)
-                xin = imgs.transpose(0, 1).reshape(VIEWS, 3, HEIGHT, WIDTH)
+                xin = imgs.transpose(0, 1).reshape(VIEWS * PB, 3, HEIGHT, WIDTH)
                 if dtype != torch.float32:   # same library path MVSNet.forward takes in eval mode
                     f = model.feature.forward_folded(xin, dtype)
                 else:
                     f = model.feature(xin)
-                feats = list(f.reshape(VIEWS, 1, CHANNELS, HF, WF).unbind(0))
+                feats = list(f.reshape(VIEWS, PB, CHANNELS, HF, WF).unbind(0))
                 e[1].record(stream)
                 rt = ops.compose_proj(res["proj_matrices"])
                 ref8 = ops.pack_c8(feats[0], dtype)
                 src8 = [ops.pack_c8(s, dtype) for s in feats[1:]]
-                var = torch.empty(1, CHANNELS // 8, NDEPTH, HF, WF, 8, dtype=dtype, device=dev)
+                var = torch.empty(PB, CHANNELS // 8, NDEPTH, HF, WF, 8, dtype=dtype, device=dev)
                 flush.zero_(); e[2].record(stream)
                 ssmvs_b200._lib.call("mvs_warp_var_fwd", ref8, ref8.data_ptr(), ops._ptr_array(src8), len(src8), rt.data_ptr(),
-                                     res["depth_values"].data_ptr(), 0, var.data_ptr(), 1, CHANNELS, NDEPTH, HF, WF,
+                                     res["depth_values"].data_ptr(), 0, var.data_ptr(), PB, CHANNELS, NDEPTH, HF, WF,
                                      ssmvs_b200._lib.dtype_code(dtype), ssmvs_b200._lib.dtype_code(dtype), 0, 0)
                 e[3].record(stream)
                 flush.zero_(); e[4].record(stream)
@@ -274,8 +276,8 @@ def main():
 
     stages = stage_times()
     peaks = load_peaks()
-    wv_gbs = warp_var_bytes(elem) / (stages["warp_var"] * 1e-3) / 1e9
-    reg_tfs = REG_FLOPS / (stages["reg3d"] * 1e-3) / 1e12
+    wv_gbs = PB * warp_var_bytes(elem) / (stages["warp_var"] * 1e-3) / 1e9
+    reg_tfs = PB * REG_FLOPS / (stages["reg3d"] * 1e-3) / 1e12
     roof_wv = {"kernel": "warp_var_fwd_kernel", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": wv_gbs / peaks["hbm_gbs"], "traffic": None, "ms": stages["warp_var"], "peak_source": peaks["source"]}
     roof_reg = {"kernel": "CostRegNet conv stack (12 launches)", "bound": "tensor", "achieved": reg_tfs, "peak": peaks["bf16_tflops"],
@@ -284,7 +286,7 @@ def main():
     dominant = roof_reg if stages["reg3d"] >= stages["warp_var"] else roof_wv
 
     if rank == 0:
-        items = world * args.steps
+        items = world * args.steps * PB
         value = items * SAMPLES_PER_ITEM / (ms_total * 1e-3)
         e2e_value = items * SAMPLES_PER_ITEM / (ms_e2e * 1e-3)
         h2d = sum(v.numel() * v.element_size() for v in pinned.values())
@@ -293,7 +295,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " storage, f32 accumulate",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": world, "per_gpu_batch": 1, "parallelism": "dp%d (items sharded, no collective)" % world,
+                "config": {"workload": WORKLOAD, "global_batch": world * PB, "per_gpu_batch": PB, "parallelism": "dp%d (items sharded, no collective)" % world,
                            "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
                            "launch": "python" if graphed is None else "cuda-graph replay (%d C-ABI launches per step)" % graphed.launches_per_replay,
                            "wall_s_incl_flush": wall},

@@ -56,10 +56,14 @@ class FeatureNet(nn.Module):
             hit = (sig, layers)
             self.__dict__.setdefault("_folded", {})[key] = hit
         y = x.to(dtype).contiguous(memory_format=torch.channels_last)
+        fused = getattr(torch, "cudnn_convolution_relu", None) if y.is_cuda else None
         for w, b, stride, pad, relu in hit[1]:
-            y = F.conv2d(y, w, b, stride, pad)
-            if relu:
-                y = F.relu_(y)
+            if relu and fused is not None:
+                y = fused(y, w, b, stride, pad, (1, 1), 1)      # cuDNN conv + bias + ReLU in one kernel
+            else:
+                y = F.conv2d(y, w, b, stride, pad)
+                if relu:
+                    y = F.relu_(y)
         return y
 
 

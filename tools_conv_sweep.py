@@ -39,6 +39,11 @@ def run(cin, cout, stride, tr, shape, nm=0):
 
 
 full = (1, 192, 128, 160)
+if len(sys.argv) > 1 and sys.argv[1] == "prof":   # short list for ncu captures
+    run(32, 8, 1, False, full)
+    run(32, 64, 1, False, full)
+    run(16, 8, 2, True, (1, 96, 64, 80))
+    sys.exit(0)
 for cout in (8, 16, 32, 64):
     run(32, cout, 1, False, full)
 for nm in (1, 2, 4):
