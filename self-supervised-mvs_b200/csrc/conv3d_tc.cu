@@ -128,7 +128,85 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // hi word = SBO >> 4 (distance between 8-row groups = 128 B) | version 1 (sm_100) at bit 46; layout type 0 = SWIZZLE_NONE.
 // They are assembled inline by the MMA issuers (one add per K step).
 
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& raw, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& raw, float (&v)[8]) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+
 struct TensorMaps { CUtensorMap m[4]; };
+
+// ------------------------------------------------------------------------------------------------ epilogue of one M-tile row
+// One accumulator row (= one lane) -> NOV output voxels x CoB channel blocks.  Every global read (skip tensor) and every
+// TMEM read of a channel block is issued before the first use, so their latencies overlap instead of adding up.
+//   NOV = 8 : transposed stride 2, column block ov = output parity (pd, ph, pw) of the 2x2x2 voxel block of this input voxel
+//   KWFOLD  : stride 1, column blocks 0,1,2 hold the taps reading input column (lane): output j = blk0[j] + blk1[j+1] + blk2[j+2]
+template <typename T, int NOV, bool KWFOLD>
+__device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t trow, bool valid, int b, int od0, int oh0, int ow0, int CoB,
+                                              int64_t HWo) {
+    constexpr int NLD = KWFOLD ? 3 : NOV;
+    for (int cb = 0; cb < CoB; ++cb) {
+        int64_t off[NOV];
+        uint4 sk[NOV];
+#pragma unroll
+        for (int ov = 0; ov < NOV; ++ov) {
+            const int od = od0 + (NOV == 8 ? (ov >> 2) : 0), oh = oh0 + (NOV == 8 ? ((ov >> 1) & 1) : 0), ow = ow0 + (NOV == 8 ? (ov & 1) : 0);
+            off[ov] = p.Cout == 1 ? ((int64_t)b * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow
+                                  : ((((int64_t)b * CoB + cb) * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow) * 8;
+            sk[ov] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && p.skip) {
+                if (p.Cout == 1) sk[ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off[ov]));
+                else sk[ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off[ov]));
+            }
+        }
+        uint32_t v[NLD][8];
+#pragma unroll
+        for (int l = 0; l < NLD; ++l) tmem_ld8(trow + (uint32_t)(l * p.CoP + cb * 8), v[l]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int ov = 0; ov < NOV; ++ov) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (KWFOLD) o[k] = __uint_as_float(v[0][k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[1][k]), 1) +
+                                   __shfl_down_sync(0xffffffffu, __uint_as_float(v[2][k]), 2);
+                else o[k] = __uint_as_float(v[ov][k]);
+            }
+            if (!valid) continue;
+            if (p.Cout == 1) {
+                float x = o[0];
+                if (p.scale) x *= __ldg(p.scale);
+                if (p.shift) x += __ldg(p.shift);
+                if (p.relu) x = fmaxf(x, 0.f);
+                if (p.skip) x += __uint_as_float(sk[ov].x);
+                reinterpret_cast<float*>(p.y)[off[ov]] = x;
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int co = cb * 8 + k;
+                float x = o[k];
+                if (p.scale) x *= __ldg(p.scale + co);
+                if (p.shift) x += __ldg(p.shift + co);
+                if (p.relu) x = fmaxf(x, 0.f);
+                o[k] = x;
+            }
+            if (p.skip) {
+                float sv[8];
+                unpack8<T>(sk[ov], sv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] += sv[k];
+            }
+            V8<T>::store(reinterpret_cast<T*>(p.y) + off[ov], o);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ kernel
 template <typename T>
@@ -259,7 +337,6 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
         const bool kwfold = p.mode == MODE_S1;
-        const int nov = p.mode == MODE_T2 ? 8 : 1;  // output voxels per accumulator row
         for (int i = 0; i < nsteps; ++i) {
             const int buf = i & 1;
             mbar_wait(acc_full + buf, (i >> 1) & 1);
@@ -269,61 +346,9 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 const int hh = r >> 5, ww = r & 31;     // a warp is one h-row of the tile: lane = w position
                 const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
                 const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N);
-                for (int cb = 0; cb < CoB; ++cb) {
-                    for (int ov = 0; ov < nov; ++ov) {
-                        float o[8];
-                        if (kwfold) {
-                            // blocks 0,1,2 hold the taps that read input column (lane), for outputs lane, lane-1, lane-2:
-                            // output column j = block0[j] + block1[j+1] + block2[j+2]
-                            uint32_t v0[8], v1[8], v2[8];
-                            tmem_ld8(trow + (uint32_t)(cb * 8), v0);
-                            tmem_ld8(trow + (uint32_t)(p.CoP + cb * 8), v1);
-                            tmem_ld8(trow + (uint32_t)(2 * p.CoP + cb * 8), v2);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                o[k] = __uint_as_float(v0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1) +
-                                       __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2);
-                        } else {
-                            uint32_t v0[8];
-                            tmem_ld8(trow + (uint32_t)(ov * p.CoP + cb * 8), v0);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v0[k]);
-                        }
-                        if (!valid) continue;
-                        int od, oh, ow;
-                        if (p.mode == MODE_T2) { od = 2 * (d0 + i) + (ov >> 2); oh = 2 * (h0 + hh) + ((ov >> 1) & 1); ow = 2 * (w0 + ww) + (ov & 1); }
-                        else { od = d0 + i; oh = h0 + hh; ow = w0 + ww; }
-                        if (p.Cout == 1) {
-                            float x = o[0];
-                            if (p.scale) x *= __ldg(p.scale);
-                            if (p.shift) x += __ldg(p.shift);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            const int64_t off = ((int64_t)b * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow;
-                            if (p.skip) x += reinterpret_cast<const float*>(p.skip)[off];
-                            reinterpret_cast<float*>(p.y)[off] = x;
-                            continue;
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int co = cb * 8 + k;
-                            float x = o[k];
-                            if (p.scale) x *= __ldg(p.scale + co);
-                            if (p.shift) x += __ldg(p.shift + co);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            o[k] = x;
-                        }
-                        const int64_t off = ((((int64_t)b * CoB + cb) * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow) * 8;
-                        if (p.skip) {
-                            float sv[8];
-                            V8<T>::load(reinterpret_cast<const T*>(p.skip) + off, sv);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) o[k] += sv[k];
-                        }
-                        V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
-                    }
-                }
+                if (p.mode == MODE_T2) epilogue_rows<T, 8, false>(p, trow, valid, b, 2 * (d0 + i), 2 * (h0 + hh), 2 * (w0 + ww), CoB, HWo);
+                else if (kwfold) epilogue_rows<T, 1, true>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                else epilogue_rows<T, 1, false>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
             }
             tc_fence_before();
             __syncwarp();
