@@ -36,6 +36,7 @@ WORKLOAD = "MVSNet forward N=5 512x640 D=192 (BASELINE.json configs[1])"
 METRIC = "depth-samples/sec (N=5,D=192,512x640)"
 # algorithmic work per item: warp+variance bytes = s*(C*D*Hf*Wf + N*C*Hf*Wf) + 4*D ; CostRegNet flops
 REG_FLOPS = 20304 * SAMPLES_PER_ITEM
+CONV0_FLOPS = 2 * 27 * 32 * 8 * SAMPLES_PER_ITEM   # conv0 of CostRegNet: 6912 MAC per depth-sample
 SOFTARGMIN_BYTES = 4 * SAMPLES_PER_ITEM + 12 * HF * WF
 
 
@@ -116,10 +117,26 @@ def cpu_forward_timer(steps: int, warmup: int):
     """The reference's CPU path (oracle port: same torch-CPU op sequence as jdacs/models/mvsnet.py:105-155)."""
     from ssmvs_b200 import synth
     oracle = load_oracle()
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    cores = os.cpu_count() or 1
     model = make_model(torch.float32)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    threads = int(os.environ.get("MVS_CPU_THREADS", "0"))
+    if not threads:
+        # torch's CPU kernels stop scaling (and regress) on many-core hosts for this op mix: give the reference its best
+        # thread count, probed on a quarter-depth problem (48 planes), instead of blindly using every core
+        probe = synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, 48, seed=0)
+        best = None
+        for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+            torch.set_num_threads(n)
+            with torch.no_grad():
+                oracle.mvsnet_forward(probe["imgs"], probe["proj_matrices"], probe["depth_values"], sd)
+                t0 = time.perf_counter()
+                oracle.mvsnet_forward(probe["imgs"], probe["proj_matrices"], probe["depth_values"], sd)
+                dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, n)
+        threads = best[1]
+    torch.set_num_threads(threads)
     inp = synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=0)
     times = []
     with torch.no_grad():
@@ -142,7 +159,7 @@ def run_reference(args, rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": 1, "sample": "1 item per step on host cores"},
             "cpu_baseline": {"value": val, "unit": "depth-samples/s", "cores": threads, "kind": "port",
-                             "sample": "%d full forward passes of 1 item (oracle port of the reference's torch-CPU path, fp32)" % len(times)},
+                             "sample": "%d full forward passes of 1 item (oracle port of the reference's torch-CPU path, fp32; best of the probed thread counts, host has %d cores)" % (len(times), os.cpu_count() or 1)},
             "e2e": {"value": val, "unit": "depth-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -239,11 +256,11 @@ def main():
 
     # ---- per-stage timing for the roofline (same inputs, each stage bracketed by events, L2 flushed before each)
     def stage_times(reps=5):
-        t = {"features": [], "warp_var": [], "reg3d": [], "softargmin": []}
+        t = {"features": [], "warp_var": [], "reg3d": [], "softargmin": [], "conv0": []}
         mk = lambda: torch.cuda.Event(enable_timing=True)
         with torch.no_grad():
             for _ in range(reps):
-                e = [mk() for _ in range(8)]
+                e = [mk() for _ in range(10)]
                 imgs = res["imgs"]
                 flush.zero_(); e[0].record(stream)
                 xin = imgs.transpose(0, 1).reshape(VIEWS * PB, 3, HEIGHT, WIDTH)
@@ -269,21 +286,37 @@ def main():
                 flush.zero_(); e[6].record(stream)
                 ops.soft_argmin(reg, res["depth_values"])
                 e[7].record(stream)
+                # the single largest launch of the stack: conv0 (32 -> 8 channels at full D x H x W), timed alone
+                flush.zero_(); e[8].record(stream)
+                model.cost_regularization.conv0(var)
+                e[9].record(stream)
                 torch.cuda.synchronize(dev)
-                for k, (i, j) in zip(t, ((0, 1), (2, 3), (4, 5), (6, 7))):
+                for k, (i, j) in zip(t, ((0, 1), (2, 3), (4, 5), (6, 7), (8, 9))):
                     t[k].append(e[i].elapsed_time(e[j]))
         return {k: statistics.median(v) for k, v in t.items()}
 
     stages = stage_times()
     peaks = load_peaks()
+    try:   # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), per item
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        traffic = {}
     wv_gbs = PB * warp_var_bytes(elem) / (stages["warp_var"] * 1e-3) / 1e9
     reg_tfs = PB * REG_FLOPS / (stages["reg3d"] * 1e-3) / 1e12
-    roof_wv = {"kernel": "warp_var_fwd_kernel", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-               "frac": wv_gbs / peaks["hbm_gbs"], "traffic": None, "ms": stages["warp_var"], "peak_source": peaks["source"]}
-    roof_reg = {"kernel": "CostRegNet conv stack (12 launches)", "bound": "tensor", "achieved": reg_tfs, "peak": peaks["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": reg_tfs / peaks["bf16_tflops"], "traffic": None, "ms": stages["reg3d"],
+    conv0_tfs = PB * CONV0_FLOPS / (stages["conv0"] * 1e-3) / 1e12
+    roof_wv = {"kernel": "warp_var_fwd_fast_kernel (fused warp + variance)", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"],
+               "unit": "GB/s", "frac": wv_gbs / peaks["hbm_gbs"], "traffic": traffic.get("warp_var_fwd"), "ms": stages["warp_var"],
+               "peak_source": peaks["source"], "algorithmic_bytes": PB * warp_var_bytes(elem)}
+    roof_conv0 = {"kernel": "conv3d_tc_kernel (conv0: 32->8, 3x3x3, full D x H x W)", "bound": "tensor", "achieved": conv0_tfs,
+                  "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": conv0_tfs / peaks["bf16_tflops"],
+                  "traffic": traffic.get("conv0"), "ms": stages["conv0"], "peak_source": peaks["source"],
+                  "algorithmic_flops": PB * CONV0_FLOPS,
+                  "note": "thin layer (N = 3 taps x 8 couts per MMA): bounded by the A-operand fetch of tcgen05.mma, not by MMA rate"}
+    roof_reg = {"kernel": "CostRegNet conv stack (12 launches)", "bound": "tensor", "achieved": reg_tfs, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": reg_tfs / peaks["bf16_tflops_sustained"], "traffic": None, "ms": stages["reg3d"],
                 "peak_source": peaks["source"]}
-    dominant = roof_reg if stages["reg3d"] >= stages["warp_var"] else roof_wv
+    dominant = roof_conv0 if stages["conv0"] >= stages["warp_var"] else roof_wv
 
     if rank == 0:
         items = world * args.steps * PB
@@ -302,11 +335,12 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "depth-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "roofline": dominant, "roofline_warp_var": roof_wv, "roofline_reg3d": roof_reg, "stage_ms": stages}
+                "roofline": dominant, "roofline_warp_var": roof_wv, "roofline_conv0": roof_conv0, "roofline_reg3d": roof_reg,
+                "stage_ms": stages}
         if world == 1 and not args.no_cpu_baseline:
             times, threads = cpu_forward_timer(3, 1)
             line["cpu_baseline"] = {"value": SAMPLES_PER_ITEM * len(times) / sum(times), "unit": "depth-samples/s", "cores": threads,
-                                    "kind": "port", "sample": "3 full forward passes of 1 item after 1 warm-up (oracle port of the reference's torch-CPU path, fp32)"}
+                                    "kind": "port", "sample": "3 full forward passes of 1 item after 1 warm-up (oracle port of the reference's torch-CPU path, fp32; best of the probed thread counts, host has %d cores)" % (os.cpu_count() or 1)}
         print(json.dumps(line))
     parallel.barrier()
 
