@@ -61,7 +61,7 @@ struct TcParams {
     int Di, Hi, Wi, Do, Ho, Wo;      // input / output grids
     int Dt, Ht, Wt;                  // grid the tiles walk (S1/S2: output, T2: input)
     int TH, PH, nM, nwt, nht, LD, nseg;
-    int nsub, stages, sps, live, groups, nentries, bstages;
+    int nsub, stages, sps, live, groups, nentries, bstages, nwork;
     int b_resident, relu, is_bf16;
     uint32_t chunk_bytes, sub_bytes, slot_bytes, btile_bytes, tmem_cols;
     Entry prog[kMaxEntries];
@@ -226,14 +226,19 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int t = blockIdx.x;
-    const int wt = t % p.nwt; t /= p.nwt;
-    const int ht = t % p.nht; t /= p.nht;
-    const int seg = t % p.nseg;
-    const int b = t / p.nseg;
-    const int w0 = wt * kTW, h0 = ht * p.TH, d0 = seg * p.LD;
-    const int nsteps = min(p.LD, p.Dt - d0);                   // depth steps of this CTA
-    const int nslots = (nsteps - 1) * p.sps + p.live;          // input slots it consumes
+    // Persistent CTA: work items (tile x depth segment) are dealt round-robin; every role walks the same list, and the
+    // slot / accumulator / weight rings simply keep running across items (no pipeline drain or TMEM re-allocation between).
+    struct Work { int b, w0, h0, d0, nsteps, nslots; };
+    auto decode = [&](int t) {
+        Work k;
+        const int wt = t % p.nwt; t /= p.nwt;
+        const int ht = t % p.nht; t /= p.nht;
+        const int seg = t % p.nseg;
+        k.b = t / p.nseg; k.w0 = wt * kTW; k.h0 = ht * p.TH; k.d0 = seg * p.LD;
+        k.nsteps = min(p.LD, p.Dt - k.d0);                     // depth steps of this item
+        k.nslots = (k.nsteps - 1) * p.sps + p.live;            // input slots it consumes
+        return k;
+    };
 
     if (threadIdx.x == 0) {
         // every issuer commits its own MMAs, so the barriers the MMAs release count one arrival per issuer
@@ -257,17 +262,21 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         if (lane == 0) {
             for (int s = 0; s < p.nsub; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[s]) : "memory");
             const uint32_t box_bytes = (uint32_t)p.PH * kPW * 16u;
-            for (int j = 0; j < nslots; ++j) {
-                const int st = j % p.stages;
-                mbar_wait(slot_empty + st, ((j / p.stages) & 1) ^ 1);
-                mbar_expect_tx(slot_full + st, box_bytes * (uint32_t)(p.CiB * p.nsub));
-                uint8_t* dst = slots + (size_t)st * p.slot_bytes;
-                for (int s = 0; s < p.nsub; ++s)
-                    for (int cb = 0; cb < p.CiB; ++cb, dst += p.chunk_bytes) {
-                        if (p.mode == MODE_S1) tma_load_4d(&maps.m[0], slot_full + st, dst, (w0 - 1) * 8, h0 - 1, d0 - 1 + j, b * p.CiB + cb);
-                        else if (p.mode == MODE_T2) tma_load_4d(&maps.m[0], slot_full + st, dst, w0 * 8, h0, d0 + j, b * p.CiB + cb);
-                        else tma_load_5d(&maps.m[s], slot_full + st, dst, 0, w0 - 1, h0 - 1, 2 * d0 - 1 + j, b * p.CiB + cb);
-                    }
+            int J = 0;                                             // slots loaded so far by this CTA
+            for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+                const Work k = decode(t);
+                for (int j = 0; j < k.nslots; ++j, ++J) {
+                    const int st = J % p.stages;
+                    mbar_wait(slot_empty + st, ((J / p.stages) & 1) ^ 1);
+                    mbar_expect_tx(slot_full + st, box_bytes * (uint32_t)(p.CiB * p.nsub));
+                    uint8_t* dst = slots + (size_t)st * p.slot_bytes;
+                    for (int s = 0; s < p.nsub; ++s)
+                        for (int cb = 0; cb < p.CiB; ++cb, dst += p.chunk_bytes) {
+                            if (p.mode == MODE_S1) tma_load_4d(&maps.m[0], slot_full + st, dst, (k.w0 - 1) * 8, k.h0 - 1, k.d0 - 1 + j, k.b * p.CiB + cb);
+                            else if (p.mode == MODE_T2) tma_load_4d(&maps.m[0], slot_full + st, dst, k.w0 * 8, k.h0, k.d0 + j, k.b * p.CiB + cb);
+                            else tma_load_5d(&maps.m[s], slot_full + st, dst, 0, k.w0 - 1, k.h0 - 1, 2 * k.d0 - 1 + j, k.b * p.CiB + cb);
+                        }
+                }
             }
         }
     } else if (warp == 5) {
@@ -278,13 +287,17 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 mbar_expect_tx(b_full, (uint32_t)p.nentries * p.btile_bytes);
                 for (int e = 0; e < p.nentries; ++e) bulk_load(bsm + (size_t)e * p.btile_bytes, wsrc + (size_t)e * p.btile_bytes, p.btile_bytes, b_full);
             } else {
-                for (int i = 0, u = 0; i < nsteps; ++i)
-                    for (int e = 0; e < p.nentries; ++e, ++u) {
-                        const int st = u % p.bstages;
-                        mbar_wait(b_empty + st, ((u / p.bstages) & 1) ^ 1);
-                        mbar_expect_tx(b_full + st, p.btile_bytes);
-                        bulk_load(bsm + (size_t)st * p.btile_bytes, wsrc + (size_t)e * p.btile_bytes, p.btile_bytes, b_full + st);
-                    }
+                int u = 0;
+                for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+                    const Work k = decode(t);
+                    for (int i = 0; i < k.nsteps; ++i)
+                        for (int e = 0; e < p.nentries; ++e, ++u) {
+                            const int st = u % p.bstages;
+                            mbar_wait(b_empty + st, ((u / p.bstages) & 1) ^ 1);
+                            mbar_expect_tx(b_full + st, p.btile_bytes);
+                            bulk_load(bsm + (size_t)st * p.btile_bytes, wsrc + (size_t)e * p.btile_bytes, p.btile_bytes, b_full + st);
+                        }
+                }
             }
         }
     } else if (warp >= 1 && warp <= 4) {
@@ -299,36 +312,42 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
             const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
             const uint32_t a_kstep = (2u * p.chunk_bytes) >> 4, b_kstep = 2u * (uint32_t)p.N, b_lbo = (uint32_t)p.N << 16;
             if (p.b_resident) mbar_wait(b_full, 0);
-            for (int i = 0, u = 0; i < nsteps; ++i) {
-                const int buf = i & 1;
-                mbar_wait(acc_empty + buf, ((i >> 1) & 1) ^ 1);
-                const int jlo = i * p.sps, jhi = jlo + p.live;             // live slots [jlo, jhi)
-                for (int j = (i == 0 ? 0 : jhi - p.sps); j < jhi; ++j) mbar_wait(slot_full + (j % p.stages), (j / p.stages) & 1);
-                tc_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)((buf * p.groups * p.nM + m) * p.N);
-                for (int e = 0; e < p.nentries; ++e, ++u) {
-                    const Entry en = p.prog[e];
-                    uint32_t btile;
-                    if (p.b_resident) {
-                        btile = b_addr + (uint32_t)e * p.btile_bytes;
-                    } else {
-                        const int st = u % p.bstages;
-                        mbar_wait(b_full + st, (u / p.bstages) & 1);
-                        tc_fence_after();
-                        btile = b_addr + (uint32_t)st * p.btile_bytes;
+            int Jb = 0, I = 0, u = 0;        // first slot of the item, steps done, weight tiles consumed (all running over items)
+            for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+                const Work k = decode(t);
+                for (int i = 0; i < k.nsteps; ++i, ++I) {
+                    const int buf = I & 1;
+                    mbar_wait(acc_empty + buf, ((I >> 1) & 1) ^ 1);
+                    const int jlo = Jb + i * p.sps, jhi = jlo + p.live;             // live slots [jlo, jhi)
+                    for (int j = (i == 0 ? jlo : jhi - p.sps); j < jhi; ++j) mbar_wait(slot_full + (j % p.stages), (j / p.stages) & 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
+                    for (int e = 0; e < p.nentries; ++e, ++u) {
+                        const Entry en = p.prog[e];
+                        uint32_t btile;
+                        if (p.b_resident) {
+                            btile = b_addr + (uint32_t)e * p.btile_bytes;
+                        } else {
+                            const int st = u % p.bstages;
+                            mbar_wait(b_full + st, (u / p.bstages) & 1);
+                            tc_fence_after();
+                            btile = b_addr + (uint32_t)st * p.btile_bytes;
+                        }
+                        const uint32_t a_addr = slots_addr + (uint32_t)((jlo + en.slot_off) % p.stages) * p.slot_bytes +
+                                                (uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16);
+                        uint32_t a_lo = (a_addr >> 4) | ((en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16);
+                        uint32_t b_lo = (btile >> 4) | b_lbo;
+                        uint32_t acc = en.first ? 0u : 1u;
+                        for (int ks = 0; ks < p.ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
+                            umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
+                        if (!p.b_resident) umma_commit(b_empty + (u % p.bstages));
                     }
-                    const uint32_t a_addr = slots_addr + (uint32_t)((jlo + en.slot_off) % p.stages) * p.slot_bytes +
-                                            (uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16);
-                    uint32_t a_lo = (a_addr >> 4) | ((en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16);
-                    uint32_t b_lo = (btile >> 4) | b_lbo;
-                    const uint32_t d_tmem = d_base + (uint32_t)(en.group * p.nM * p.N);
-                    uint32_t acc = en.first ? 0u : 1u;
-                    for (int ks = 0; ks < p.ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
-                        umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
-                    if (!p.b_resident) umma_commit(b_empty + (u % p.bstages));
+                    // slots no later step of this item reads retire with these MMAs (all remaining ones after the last step)
+                    const int jrel = (i == k.nsteps - 1) ? jhi : jlo + p.sps;
+                    for (int j = jlo; j < jrel; ++j) umma_commit(slot_empty + (j % p.stages));
+                    umma_commit(acc_full + buf);
                 }
-                for (int j = jlo; j < jlo + p.sps; ++j) umma_commit(slot_empty + (j % p.stages));  // oldest slots retire with these MMAs
-                umma_commit(acc_full + buf);
+                Jb += k.nslots;
             }
         }
     } else {
@@ -337,22 +356,27 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
         const bool kwfold = p.mode == MODE_S1;
-        for (int i = 0; i < nsteps; ++i) {
-            const int buf = i & 1;
-            mbar_wait(acc_full + buf, (i >> 1) & 1);
-            tc_fence_after();
-            for (int m = 0; m < p.nM; ++m) {
-                const int r = m * 128 + quad * 32 + lane;
-                const int hh = r >> 5, ww = r & 31;     // a warp is one h-row of the tile: lane = w position
-                const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
-                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N);
-                if (p.mode == MODE_T2) epilogue_rows<T, 8, false>(p, trow, valid, b, 2 * (d0 + i), 2 * (h0 + hh), 2 * (w0 + ww), CoB, HWo);
-                else if (kwfold) epilogue_rows<T, 1, true>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
-                else epilogue_rows<T, 1, false>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+        int I = 0;
+        for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+            const Work k = decode(t);
+            const int b = k.b, w0 = k.w0, h0 = k.h0, d0 = k.d0;
+            for (int i = 0; i < k.nsteps; ++i, ++I) {
+                const int buf = I & 1;
+                mbar_wait(acc_full + buf, (I >> 1) & 1);
+                tc_fence_after();
+                for (int m = 0; m < p.nM; ++m) {
+                    const int r = m * 128 + quad * 32 + lane;
+                    const int hh = r >> 5, ww = r & 31;     // a warp is one h-row of the tile: lane = w position
+                    const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+                    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N);
+                    if (p.mode == MODE_T2) epilogue_rows<T, 8, false>(p, trow, valid, b, 2 * (d0 + i), 2 * (h0 + hh), 2 * (w0 + ww), CoB, HWo);
+                    else if (kwfold) epilogue_rows<T, 1, true>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                    else epilogue_rows<T, 1, false>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + buf);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + buf);
         }
     }
 
@@ -619,7 +643,11 @@ int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, c
             MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_conv3d_fwd: cuTensorMapEncodeTiled (parity %d) failed (%d)", s, (int)cr);
         }
     }
-    const unsigned nblocks = (unsigned)((int64_t)p.B * p.nwt * p.nht * p.nseg);
+    p.nwork = (int)((int64_t)p.B * p.nwt * p.nht * p.nseg);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned nblocks = (unsigned)min(p.nwork, sms);          // persistent: one CTA per SM walks the work list
     if (p.is_bf16) {
         cudaFuncSetAttribute(conv3d_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         conv3d_tc_kernel<__nv_bfloat16><<<nblocks, kThreads, pl.smem, st>>>(maps, p);
