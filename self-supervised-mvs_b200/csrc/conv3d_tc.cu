@@ -39,6 +39,8 @@ constexpr int kTW = 30;
 constexpr int kBStages = 16;     // max depth of the weight-tile ring (streaming mode; p.bstages are used)
 constexpr int kMaxStages = 6;    // input-slot ring
 constexpr int kMaxEntries = 27;
+constexpr int kAccRing = 4;      // accumulator ring slots of the kd-folded program (output planes in flight)
+constexpr int kPG = 32;          // kd-fold: TMEM columns per output plane (3 kw blocks of 8 + pad; N must be a multiple of 16)
 constexpr int kSmemLimit = 227 * 1024;
 enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2 };
 
@@ -62,7 +64,7 @@ struct TcParams {
     int Dt, Ht, Wt;                  // grid the tiles walk (S1/S2: output, T2: input)
     int TH, PH, nM, nwt, nht, LD, nseg;
     int nsub, stages, sps, live, groups, nentries, bstages, nwork;
-    int b_resident, relu, is_bf16;
+    int b_resident, relu, is_bf16, kdfold;
     uint32_t chunk_bytes, sub_bytes, slot_bytes, btile_bytes, tmem_cols;
     Entry prog[kMaxEntries];
 };
@@ -221,9 +223,9 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     uint64_t* slot_empty = bars + kMaxStages;      // [kMaxStages]
     uint64_t* b_full = bars + 2 * kMaxStages;      // [kBStages]
     uint64_t* b_empty = b_full + kBStages;         // [kBStages]
-    uint64_t* acc_full = b_empty + kBStages;       // [2]
-    uint64_t* acc_empty = acc_full + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_full = b_empty + kBStages;       // [kAccRing]  (2 are used unless kd-folded)
+    uint64_t* acc_empty = acc_full + kAccRing;     // [kAccRing]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccRing);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTA: work items (tile x depth segment) are dealt round-robin; every role walks the same list, and the
@@ -244,7 +246,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         // every issuer commits its own MMAs, so the barriers the MMAs release count one arrival per issuer
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(slot_full + i, 1); mbar_init(slot_empty + i, (uint32_t)p.nM); }
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, (uint32_t)p.nM); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, (uint32_t)p.nM); mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < kAccRing; ++i) { mbar_init(acc_full + i, (uint32_t)p.nM); mbar_init(acc_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -312,8 +314,50 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
             const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
             const uint32_t a_kstep = (2u * p.chunk_bytes) >> 4, b_kstep = 2u * (uint32_t)p.N, b_lbo = (uint32_t)p.N << 16;
             if (p.b_resident) mbar_wait(b_full, 0);
+            if (p.kdfold) {
+                // ---- kd-folded stride-1 program (Cout <= 8): a step is an INPUT plane p; its kh entries multiply all 9 (kd, kw)
+                // taps at once: N = 3 plane groups of kPG columns, for the output planes p-1, p, p+1, which live in a ring of
+                // kAccRing accumulator slots per M-tile.  Plane p+1 is first touched here (overwrite), so the first MMA of a step is
+                // split by flag, and any MMA is split where the three slots wrap around the ring.
+                const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
+                const uint32_t kb_lbo = (uint32_t)(3 * kPG) << 16, kb_kstep = 2u * 3u * kPG;
+                int J = 0, Qb = 0;            // input slots consumed, output planes started (running over items)
+                for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+                    const Work k = decode(t);
+                    for (int j = 0; j < k.nslots; ++j, ++J) {
+                        mbar_wait(slot_full + (J % p.stages), (J / p.stages) & 1);
+                        if (j < k.nsteps) { const int q = Qb + j; mbar_wait(acc_empty + (q % kAccRing), ((q / kAccRing) & 1) ^ 1); }
+                        tc_fence_after();
+                        int rs[3]; bool ok[3];
+                        for (int g = 0; g < 3; ++g) { const int i = j - 2 + g; ok[g] = i >= 0 && i < k.nsteps; rs[g] = (Qb + (ok[g] ? i : 0)) % kAccRing; }
+                        const uint32_t a_slot = slots_addr + (uint32_t)(J % p.stages) * p.slot_bytes;
+                        for (int e = 0; e < p.nentries; ++e) {
+                            const Entry en = p.prog[e];
+                            const uint32_t a_addr = a_slot + (uint32_t)((int)en.row_shift * 16);
+                            uint32_t a_lo = (a_addr >> 4) | ((en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16);
+                            uint32_t b_lo = ((b_addr + (uint32_t)e * p.btile_bytes) >> 4) | kb_lbo;
+                            for (int ks = 0; ks < p.ksteps; ++ks, a_lo += a_kstep, b_lo += kb_kstep) {
+                                const bool fresh2 = (e == 0 && ks == 0);      // group 2 (plane p+1) is overwritten by the step's first MMA
+                                int g = 0;
+                                while (g < 3) {
+                                    if (!ok[g]) { ++g; continue; }
+                                    int cnt = 1;
+                                    const bool fresh = fresh2 && g == 2;
+                                    while (g + cnt < 3 && ok[g + cnt] && rs[g + cnt] == rs[g + cnt - 1] + 1 && !(fresh2 && g + cnt == 2)) ++cnt;
+                                    umma_f16(tmem_base + (uint32_t)((m * kAccRing + rs[g]) * kPG), desc_hi | a_lo, desc_hi | (b_lo + (uint32_t)(g * kPG)),
+                                             idesc0 | ((uint32_t)((cnt * kPG) >> 3) << 17), fresh ? 0u : 1u);
+                                    g += cnt;
+                                }
+                            }
+                        }
+                        umma_commit(slot_empty + (J % p.stages));
+                        if (j >= 2) umma_commit(acc_full + ((Qb + j - 2) % kAccRing));      // output plane j-2 has all three contributions
+                    }
+                    Qb += k.nsteps;
+                }
+            }
             int Jb = 0, I = 0, u = 0;        // first slot of the item, steps done, weight tiles consumed (all running over items)
-            for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+            for (int t = blockIdx.x; t < p.nwork && !p.kdfold; t += gridDim.x) {
                 const Work k = decode(t);
                 for (int i = 0; i < k.nsteps; ++i, ++I) {
                     const int buf = I & 1;
@@ -361,6 +405,22 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
             const Work k = decode(t);
             const int b = k.b, w0 = k.w0, h0 = k.h0, d0 = k.d0;
             for (int i = 0; i < k.nsteps; ++i, ++I) {
+                if (p.kdfold) {    // output plane I sits in ring slot I % kAccRing of every M-tile (kPG columns, kw blocks at +0, +8, +16)
+                    const int rsl = I % kAccRing;
+                    mbar_wait(acc_full + rsl, (I / kAccRing) & 1);
+                    tc_fence_after();
+                    for (int m = 0; m < p.nM; ++m) {
+                        const int r = m * 128 + quad * 32 + lane;
+                        const int hh = r >> 5, ww = r & 31;
+                        const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+                        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((m * kAccRing + rsl) * kPG);
+                        epilogue_rows<T, 1, true>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + rsl);
+                    continue;
+                }
                 const int buf = I & 1;
                 mbar_wait(acc_full + buf, (I >> 1) & 1);
                 tc_fence_after();
@@ -391,7 +451,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
 // ------------------------------------------------------------------------------------------------ weight tiles
 // One tile per program entry: wt[entry][kchunk][n][8], n = block * CoP + co.  `src` lists, per (entry, kchunk, column
 // block), which tap of the gather form G[27][Cin][CoutPad] (and which 8 input channels) it holds; -1 = zeros.
-struct TileSrc { int8_t tap[kMaxEntries][8][8]; int8_t cib[kMaxEntries][8]; };
+struct TileSrc { int8_t tap[kMaxEntries][8][12]; int8_t cib[kMaxEntries][8]; };
 
 template <typename T>
 __global__ void pack_tiles_kernel(const float* __restrict__ g, T* __restrict__ w, const __grid_constant__ TileSrc src, int nentries,
@@ -435,11 +495,16 @@ struct Plan { TcParams p; TileSrc src; size_t smem; };
 int mode_of(const mvs_conv3d_desc* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
 
 int cop_of(const mvs_conv3d_desc* d) { return d->Cout == 1 ? 8 : d->Cout; }
-int nblk_of(const mvs_conv3d_desc* d) { return mode_of(d) == MODE_S1 ? 3 : (mode_of(d) == MODE_T2 ? 8 : 1); }
+// kd-fold (stride 1, <= 8 output channels): the 9 (kd, kw) taps of one kh share an MMA; see the issuer.  MVS_TC_KDFOLD=0 disables.
+bool kdfold_of(const mvs_conv3d_desc* d) {
+    const char* e = getenv("MVS_TC_KDFOLD");
+    return mode_of(d) == MODE_S1 && cop_of(d) == 8 && !(e && atoi(e) == 0);
+}
+int nblk_of(const mvs_conv3d_desc* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : 3) : (mode_of(d) == MODE_T2 ? 8 : 1); }
 int n_of(const mvs_conv3d_desc* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 
 // A "fold tap": one A view (slot, sub-plane, row shift) and, per column block, the filter tap it multiplies (-1 = none).
-struct FoldTap { int slot, sub, shift, tap[8]; };
+struct FoldTap { int slot, sub, shift, tap[12]; };
 
 // Build the entry list + weight-tile sources.  Returns the number of entries.
 int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
@@ -447,13 +512,24 @@ int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
     memset(&src, -1, sizeof(src));
     FoldTap ft[27];
     int nft = 0;
-    if (mode == MODE_S1) {
+    if (mode == MODE_S1 && kdfold_of(d)) {
+        // one fold tap per kh; column block g * 4 + c: plane group g (output plane p - 1 + g of input plane p) x input column offset c
+        for (int kh = 0; kh < 3; ++kh) {
+            FoldTap& t = ft[nft++];
+            t.slot = 0; t.sub = 0; t.shift = (d->transposed ? 2 - kh : kh) * kPW;
+            for (int blk = 0; blk < 12; ++blk) {
+                const int g = blk >> 2, c = blk & 3;
+                const int kd = d->transposed ? g : 2 - g;       // Conv3d: out q reads x[q - 1 + kd]; transposed: x[q + 1 - kd]
+                t.tap[blk] = c < 3 ? (kd * 3 + kh) * 3 + (d->transposed ? 2 - c : c) : -1;
+            }
+        }
+    } else if (mode == MODE_S1) {
         // gather form: Conv3d reads x[o - 1 + k]; stride-1 ConvTranspose3d reads x[o + 1 - k].  Block c = input column offset c.
         for (int kd = 0; kd < 3; ++kd)
             for (int kh = 0; kh < 3; ++kh) {
                 FoldTap& t = ft[nft++];
                 t.slot = d->transposed ? 2 - kd : kd; t.sub = 0; t.shift = (d->transposed ? 2 - kh : kh) * kPW;
-                for (int c = 0; c < 8; ++c) t.tap[c] = c < 3 ? (kd * 3 + kh) * 3 + (d->transposed ? 2 - c : c) : -1;
+                for (int c = 0; c < 12; ++c) t.tap[c] = c < 3 ? (kd * 3 + kh) * 3 + (d->transposed ? 2 - c : c) : -1;
             }
     } else if (mode == MODE_S2) {
         // x[2o - 1 + k]: k = 1 -> even parity at index o (shift 1 from the tile origin o-1), k = 0 / 2 -> odd parity at o-1 / o
@@ -462,7 +538,7 @@ int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
             const int k[3] = {tp / 9, (tp / 3) % 3, tp % 3};
             FoldTap& t = ft[nft++];
             t.slot = k[0]; t.sub = (k[1] == 1 ? 0 : 1) * 2 + (k[2] == 1 ? 0 : 1); t.shift = sh[k[1]] * kPW + sh[k[2]];
-            for (int c = 0; c < 8; ++c) t.tap[c] = c == 0 ? tp : -1;
+            for (int c = 0; c < 12; ++c) t.tap[c] = c == 0 ? tp : -1;
         }
     } else {
         // output parity 0 <- (offset 0, k = 1); parity 1 <- (offset 0, k = 2), (offset 1, k = 0); block c = (pd, ph, pw)
@@ -472,7 +548,8 @@ int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
                 for (int ow = 0; ow < 2; ++ow) {
                     FoldTap& t = ft[nft++];
                     t.slot = od; t.sub = 0; t.shift = oh * kPW + ow;
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < 12; ++c) {
+                        if (c >= 8) { t.tap[c] = -1; continue; }
                         const int kd = kk[c >> 2][od], kh = kk[(c >> 1) & 1][oh], kw = kk[c & 1][ow];
                         t.tap[c] = (kd < 0 || kh < 0 || kw < 0) ? -1 : (kd * 3 + kh) * 3 + kw;
                     }
@@ -488,7 +565,7 @@ int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
     if (d->Cin != 8) {
         for (int i = 0; i < nft; ++i) {
             const int e = add(ft[i], ft[i].shift, 0);
-            for (int kc = 0; kc < d->Cin / 8; ++kc) { for (int c = 0; c < 8; ++c) src.tap[e][kc][c] = (int8_t)ft[i].tap[c]; src.cib[e][kc] = (int8_t)kc; }
+            for (int kc = 0; kc < d->Cin / 8; ++kc) { for (int c = 0; c < 12; ++c) src.tap[e][kc][c] = (int8_t)ft[i].tap[c]; src.cib[e][kc] = (int8_t)kc; }
         }
         return ne;
     }
@@ -506,13 +583,13 @@ int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
             used[best] = true;
             const int lo = ft[best].shift < ft[a].shift ? best : a, hi = lo == a ? best : a;
             e = add(ft[lo], ft[lo].shift, ft[hi].shift - ft[lo].shift);
-            for (int c = 0; c < 8; ++c) { src.tap[e][0][c] = (int8_t)ft[lo].tap[c]; src.tap[e][1][c] = (int8_t)ft[hi].tap[c]; }
+            for (int c = 0; c < 12; ++c) { src.tap[e][0][c] = (int8_t)ft[lo].tap[c]; src.tap[e][1][c] = (int8_t)ft[hi].tap[c]; }
         } else if (ft[a].shift > 0) {      // lone tap: zero weights on the row before it
             e = add(ft[a], ft[a].shift - 1, 1);
-            for (int c = 0; c < 8; ++c) src.tap[e][1][c] = (int8_t)ft[a].tap[c];
+            for (int c = 0; c < 12; ++c) src.tap[e][1][c] = (int8_t)ft[a].tap[c];
         } else {                            // lone tap at shift 0: zero weights on the row after it
             e = add(ft[a], 0, 1);
-            for (int c = 0; c < 8; ++c) src.tap[e][0][c] = (int8_t)ft[a].tap[c];
+            for (int c = 0; c < 12; ++c) src.tap[e][0][c] = (int8_t)ft[a].tap[c];
         }
         src.cib[e][0] = 0; src.cib[e][1] = 0;
     }
@@ -533,8 +610,9 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     p.sps = p.mode == MODE_S2 ? 2 : 1;
     p.live = p.mode == MODE_T2 ? 2 : 3;
     p.groups = 1;
+    p.kdfold = kdfold_of(d) ? 1 : 0;
     // ring depth = live slots + the slots of one step prefetched while the current step computes
-    p.stages = p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 5);
+    p.stages = p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 5));
     p.nentries = build_program(d, p, pl.src);
     p.btile_bytes = (uint32_t)p.kchunks * p.N * 16;
     int max_reach = 0;   // furthest row an A descriptor touches beyond its 128-row window
@@ -547,7 +625,7 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     const char* force = getenv("MVS_TC_NM");          // test knob: force the M-tile count (when it fits)
     const int forced = force ? atoi(force) : 0;
     for (int nM = 4; nM >= 1 && !found; --nM) {
-        if (2 * p.groups * nM * p.N > 512) continue;
+        if ((p.kdfold ? nM * kAccRing * kPG : 2 * p.groups * nM * p.N) > 512) continue;
         if (forced >= 1 && forced <= 4 && nM > forced) continue;
         p.nM = nM; p.TH = 4 * nM; p.PH = p.TH + halo;
         const int rows = max(nM * 128 + max_reach + 1, p.PH * kPW);
@@ -567,12 +645,13 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     }
     if (!found) return false;
     uint32_t cols = 32;
-    while ((int)cols < 2 * p.groups * p.nM * p.N) cols <<= 1;
+    while ((int)cols < (p.kdfold ? p.nM * kAccRing * kPG : 2 * p.groups * p.nM * p.N)) cols <<= 1;
     p.tmem_cols = cols;
     // depth segments: enough CTAs for >= ~3 waves of 148 SMs, but >= 4 steps each (halo slots are reloaded per segment)
     const int64_t tiles = (int64_t)p.B * p.nwt * p.nht;
     int LD = p.Dt;
-    while (LD > 4 && tiles * ((p.Dt + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
+    const int min_ld = p.kdfold ? 8 : 4;   // the kd-folded program pays two extra input planes per item
+    while (LD > min_ld && tiles * ((p.Dt + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
     p.LD = LD; p.nseg = (p.Dt + LD - 1) / LD;
     return tiles * p.nseg < (1ll << 31);
 }

@@ -31,10 +31,22 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("dtype,force_nm", [(torch.float16, 0), (torch.bfloat16, 0), (torch.float16, 4), (torch.float16, 2)])
+CASES += [
+    (8, 8, 1, True, (1, 7, 18, 33)),        # stride-1 ConvTranspose3d with <= 8 output channels (kd-folded, flipped taps)
+    (32, 8, 1, False, (1, 40, 64, 90)),     # several depth segments and (h, w) tiles per persistent CTA
+    (16, 16, 1, False, (2, 24, 40, 70)),
+    (16, 8, 2, True, (1, 20, 24, 50)),
+]
+
+
+@pytest.mark.parametrize("dtype,force_nm,kdfold", [(torch.float16, 0, 1), (torch.bfloat16, 0, 1), (torch.float16, 4, 1), (torch.float16, 2, 1),
+                                                   (torch.float16, 0, 0), (torch.float16, 4, 0)])
 @pytest.mark.parametrize("cin,cout,stride,tr,shape", CASES)
-def test_tc_matches_simt_and_aten(gpu, monkeypatch, cin, cout, stride, tr, shape, dtype, force_nm):
+def test_tc_matches_simt_and_aten(gpu, monkeypatch, cin, cout, stride, tr, shape, dtype, force_nm, kdfold):
     from ssmvs_b200 import ops
+    if not kdfold and not (stride == 1 and cout <= 8):
+        pytest.skip("MVS_TC_KDFOLD only changes stride-1 layers with <= 8 output channels")
+    monkeypatch.setenv("MVS_TC_KDFOLD", str(kdfold))       # library test knob: fold the kd taps into N as well (default on)
     if force_nm:
         monkeypatch.setenv("MVS_TC_NM", str(force_nm))     # library test knob: M-tiles per CTA (default: by volume size)
     else:
