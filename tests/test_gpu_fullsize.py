@@ -163,3 +163,26 @@ def test_feature_net_folded_fast_path(gpu):
         assert got.dtype == torch.float16 and got.is_contiguous(memory_format=torch.channels_last)
         assert (got.float() - want).abs().max().item() < 2e-2 * want.abs().max().item()
         assert torch.equal(ops.unpack_c8(ops.pack_c8(got, torch.float16)), got.float())
+
+
+def test_cvpmvsnet_half_precision_volume(gpu):
+    """CVP-MVSNet (coarse sweep + per-pixel refinement levels) with fp16 volumes on the tensor-core path vs fp32 volumes."""
+    from types import SimpleNamespace
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    torch.manual_seed(0)
+    model = CVPMVSNet(SimpleNamespace(nsrc=3, nscale=2, mode="test"))
+    with torch.no_grad():
+        model.cost_reg_refine.prob0.weight.mul_(16.0)
+    model = model.to(gpu.device).eval()
+    inp = gpu.to(synth.cvp_inputs(1, 3, 128, 160, seed=3))
+    args = [inp[k] for k in ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")]
+    with torch.no_grad():
+        model.volume_dtype = torch.float32
+        ref = model(*args)
+        model.volume_dtype = torch.float16
+        got = model(*args)
+    for a, b in zip(got["depth_est_list"], ref["depth_est_list"]):
+        assert torch.isfinite(a).all()
+        assert ((a - b).abs() / b).max().item() < 3e-3
+    assert (got["prob_confidence"] - ref["prob_confidence"]).abs().max().item() < 3e-2
