@@ -302,6 +302,7 @@ def main():
             traffic = json.load(f)
     except Exception:
         traffic = {}
+    traffic = {k: (v * PB if isinstance(v, (int, float)) else v) for k, v in traffic.items()}   # captures are for one item
     wv_gbs = PB * warp_var_bytes(elem) / (stages["warp_var"] * 1e-3) / 1e9
     reg_tfs = PB * REG_FLOPS / (stages["reg3d"] * 1e-3) / 1e12
     conv0_tfs = PB * CONV0_FLOPS / (stages["conv0"] * 1e-3) / 1e12
