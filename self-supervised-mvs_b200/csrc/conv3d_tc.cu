@@ -37,7 +37,7 @@ constexpr int kThreads = 320;     // producer | 4 MMA issuers | weight loader | 
 constexpr int kPW = 32;          // staged tile width (30 positions + halo)
 constexpr int kTW = 30;
 constexpr int kBStages = 16;     // max depth of the weight-tile ring (streaming mode; p.bstages are used)
-constexpr int kMaxStages = 6;    // input-slot ring
+constexpr int kMaxStages = 12;   // max depth of the input-slot ring (p.stages are used)
 constexpr int kMaxEntries = 27;
 constexpr int kAccRing = 4;      // accumulator ring slots of the kd-folded program (output planes in flight)
 constexpr int kPG = 32;          // kd-fold: TMEM columns per output plane (3 kw blocks of 8 + pad; N must be a multiple of 16)
@@ -490,7 +490,7 @@ EncodeTiledFn encode_tiled() {
 }
 
 // ------------------------------------------------------------------------------------------------ tap programs
-struct Plan { TcParams p; TileSrc src; size_t smem; };
+struct Plan { TcParams p; TileSrc src; size_t smem; int stages_chosen; };
 
 int mode_of(const mvs_conv3d_desc* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
 
@@ -632,18 +632,30 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
         p.chunk_bytes = (uint32_t)((rows + 7) / 8 * 8) * 16u;
         p.sub_bytes = p.chunk_bytes * (uint32_t)p.CiB;
         p.slot_bytes = p.sub_bytes * (uint32_t)p.nsub;
-        const size_t ring = (size_t)p.stages * p.slot_bytes;
-        const size_t room = ring + 512 <= (size_t)kSmemLimit ? (size_t)kSmemLimit - ring - 512 : 0;
-        if (room >= all_b) { p.b_resident = 1; p.bstages = 1; pl.smem = ring + all_b + 512; }
+        const int min_stages = p.stages;                       // live slots + one step of prefetch
+        const size_t ring = (size_t)min_stages * p.slot_bytes;
+        const size_t room = ring + 1024 <= (size_t)kSmemLimit ? (size_t)kSmemLimit - ring - 1024 : 0;
+        size_t bbytes;
+        if (room >= all_b) { p.b_resident = 1; p.bstages = 1; bbytes = all_b; }
         else if (room >= 4 * (size_t)p.btile_bytes) {
-            p.b_resident = 0; p.bstages = (int)min((size_t)kBStages, room / p.btile_bytes); pl.smem = ring + (size_t)p.bstages * p.btile_bytes + 512;
+            // streamed weights: half of what is left (at least 4 tiles) for the weight ring, the rest for deeper prefetch
+            p.b_resident = 0; p.bstages = (int)min((size_t)kBStages, max((size_t)4, room / 2 / p.btile_bytes)); bbytes = (size_t)p.bstages * p.btile_bytes;
         } else continue;
+        // The input ring is what hides HBM latency (one slot = one plane of the tile): the kernel was latency-bound with a
+        // single slot in flight per SM (0.8 TB/s), so every byte of shared memory left over goes to more slots in flight.
+        int stages_fit = (int)(((size_t)kSmemLimit - 1024 - bbytes) / p.slot_bytes);
+        if (stages_fit > kMaxStages) stages_fit = kMaxStages;
+        const char* fs = getenv("MVS_TC_STAGES");              // test / tuning knob
+        if (fs && atoi(fs) >= min_stages && atoi(fs) <= stages_fit) stages_fit = atoi(fs);
+        pl.stages_chosen = stages_fit;
+        pl.smem = (size_t)stages_fit * p.slot_bytes + bbytes + 1024;
         p.nwt = (p.Wt + kTW - 1) / kTW;
         p.nht = (p.Ht + p.TH - 1) / p.TH;
         const int64_t tiles_nm = (int64_t)p.B * p.nwt * p.nht;
         found = nM == 1 || nM == forced || tiles_nm * ((p.Dt + 3) / 4) >= 2 * 148;
     }
     if (!found) return false;
+    p.stages = pl.stages_chosen;
     uint32_t cols = 32;
     while ((int)cols < (p.kdfold ? p.nM * kAccRing * kPG : 2 * p.groups * p.nM * p.N)) cols <<= 1;
     p.tmem_cols = cols;
