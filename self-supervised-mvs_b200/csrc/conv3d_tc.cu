@@ -22,18 +22,19 @@
 //                                           8 column blocks = output parities, so each lane stores a 2x2x2 block of voxels.
 //   Cin = 8 layers pair two taps into one K = 16 step: the descriptor's LBO is the row distance between the two taps.
 //
-// Warp roles (320 threads): 0 = TMA producer of input planes (ring over depth); 1..4 = MMA issuers, one elected lane each,
+// Warp roles (448 threads): 0 = TMA producer of input planes (ring over depth); 1..4 = MMA issuers, one elected lane each,
 // issuer k owns the accumulators of M-tile k (these MMAs are only N = 16..64 wide, so ONE issuing thread is the
 // bottleneck: measured 225 cycles per MMA against ~36 cycles of operand reads) and warp 1 also owns TMEM; 5 = weight-tile
-// loader (resident when all tiles fit, else a ring streamed per step); 6..9 = epilogue (tcgen05.ld -> folded-BN affine,
-// ReLU, skip add -> C8 store), double-buffered against the MMAs through TMEM.
+// loader (resident when all tiles fit, else a ring streamed per step); 6..13 = epilogue, two warps per TMEM lane quadrant
+// (tcgen05.ld -> folded-BN affine, ReLU, skip add -> C8 store), double-buffered against the MMAs through TMEM.
 #include "mvs_rt.h"
 #include <cuda.h>
 #include <stdlib.h>
 
 namespace {
 
-constexpr int kThreads = 320;     // producer | 4 MMA issuers | weight loader | 4 epilogue warps
+constexpr int kEpiWarps = 8;      // two warps per TMEM lane quadrant, taking alternate M-tiles
+constexpr int kThreads = (6 + kEpiWarps) * 32;   // producer | 4 MMA issuers | weight loader | epilogue warps
 constexpr int kPW = 32;          // staged tile width (30 positions + halo)
 constexpr int kTW = 30;
 constexpr int kBStages = 16;     // max depth of the weight-tile ring (streaming mode; p.bstages are used)
@@ -42,6 +43,7 @@ constexpr int kMaxEntries = 27;
 constexpr int kAccRing = 4;      // accumulator ring slots of the kd-folded program (output planes in flight)
 constexpr int kPG = 32;          // kd-fold: TMEM columns per output plane (3 kw blocks of 8 + pad; N must be a multiple of 16)
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kTail = 2048;      // barriers + TMEM slot + affine table behind the rings
 enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2 };
 
 struct Entry {
@@ -150,8 +152,8 @@ struct TensorMaps { CUtensorMap m[4]; };
 //   NOV = 8 : transposed stride 2, column block ov = output parity (pd, ph, pw) of the 2x2x2 voxel block of this input voxel
 //   KWFOLD  : stride 1, column blocks 0,1,2 hold the taps reading input column (lane): output j = blk0[j] + blk1[j+1] + blk2[j+2]
 template <typename T, int NOV, bool KWFOLD>
-__device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t trow, bool valid, int b, int od0, int oh0, int ow0, int CoB,
-                                              int64_t HWo) {
+__device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
+                                              int oh0, int ow0, int CoB, int64_t HWo) {
     constexpr int NLD = KWFOLD ? 3 : NOV;
     for (int cb = 0; cb < CoB; ++cb) {
         int64_t off[NOV];
@@ -183,8 +185,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t trow, 
             if (!valid) continue;
             if (p.Cout == 1) {
                 float x = o[0];
-                if (p.scale) x *= __ldg(p.scale);
-                if (p.shift) x += __ldg(p.shift);
+                x = x * aff[0] + aff[64];
                 if (p.relu) x = fmaxf(x, 0.f);
                 if (p.skip) x += __uint_as_float(sk[ov].x);
                 reinterpret_cast<float*>(p.y)[off[ov]] = x;
@@ -194,8 +195,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t trow, 
             for (int k = 0; k < 8; ++k) {
                 const int co = cb * 8 + k;
                 float x = o[k];
-                if (p.scale) x *= __ldg(p.scale + co);
-                if (p.shift) x += __ldg(p.shift + co);
+                x = x * aff[co] + aff[64 + co];
                 if (p.relu) x = fmaxf(x, 0.f);
                 o[k] = x;
             }
@@ -226,6 +226,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     uint64_t* acc_full = b_empty + kBStages;       // [kAccRing]  (2 are used unless kd-folded)
     uint64_t* acc_empty = acc_full + kAccRing;     // [kAccRing]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccRing);
+    float* aff = reinterpret_cast<float*>(tmem_slot + 4);    // [2][64] folded-BN scale / shift (1 / 0 when absent)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTA: work items (tile x depth segment) are dealt round-robin; every role walks the same list, and the
@@ -246,9 +247,13 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         // every issuer commits its own MMAs, so the barriers the MMAs release count one arrival per issuer
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(slot_full + i, 1); mbar_init(slot_empty + i, (uint32_t)p.nM); }
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, (uint32_t)p.nM); }
-        for (int i = 0; i < kAccRing; ++i) { mbar_init(acc_full + i, (uint32_t)p.nM); mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < kAccRing; ++i) { mbar_init(acc_full + i, (uint32_t)p.nM); mbar_init(acc_empty + i, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+        const int co = c & 63;
+        aff[c] = c < 64 ? ((p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f) : ((p.shift && co < p.Cout) ? __ldg(p.shift + co) : 0.f);
     }
     if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -396,7 +401,8 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         }
     } else {
         // ===================== epilogue: TMEM -> affine / ReLU / skip -> C8 store =====================
-        const int quad = warp & 3;                 // warps 6..9 -> quads 2,3,0,1; TMEM lanes [32 quad, 32 quad + 32) belong to this warp
+        const int quad = warp & 3;                 // TMEM lanes [32 quad, 32 quad + 32) belong to this warp
+        const int mpar = (warp - 6) >> 2;          // the two warps of a quadrant take alternate M-tiles
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
         const bool kwfold = p.mode == MODE_S1;
@@ -409,12 +415,12 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     const int rsl = I % kAccRing;
                     mbar_wait(acc_full + rsl, (I / kAccRing) & 1);
                     tc_fence_after();
-                    for (int m = 0; m < p.nM; ++m) {
+                    for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
                         const int r = m * 128 + quad * 32 + lane;
                         const int hh = r >> 5, ww = r & 31;
                         const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
                         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((m * kAccRing + rsl) * kPG);
-                        epilogue_rows<T, 1, true>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                        epilogue_rows<T, 1, true>(p, aff, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -424,14 +430,14 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 const int buf = I & 1;
                 mbar_wait(acc_full + buf, (I >> 1) & 1);
                 tc_fence_after();
-                for (int m = 0; m < p.nM; ++m) {
+                for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
                     const int r = m * 128 + quad * 32 + lane;
                     const int hh = r >> 5, ww = r & 31;     // a warp is one h-row of the tile: lane = w position
                     const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
                     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N);
-                    if (p.mode == MODE_T2) epilogue_rows<T, 8, false>(p, trow, valid, b, 2 * (d0 + i), 2 * (h0 + hh), 2 * (w0 + ww), CoB, HWo);
-                    else if (kwfold) epilogue_rows<T, 1, true>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
-                    else epilogue_rows<T, 1, false>(p, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                    if (p.mode == MODE_T2) epilogue_rows<T, 8, false>(p, aff, trow, valid, b, 2 * (d0 + i), 2 * (h0 + hh), 2 * (w0 + ww), CoB, HWo);
+                    else if (kwfold) epilogue_rows<T, 1, true>(p, aff, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                    else epilogue_rows<T, 1, false>(p, aff, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -634,7 +640,7 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
         p.slot_bytes = p.sub_bytes * (uint32_t)p.nsub;
         const int min_stages = p.stages;                       // live slots + one step of prefetch
         const size_t ring = (size_t)min_stages * p.slot_bytes;
-        const size_t room = ring + 1024 <= (size_t)kSmemLimit ? (size_t)kSmemLimit - ring - 1024 : 0;
+        const size_t room = ring + kTail <= (size_t)kSmemLimit ? (size_t)kSmemLimit - ring - kTail : 0;
         size_t bbytes;
         if (room >= all_b) { p.b_resident = 1; p.bstages = 1; bbytes = all_b; }
         else if (room >= 4 * (size_t)p.btile_bytes) {
@@ -643,12 +649,12 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
         } else continue;
         // The input ring is what hides HBM latency (one slot = one plane of the tile): the kernel was latency-bound with a
         // single slot in flight per SM (0.8 TB/s), so every byte of shared memory left over goes to more slots in flight.
-        int stages_fit = (int)(((size_t)kSmemLimit - 1024 - bbytes) / p.slot_bytes);
+        int stages_fit = (int)(((size_t)kSmemLimit - kTail - bbytes) / p.slot_bytes);
         if (stages_fit > kMaxStages) stages_fit = kMaxStages;
         const char* fs = getenv("MVS_TC_STAGES");              // test / tuning knob
         if (fs && atoi(fs) >= min_stages && atoi(fs) <= stages_fit) stages_fit = atoi(fs);
         pl.stages_chosen = stages_fit;
-        pl.smem = (size_t)stages_fit * p.slot_bytes + bbytes + 1024;
+        pl.smem = (size_t)stages_fit * p.slot_bytes + bbytes + kTail;
         p.nwt = (p.Wt + kTW - 1) / kTW;
         p.nht = (p.Ht + p.TH - 1) / p.TH;
         const int64_t tiles_nm = (int64_t)p.B * p.nwt * p.nht;
