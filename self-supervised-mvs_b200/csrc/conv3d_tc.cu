@@ -43,7 +43,7 @@ constexpr int kMaxEntries = 27;
 constexpr int kAccRing = 4;      // accumulator ring slots of the kd-folded program (output planes in flight)
 constexpr int kPG = 32;          // kd-fold: TMEM columns per output plane (3 kw blocks of 8 + pad; N must be a multiple of 16)
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kTail = 2048;      // barriers + TMEM slot + affine table behind the rings
+constexpr int kTail = 1152;      // barriers (512 B) + TMEM slot (16 B) + affine table (512 B) behind the rings
 enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2 };
 
 struct Entry {
@@ -618,7 +618,7 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     p.groups = 1;
     p.kdfold = kdfold_of(d) ? 1 : 0;
     // ring depth = live slots + the slots of one step prefetched while the current step computes
-    p.stages = p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 5));
+    p.stages = p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 4));   // minimum; make_plan adds what fits
     p.nentries = build_program(d, p, pl.src);
     p.btile_bytes = (uint32_t)p.kchunks * p.N * 16;
     int max_reach = 0;   // furthest row an A descriptor touches beyond its 128-row window
