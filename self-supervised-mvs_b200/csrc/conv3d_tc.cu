@@ -43,7 +43,7 @@ constexpr int kMaxEntries = 27;
 constexpr int kAccRing = 4;      // accumulator ring slots of the kd-folded program (output planes in flight)
 constexpr int kPG = 32;          // kd-fold: TMEM columns per output plane (3 kw blocks of 8 + pad; N must be a multiple of 16)
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kTail = 1152;      // barriers (512 B) + TMEM slot (16 B) + affine table (512 B) behind the rings
+constexpr int kTail = 1536;      // barriers (512 B) + TMEM slot (16 B) + affine table (512 B) + entry table (432 B) behind the rings
 enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2 };
 
 struct Entry {
@@ -227,6 +227,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     uint64_t* acc_empty = acc_full + kAccRing;     // [kAccRing]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccRing);
     float* aff = reinterpret_cast<float*>(tmem_slot + 4);    // [2][64] folded-BN scale / shift (1 / 0 when absent)
+    uint4* etab = reinterpret_cast<uint4*>(aff + 128);       // [kMaxEntries] decoded tap program for the MMA issuers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTA: work items (tile x depth segment) are dealt round-robin; every role walks the same list, and the
@@ -254,6 +255,11 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     for (int c = threadIdx.x; c < 128; c += blockDim.x) {
         const int co = c & 63;
         aff[c] = c < 64 ? ((p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f) : ((p.shift && co < p.Cout) ? __ldg(p.shift + co) : 0.f);
+    }
+    if ((int)threadIdx.x < p.nentries) {
+        const Entry en = p.prog[threadIdx.x];
+        etab[threadIdx.x] = make_uint4((uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16),
+                                       (en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16, (uint32_t)en.slot_off, (uint32_t)en.first);
     }
     if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -309,94 +315,118 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         }
     } else if (warp >= 1 && warp <= 4) {
         // ===================== MMA issuers: issuer m accumulates M-tile m =====================
+        // One elected lane issues; a lone thread can start a tcgen05.mma every ~77 cycles and the issue loop was the bottleneck
+        // when it carried the tap decode (85 instructions per MMA), so everything per-entry comes from the shared-memory table
+        // `etab` built before the roles split, ring positions advance by compare-and-subtract, and a K step is two adds.
         const int m = warp - 1;
         if (lane == 0 && m < p.nM) {
             // instruction descriptor: D = f32, A/B = f16|bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
+            const uint32_t idesc = idesc0 | ((uint32_t)(p.N >> 3) << 17);
             const uint32_t slots_addr = smem_u32(slots) + (uint32_t)m * 128u * 16u, b_addr = smem_u32(bsm);
             // descriptor words: lo = start >> 4 | (LBO >> 4) << 16 ; hi = SBO >> 4 (128 B) | version 1 at bit 46
             const uint64_t desc_hi = (uint64_t)(8u | (1u << 14)) << 32;
             const uint32_t a_kstep = (2u * p.chunk_bytes) >> 4, b_kstep = 2u * (uint32_t)p.N, b_lbo = (uint32_t)p.N << 16;
+            const uint32_t btile16 = p.btile_bytes >> 4;
+            const int nent = p.nentries, ksteps = p.ksteps, stages = p.stages;
             if (p.b_resident) mbar_wait(b_full, 0);
             if (p.kdfold) {
                 // ---- kd-folded stride-1 program (Cout <= 8): a step is an INPUT plane p; its kh entries multiply all 9 (kd, kw)
                 // taps at once: N = 3 plane groups of kPG columns, for the output planes p-1, p, p+1, which live in a ring of
                 // kAccRing accumulator slots per M-tile.  Plane p+1 is first touched here (overwrite), so the first MMA of a step is
                 // split by flag, and any MMA is split where the three slots wrap around the ring.
-                const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
                 const uint32_t kb_lbo = (uint32_t)(3 * kPG) << 16, kb_kstep = 2u * 3u * kPG;
-                int J = 0, Qb = 0;            // input slots consumed, output planes started (running over items)
+                const uint32_t d_m = tmem_base + (uint32_t)(m * kAccRing * kPG);
+                int st = 0, sph = 0, Qb = 0;   // ring stage / phase of the next input slot, output planes started (running over items)
                 for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
                     const Work k = decode(t);
-                    for (int j = 0; j < k.nslots; ++j, ++J) {
-                        mbar_wait(slot_full + (J % p.stages), (J / p.stages) & 1);
-                        if (j < k.nsteps) { const int q = Qb + j; mbar_wait(acc_empty + (q % kAccRing), ((q / kAccRing) & 1) ^ 1); }
+                    for (int j = 0; j < k.nslots; ++j) {
+                        mbar_wait(slot_full + st, (uint32_t)sph);
+                        if (j < k.nsteps) { const int q = Qb + j; mbar_wait(acc_empty + (q & (kAccRing - 1)), ((q / kAccRing) & 1) ^ 1); }
                         tc_fence_after();
-                        int rs[3]; bool ok[3];
-                        for (int g = 0; g < 3; ++g) { const int i = j - 2 + g; ok[g] = i >= 0 && i < k.nsteps; rs[g] = (Qb + (ok[g] ? i : 0)) % kAccRing; }
-                        const uint32_t a_slot = slots_addr + (uint32_t)(J % p.stages) * p.slot_bytes;
-                        for (int e = 0; e < p.nentries; ++e) {
-                            const Entry en = p.prog[e];
-                            const uint32_t a_addr = a_slot + (uint32_t)((int)en.row_shift * 16);
-                            uint32_t a_lo = (a_addr >> 4) | ((en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16);
-                            uint32_t b_lo = ((b_addr + (uint32_t)e * p.btile_bytes) >> 4) | kb_lbo;
-                            for (int ks = 0; ks < p.ksteps; ++ks, a_lo += a_kstep, b_lo += kb_kstep) {
-                                const bool fresh2 = (e == 0 && ks == 0);      // group 2 (plane p+1) is overwritten by the step's first MMA
-                                int g = 0;
-                                while (g < 3) {
-                                    if (!ok[g]) { ++g; continue; }
-                                    int cnt = 1;
-                                    const bool fresh = fresh2 && g == 2;
-                                    while (g + cnt < 3 && ok[g + cnt] && rs[g + cnt] == rs[g + cnt - 1] + 1 && !(fresh2 && g + cnt == 2)) ++cnt;
-                                    umma_f16(tmem_base + (uint32_t)((m * kAccRing + rs[g]) * kPG), desc_hi | a_lo, desc_hi | (b_lo + (uint32_t)(g * kPG)),
-                                             idesc0 | ((uint32_t)((cnt * kPG) >> 3) << 17), fresh ? 0u : 1u);
-                                    g += cnt;
-                                }
+                        // MMA segments of this step, [TMEM address, B row offset, instruction descriptor]: one list for the step's first
+                        // MMA (plane group 2 = output p+1 is overwritten there, so it stands alone) and one for all later MMAs
+                        // (groups merge wherever their ring slots are adjacent)
+                        uint32_t sd[2][3], sb[2][3], si[2][3]; int ns[2] = {0, 0};
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            int g = 0;
+                            while (g < 3) {
+                                const int i0 = j - 2 + g;
+                                if (i0 < 0 || i0 >= k.nsteps) { ++g; continue; }
+                                const int r0 = (Qb + i0) & (kAccRing - 1);
+                                int cnt = 1;
+                                while (g + cnt < (v == 0 ? 2 : 3) && g < (v == 0 ? 2 : 3) && (j - 2 + g + cnt) < k.nsteps && r0 + cnt < kAccRing) ++cnt;
+                                sd[v][ns[v]] = d_m + (uint32_t)(r0 * kPG); sb[v][ns[v]] = (uint32_t)(g * kPG);
+                                si[v][ns[v]] = idesc0 | ((uint32_t)((cnt * kPG) >> 3) << 17);
+                                ++ns[v]; g += cnt;
                             }
                         }
-                        umma_commit(slot_empty + (J % p.stages));
-                        if (j >= 2) umma_commit(acc_full + ((Qb + j - 2) % kAccRing));      // output plane j-2 has all three contributions
+                        const bool g2_valid = j < k.nsteps;      // output plane p+1 = item-local index j exists
+                        const uint32_t a_slot = slots_addr + (uint32_t)st * p.slot_bytes;
+                        uint32_t b_ent = (b_addr >> 4) | kb_lbo;
+                        for (int e = 0; e < nent; ++e, b_ent += btile16) {
+                            const uint4 en = etab[e];                      // x = A byte offset, y = LBO field, z = slot, w = first
+                            uint32_t a_lo = ((a_slot + en.x) >> 4) | en.y, b_lo = b_ent;
+                            for (int ks = 0; ks < ksteps; ++ks, a_lo += a_kstep, b_lo += kb_kstep) {
+                                const int v = (e | ks) == 0 ? 0 : 1;
+#pragma unroll
+                                for (int sg = 0; sg < 3; ++sg)
+                                    if (sg < ns[v]) {
+                                        // in the first-MMA list the last segment is plane group 2 (when that plane exists): overwrite
+                                        const bool fresh = v == 0 && g2_valid && sg == ns[0] - 1;
+                                        umma_f16(sd[v][sg], desc_hi | a_lo, desc_hi | (b_lo + sb[v][sg]), si[v][sg], fresh ? 0u : 1u);
+                                    }
+                            }
+                        }
+                        umma_commit(slot_empty + st);
+                        if (j >= 2) umma_commit(acc_full + ((Qb + j - 2) & (kAccRing - 1)));      // output plane j-2 has all three contributions
+                        if (++st == stages) { st = 0; sph ^= 1; }
                     }
                     Qb += k.nsteps;
                 }
-            }
-            int Jb = 0, I = 0, u = 0;        // first slot of the item, steps done, weight tiles consumed (all running over items)
-            for (int t = blockIdx.x; t < p.nwork && !p.kdfold; t += gridDim.x) {
-                const Work k = decode(t);
-                for (int i = 0; i < k.nsteps; ++i, ++I) {
-                    const int buf = I & 1;
-                    mbar_wait(acc_empty + buf, ((I >> 1) & 1) ^ 1);
-                    const int jlo = Jb + i * p.sps, jhi = jlo + p.live;             // live slots [jlo, jhi)
-                    for (int j = (i == 0 ? jlo : jhi - p.sps); j < jhi; ++j) mbar_wait(slot_full + (j % p.stages), (j / p.stages) & 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
-                    for (int e = 0; e < p.nentries; ++e, ++u) {
-                        const Entry en = p.prog[e];
-                        uint32_t btile;
-                        if (p.b_resident) {
-                            btile = b_addr + (uint32_t)e * p.btile_bytes;
-                        } else {
-                            const int st = u % p.bstages;
-                            mbar_wait(b_full + st, (u / p.bstages) & 1);
-                            tc_fence_after();
-                            btile = b_addr + (uint32_t)st * p.btile_bytes;
+            } else {
+                int st0 = 0, ph0 = 0;          // ring stage / phase of the first live slot of the current step
+                int I = 0, bst = 0, bph = 0;   // steps done; weight ring position (streaming)
+                for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
+                    const Work k = decode(t);
+                    for (int i = 0; i < k.nsteps; ++i, ++I) {
+                        const int buf = I & 1;
+                        mbar_wait(acc_empty + buf, ((I >> 1) & 1) ^ 1);
+                        // live slots: stages st0, st0+1, .. (mod stages); only the newest `sps` (all of them at i = 0) can be unready
+                        uint32_t slot_a[3];
+                        {
+                            int s2 = st0, p2 = ph0;
+                            for (int l = 0; l < p.live; ++l) {
+                                if (i == 0 || l >= p.live - p.sps) mbar_wait(slot_full + s2, (uint32_t)p2);
+                                slot_a[l] = slots_addr + (uint32_t)s2 * p.slot_bytes;
+                                if (++s2 == stages) { s2 = 0; p2 ^= 1; }
+                            }
                         }
-                        const uint32_t a_addr = slots_addr + (uint32_t)((jlo + en.slot_off) % p.stages) * p.slot_bytes +
-                                                (uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16);
-                        uint32_t a_lo = (a_addr >> 4) | ((en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16);
-                        uint32_t b_lo = (btile >> 4) | b_lbo;
-                        uint32_t acc = en.first ? 0u : 1u;
-                        for (int ks = 0; ks < p.ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
-                            umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
-                        if (!p.b_resident) umma_commit(b_empty + (u % p.bstages));
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
+                        uint32_t b_ent = (b_addr >> 4) | b_lbo;
+                        for (int e = 0; e < nent; ++e, b_ent += btile16) {
+                            const uint4 en = etab[e];
+                            uint32_t b_lo = b_ent;
+                            if (!p.b_resident) {
+                                mbar_wait(b_full + bst, (uint32_t)bph);
+                                tc_fence_after();
+                                b_lo = ((b_addr + (uint32_t)bst * p.btile_bytes) >> 4) | b_lbo;
+                            }
+                            uint32_t a_lo = ((slot_a[en.z] + en.x) >> 4) | en.y;
+                            uint32_t acc = en.w ? 0u : 1u;
+                            for (int ks = 0; ks < ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
+                                umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
+                            if (!p.b_resident) { umma_commit(b_empty + bst); if (++bst == p.bstages) { bst = 0; bph ^= 1; } }
+                        }
+                        // slots no later step of this item reads retire with these MMAs (all remaining ones after the last step)
+                        const int nrel = (i == k.nsteps - 1) ? p.live : p.sps;
+                        for (int l = 0; l < nrel; ++l) { umma_commit(slot_empty + st0); if (++st0 == stages) { st0 = 0; ph0 ^= 1; } }
+                        umma_commit(acc_full + buf);
                     }
-                    // slots no later step of this item reads retire with these MMAs (all remaining ones after the last step)
-                    const int jrel = (i == k.nsteps - 1) ? jhi : jlo + p.sps;
-                    for (int j = jlo; j < jrel; ++j) umma_commit(slot_empty + (j % p.stages));
-                    umma_commit(acc_full + buf);
                 }
-                Jb += k.nslots;
             }
         }
     } else {
