@@ -113,6 +113,22 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-uniform callers: every lane executes the call, one elected lane issues.  Keeping the issue loop warp-uniform lets the
+// compiler hold descriptors in uniform registers instead of moving them there (R2UR) for every tcgen05.mma.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -145,6 +161,14 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
 }
 
 struct TensorMaps { CUtensorMap m[4]; };
+
+#ifdef MVS_TC_TRACE
+// Debug build only (tools/tc_trace.py): CTA 0 records clock64() at pipeline events; 8 lanes x 1024 slots.
+__device__ long long g_trace[8][1024];
+#define TRACE(lane_id, idx) do { if (blockIdx.x == 0 && (idx) < 1024) g_trace[lane_id][idx] = clock64(); } while (0)
+#else
+#define TRACE(lane_id, idx) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------ epilogue of one M-tile row
 // One accumulator row (= one lane) -> NOV output voxels x CoB channel blocks.  Every global read (skip tensor) and every
@@ -289,6 +313,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                             else if (p.mode == MODE_T2) tma_load_4d(&maps.m[0], slot_full + st, dst, k.w0 * 8, k.h0, k.d0 + j, k.b * p.CiB + cb);
                             else tma_load_5d(&maps.m[s], slot_full + st, dst, 0, k.w0 - 1, k.h0 - 1, 2 * k.d0 - 1 + j, k.b * p.CiB + cb);
                         }
+                    TRACE(0, J);
                 }
             }
         }
@@ -315,11 +340,13 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         }
     } else if (warp >= 1 && warp <= 4) {
         // ===================== MMA issuers: issuer m accumulates M-tile m =====================
-        // One elected lane issues; a lone thread can start a tcgen05.mma every ~77 cycles and the issue loop was the bottleneck
-        // when it carried the tap decode (85 instructions per MMA), so everything per-entry comes from the shared-memory table
-        // `etab` built before the roles split, ring positions advance by compare-and-subtract, and a K step is two adds.
-        const int m = warp - 1;
-        if (lane == 0 && m < p.nM) {
+        // The whole warp runs this (warp-uniform) code and one elected lane issues each tcgen05.mma / commit.  Measured on the
+        // way here: a step's issue loop took ~4500 cycles per issuer when one lane ran it with the tap decode, local-memory
+        // segment arrays and register->uniform moves per operand, against ~1800 cycles of operand fetch; so per-entry data
+        // comes decoded from shared memory (`etab`), ring positions advance by compare-and-subtract, the (at most 3) column
+        // segments of a kd-folded step live in scalars, and a K step is two adds.
+        const int m = __shfl_sync(0xffffffffu, warp - 1, 0);
+        if (m < p.nM) {
             // instruction descriptor: D = f32, A/B = f16|bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t fmt = p.is_bf16 ? 1u : 0u;
             const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
@@ -334,54 +361,53 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
             if (p.kdfold) {
                 // ---- kd-folded stride-1 program (Cout <= 8): a step is an INPUT plane p; its kh entries multiply all 9 (kd, kw)
                 // taps at once: N = 3 plane groups of kPG columns, for the output planes p-1, p, p+1, which live in a ring of
-                // kAccRing accumulator slots per M-tile.  Plane p+1 is first touched here (overwrite), so the first MMA of a step is
-                // split by flag, and any MMA is split where the three slots wrap around the ring.
+                // kAccRing accumulator slots per M-tile.  Plane p+1 is first touched here (overwrite), so in the step's first MMA
+                // group 2 stands alone, and groups split wherever their slots wrap around the ring.
                 const uint32_t kb_lbo = (uint32_t)(3 * kPG) << 16, kb_kstep = 2u * 3u * kPG;
                 const uint32_t d_m = tmem_base + (uint32_t)(m * kAccRing * kPG);
+                const uint32_t id1 = idesc0 | ((uint32_t)(kPG >> 3) << 17), id2 = idesc0 | ((uint32_t)((2 * kPG) >> 3) << 17),
+                               id3 = idesc0 | ((uint32_t)((3 * kPG) >> 3) << 17);
                 int st = 0, sph = 0, Qb = 0;   // ring stage / phase of the next input slot, output planes started (running over items)
                 for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
                     const Work k = decode(t);
                     for (int j = 0; j < k.nslots; ++j) {
                         mbar_wait(slot_full + st, (uint32_t)sph);
+                        if (m == 0 && lane == 0) TRACE(1, Qb + 2 * (t / gridDim.x) + j);
                         if (j < k.nsteps) { const int q = Qb + j; mbar_wait(acc_empty + (q & (kAccRing - 1)), ((q / kAccRing) & 1) ^ 1); }
+                        if (m == 0 && lane == 0) TRACE(2, Qb + 2 * (t / gridDim.x) + j);
                         tc_fence_after();
-                        // MMA segments of this step, [TMEM address, B row offset, instruction descriptor]: one list for the step's first
-                        // MMA (plane group 2 = output p+1 is overwritten there, so it stands alone) and one for all later MMAs
-                        // (groups merge wherever their ring slots are adjacent)
-                        uint32_t sd[2][3], sb[2][3], si[2][3]; int ns[2] = {0, 0};
-#pragma unroll
-                        for (int v = 0; v < 2; ++v) {
-                            int g = 0;
-                            while (g < 3) {
-                                const int i0 = j - 2 + g;
-                                if (i0 < 0 || i0 >= k.nsteps) { ++g; continue; }
-                                const int r0 = (Qb + i0) & (kAccRing - 1);
-                                int cnt = 1;
-                                while (g + cnt < (v == 0 ? 2 : 3) && g < (v == 0 ? 2 : 3) && (j - 2 + g + cnt) < k.nsteps && r0 + cnt < kAccRing) ++cnt;
-                                sd[v][ns[v]] = d_m + (uint32_t)(r0 * kPG); sb[v][ns[v]] = (uint32_t)(g * kPG);
-                                si[v][ns[v]] = idesc0 | ((uint32_t)((cnt * kPG) >> 3) << 17);
-                                ++ns[v]; g += cnt;
-                            }
-                        }
-                        const bool g2_valid = j < k.nsteps;      // output plane p+1 = item-local index j exists
+                        // plane groups g = 0,1,2 <-> item-local output planes j-2, j-1, j; ring slots r0, r0+1, r0+2 (mod kAccRing)
+                        const bool v0 = j >= 2, v1 = j >= 1 && j - 1 < k.nsteps, v2 = j < k.nsteps;
+                        const int r0 = (Qb + j - 2) & (kAccRing - 1), r1 = (r0 + 1) & (kAccRing - 1), r2 = (r0 + 2) & (kAccRing - 1);
+                        const bool c01 = v0 && v1 && r1 == r0 + 1, c12 = v1 && v2 && r2 == r1 + 1;   // adjacent in TMEM (no ring wrap)
+                        const uint32_t dg0 = d_m + (uint32_t)(r0 * kPG), dg1 = d_m + (uint32_t)(r1 * kPG), dg2 = d_m + (uint32_t)(r2 * kPG);
                         const uint32_t a_slot = slots_addr + (uint32_t)st * p.slot_bytes;
                         uint32_t b_ent = (b_addr >> 4) | kb_lbo;
+                        bool first = true;
                         for (int e = 0; e < nent; ++e, b_ent += btile16) {
-                            const uint4 en = etab[e];                      // x = A byte offset, y = LBO field, z = slot, w = first
+                            const uint4 en = etab[e];                      // x = A byte offset, y = LBO field
                             uint32_t a_lo = ((a_slot + en.x) >> 4) | en.y, b_lo = b_ent;
-                            for (int ks = 0; ks < ksteps; ++ks, a_lo += a_kstep, b_lo += kb_kstep) {
-                                const int v = (e | ks) == 0 ? 0 : 1;
-#pragma unroll
-                                for (int sg = 0; sg < 3; ++sg)
-                                    if (sg < ns[v]) {
-                                        // in the first-MMA list the last segment is plane group 2 (when that plane exists): overwrite
-                                        const bool fresh = v == 0 && g2_valid && sg == ns[0] - 1;
-                                        umma_f16(sd[v][sg], desc_hi | a_lo, desc_hi | (b_lo + sb[v][sg]), si[v][sg], fresh ? 0u : 1u);
-                                    }
+                            for (int ks = 0; ks < ksteps; ++ks, a_lo += a_kstep, b_lo += kb_kstep, first = false) {
+                                const uint64_t ad = desc_hi | a_lo;
+                                const bool join12 = c12 && !first;          // group 2 may ride along once it has been overwritten
+                                // segment starting at group 0
+                                if (v0) {
+                                    if (c01 && join12) umma_f16_elect(dg0, ad, desc_hi | b_lo, id3, 1u);
+                                    else if (c01) umma_f16_elect(dg0, ad, desc_hi | b_lo, id2, 1u);
+                                    else umma_f16_elect(dg0, ad, desc_hi | b_lo, id1, 1u);
+                                }
+                                // segment starting at group 1 (when it did not ride with group 0)
+                                if (v1 && !c01) {
+                                    if (join12) umma_f16_elect(dg1, ad, desc_hi | (b_lo + kPG), id2, 1u);
+                                    else umma_f16_elect(dg1, ad, desc_hi | (b_lo + kPG), id1, 1u);
+                                }
+                                // group 2 alone: always in the step's first MMA (overwrite), later only across a ring wrap
+                                if (v2 && !join12) umma_f16_elect(dg2, ad, desc_hi | (b_lo + 2 * kPG), id1, first ? 0u : 1u);
                             }
                         }
-                        umma_commit(slot_empty + st);
-                        if (j >= 2) umma_commit(acc_full + ((Qb + j - 2) & (kAccRing - 1)));      // output plane j-2 has all three contributions
+                        umma_commit_elect(slot_empty + st);
+                        if (j >= 2) umma_commit_elect(acc_full + ((Qb + j - 2) & (kAccRing - 1)));      // output plane j-2 has all three contributions
+                        if (m == 0 && lane == 0) TRACE(3, Qb + 2 * (t / gridDim.x) + j);
                         if (++st == stages) { st = 0; sph ^= 1; }
                     }
                     Qb += k.nsteps;
@@ -395,12 +421,13 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                         const int buf = I & 1;
                         mbar_wait(acc_empty + buf, ((I >> 1) & 1) ^ 1);
                         // live slots: stages st0, st0+1, .. (mod stages); only the newest `sps` (all of them at i = 0) can be unready
-                        uint32_t slot_a[3];
+                        uint32_t sa0 = 0, sa1 = 0, sa2 = 0;
                         {
                             int s2 = st0, p2 = ph0;
                             for (int l = 0; l < p.live; ++l) {
                                 if (i == 0 || l >= p.live - p.sps) mbar_wait(slot_full + s2, (uint32_t)p2);
-                                slot_a[l] = slots_addr + (uint32_t)s2 * p.slot_bytes;
+                                const uint32_t sa = slots_addr + (uint32_t)s2 * p.slot_bytes;
+                                if (l == 0) sa0 = sa; else if (l == 1) sa1 = sa; else sa2 = sa;
                                 if (++s2 == stages) { s2 = 0; p2 ^= 1; }
                             }
                         }
@@ -408,23 +435,24 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                         const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
                         uint32_t b_ent = (b_addr >> 4) | b_lbo;
                         for (int e = 0; e < nent; ++e, b_ent += btile16) {
-                            const uint4 en = etab[e];
+                            const uint4 en = etab[e];                      // x = A byte offset, y = LBO field, z = slot, w = first
                             uint32_t b_lo = b_ent;
                             if (!p.b_resident) {
                                 mbar_wait(b_full + bst, (uint32_t)bph);
                                 tc_fence_after();
                                 b_lo = ((b_addr + (uint32_t)bst * p.btile_bytes) >> 4) | b_lbo;
                             }
-                            uint32_t a_lo = ((slot_a[en.z] + en.x) >> 4) | en.y;
+                            const uint32_t sa = en.z == 0 ? sa0 : (en.z == 1 ? sa1 : sa2);
+                            uint32_t a_lo = ((sa + en.x) >> 4) | en.y;
                             uint32_t acc = en.w ? 0u : 1u;
                             for (int ks = 0; ks < ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
-                                umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
-                            if (!p.b_resident) { umma_commit(b_empty + bst); if (++bst == p.bstages) { bst = 0; bph ^= 1; } }
+                                umma_f16_elect(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
+                            if (!p.b_resident) { umma_commit_elect(b_empty + bst); if (++bst == p.bstages) { bst = 0; bph ^= 1; } }
                         }
                         // slots no later step of this item reads retire with these MMAs (all remaining ones after the last step)
                         const int nrel = (i == k.nsteps - 1) ? p.live : p.sps;
-                        for (int l = 0; l < nrel; ++l) { umma_commit(slot_empty + st0); if (++st0 == stages) { st0 = 0; ph0 ^= 1; } }
-                        umma_commit(acc_full + buf);
+                        for (int l = 0; l < nrel; ++l) { umma_commit_elect(slot_empty + st0); if (++st0 == stages) { st0 = 0; ph0 ^= 1; } }
+                        umma_commit_elect(acc_full + buf);
                     }
                 }
             }
@@ -444,6 +472,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 if (p.kdfold) {    // output plane I sits in ring slot I % kAccRing of every M-tile (kPG columns, kw blocks at +0, +8, +16)
                     const int rsl = I % kAccRing;
                     mbar_wait(acc_full + rsl, (I / kAccRing) & 1);
+                    if (warp == 6) TRACE(4, I);
                     tc_fence_after();
                     for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
                         const int r = m * 128 + quad * 32 + lane;
@@ -455,6 +484,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + rsl);
+                    if (warp == 6) TRACE(5, I);
                     continue;
                 }
                 const int buf = I & 1;
@@ -784,3 +814,9 @@ int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, c
     }
     return MVS_CHECK_LAUNCH("mvs_conv3d_fwd (tcgen05)");
 }
+
+#ifdef MVS_TC_TRACE
+extern "C" int mvs_debug_tc_trace(long long* host_out) {   // [8][1024]
+    return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 8 * 1024) == cudaSuccess ? 0 : -1;
+}
+#endif

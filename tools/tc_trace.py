@@ -1,0 +1,36 @@
+"""Timeline of one CTA of the tcgen05 convolution (debug build with -DMVS_TC_TRACE): prints, per depth step, when the
+producer issued the slot, when the issuer passed its waits / finished issuing, and when the epilogue started / finished."""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = os.path.join(ROOT, "self-supervised-mvs_b200")
+lib = os.path.join(pkg, "libmvs_b200_trace.so")
+srcs = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "conv3d_tc.cu", "invwarp.cu"]
+if "--build" in sys.argv:
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+                           "-DMVS_TC_TRACE", "-shared", "-o", lib] + [os.path.join(pkg, "csrc", s) for s in srcs] + ["-lcudart"])
+    sys.exit(0)
+import torch
+import ssmvs_b200
+from ssmvs_b200 import ops
+ssmvs_b200._lib.bind(lib)
+dev = torch.device("cuda:0")
+cin, cout = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32, 8)
+x8 = ops.pack_c8(torch.randn(1, cin, 192, 128, 160, device=dev), torch.float16)
+g = ops.pack_conv3d_weight(0.1 * torch.randn(cout, cin, 3, 3, 3, device=dev), False)
+for _ in range(3):
+    ops.conv3d_raw(x8, g, cout, relu=True, algo=2)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (8 * 1024))()
+fn = ssmvs_b200._lib.lib().mvs_debug_tc_trace
+fn.argtypes, fn.restype = [ctypes.c_void_p], ctypes.c_int
+assert fn(buf) == 0
+t = [[buf[r * 1024 + i] for i in range(1024)] for r in range(8)]
+t0 = min(v for v in t[0][:8] if v)
+print("step: producer_issue | issuer: at_wait, past_wait, issued | epilogue: start, done   (cycles since first TMA)")
+for i in range(40):
+    print("%3d: %8d | %8d %8d %8d | %8d %8d" % (i, t[0][i] - t0, t[1][i] - t0, t[2][i] - t0, t[3][i] - t0, t[4][i] - t0, t[5][i] - t0))
