@@ -179,20 +179,26 @@ template <typename T, int NOV, bool KWFOLD>
 __device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
                                               int oh0, int ow0, int CoB, int64_t HWo) {
     constexpr int NLD = KWFOLD ? 3 : NOV;
+    const int64_t plane = HWo, row = p.Wo;
     for (int cb = 0; cb < CoB; ++cb) {
-        int64_t off[NOV];
+        // element offset of the row's first output voxel; the other voxels of a 2x2x2 block are +pd*plane +ph*row +pw
+        const int64_t off0 = p.Cout == 1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)oh0 * row + ow0
+                                         : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)oh0 * row + ow0) * 8;
+        const int64_t vs = p.Cout == 1 ? 1 : 8;
         uint4 sk[NOV];
 #pragma unroll
         for (int ov = 0; ov < NOV; ++ov) {
-            const int od = od0 + (NOV == 8 ? (ov >> 2) : 0), oh = oh0 + (NOV == 8 ? ((ov >> 1) & 1) : 0), ow = ow0 + (NOV == 8 ? (ov & 1) : 0);
-            off[ov] = p.Cout == 1 ? ((int64_t)b * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow
-                                  : ((((int64_t)b * CoB + cb) * p.Do + od) * HWo + (int64_t)oh * p.Wo + ow) * 8;
             sk[ov] = make_uint4(0u, 0u, 0u, 0u);
             if (valid && p.skip) {
-                if (p.Cout == 1) sk[ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off[ov]));
-                else sk[ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off[ov]));
+                const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
+                if (p.Cout == 1) sk[ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
+                else sk[ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
             }
         }
+        // folded-BN affine of this channel block: read once (the asm memory clobbers below would force re-reads per voxel)
+        float sc[8], sh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = aff[cb * 8 + k]; sh[k] = aff[64 + cb * 8 + k]; }
         uint32_t v[NLD][8];
 #pragma unroll
         for (int l = 0; l < NLD; ++l) tmem_ld8(trow + (uint32_t)(l * p.CoP + cb * 8), v[l]);
@@ -207,19 +213,17 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __
                 else o[k] = __uint_as_float(v[ov][k]);
             }
             if (!valid) continue;
+            const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
             if (p.Cout == 1) {
-                float x = o[0];
-                x = x * aff[0] + aff[64];
+                float x = o[0] * sc[0] + sh[0];
                 if (p.relu) x = fmaxf(x, 0.f);
                 if (p.skip) x += __uint_as_float(sk[ov].x);
-                reinterpret_cast<float*>(p.y)[off[ov]] = x;
+                reinterpret_cast<float*>(p.y)[off] = x;
                 continue;
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int co = cb * 8 + k;
-                float x = o[k];
-                x = x * aff[co] + aff[64 + co];
+                float x = o[k] * sc[k] + sh[k];
                 if (p.relu) x = fmaxf(x, 0.f);
                 o[k] = x;
             }
@@ -229,7 +233,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] += sv[k];
             }
-            V8<T>::store(reinterpret_cast<T*>(p.y) + off[ov], o);
+            V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
         }
     }
 }
@@ -419,6 +423,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     const Work k = decode(t);
                     for (int i = 0; i < k.nsteps; ++i, ++I) {
                         const int buf = I & 1;
+                        if (m == 0 && lane == 0) TRACE(1, I);
                         mbar_wait(acc_empty + buf, ((I >> 1) & 1) ^ 1);
                         // live slots: stages st0, st0+1, .. (mod stages); only the newest `sps` (all of them at i = 0) can be unready
                         uint32_t sa0 = 0, sa1 = 0, sa2 = 0;
@@ -432,6 +437,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                             }
                         }
                         tc_fence_after();
+                        if (m == 0 && lane == 0) TRACE(2, I);
                         const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
                         uint32_t b_ent = (b_addr >> 4) | b_lbo;
                         for (int e = 0; e < nent; ++e, b_ent += btile16) {
@@ -453,6 +459,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                         const int nrel = (i == k.nsteps - 1) ? p.live : p.sps;
                         for (int l = 0; l < nrel; ++l) { umma_commit_elect(slot_empty + st0); if (++st0 == stages) { st0 = 0; ph0 ^= 1; } }
                         umma_commit_elect(acc_full + buf);
+                        if (m == 0 && lane == 0) TRACE(3, I);
                     }
                 }
             }
@@ -472,7 +479,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 if (p.kdfold) {    // output plane I sits in ring slot I % kAccRing of every M-tile (kPG columns, kw blocks at +0, +8, +16)
                     const int rsl = I % kAccRing;
                     mbar_wait(acc_full + rsl, (I / kAccRing) & 1);
-                    if (warp == 6) TRACE(4, I);
+                    if (warp == 6 && lane == 0) TRACE(4, I);
                     tc_fence_after();
                     for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
                         const int r = m * 128 + quad * 32 + lane;
@@ -484,11 +491,12 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + rsl);
-                    if (warp == 6) TRACE(5, I);
+                    if (warp == 6 && lane == 0) TRACE(5, I);
                     continue;
                 }
                 const int buf = I & 1;
                 mbar_wait(acc_full + buf, (I >> 1) & 1);
+                if (warp == 6 && lane == 0) TRACE(4, I);
                 tc_fence_after();
                 for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
                     const int r = m * 128 + quad * 32 + lane;
@@ -502,6 +510,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + buf);
+                if (warp == 6 && lane == 0) TRACE(5, I);
             }
         }
     }

@@ -20,10 +20,16 @@ from ssmvs_b200 import ops
 ssmvs_b200._lib.bind(lib)
 dev = torch.device("cuda:0")
 cin, cout = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32, 8)
-x8 = ops.pack_c8(torch.randn(1, cin, 192, 128, 160, device=dev), torch.float16)
-g = ops.pack_conv3d_weight(0.1 * torch.randn(cout, cin, 3, 3, 3, device=dev), False)
+stride = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+tr = len(sys.argv) > 4 and sys.argv[4] == "T"
+shape = (1, cin, 96, 64, 80) if (tr and stride == 2) else (1, cin, 192, 128, 160)
+x8 = ops.pack_c8(torch.randn(*shape, device=dev), torch.float16)
+g = ops.pack_conv3d_weight(0.1 * (torch.randn(cin, cout, 3, 3, 3, device=dev) if tr else torch.randn(cout, cin, 3, 3, 3, device=dev)), tr)
+skip = None
+if tr and stride == 2:
+    skip = ops.pack_c8(torch.randn(1, cout, 192, 128, 160, device=dev), torch.float16)
 for _ in range(3):
-    ops.conv3d_raw(x8, g, cout, relu=True, algo=2)
+    ops.conv3d_raw(x8, g, cout, stride, tr, skip=skip, relu=cout > 1, algo=2)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (8 * 1024))()
 fn = ssmvs_b200._lib.lib().mvs_debug_tc_trace
