@@ -165,6 +165,7 @@ struct TensorMaps { CUtensorMap m[4]; };
 #ifdef MVS_TC_TRACE
 // Debug build only (tools/tc_trace.py): CTA 0 records clock64() at pipeline events; 8 lanes x 1024 slots.
 __device__ long long g_trace[8][1024];
+__device__ int g_tcount;
 #define TRACE(lane_id, idx) do { if (blockIdx.x == 0 && (idx) < 1024) g_trace[lane_id][idx] = clock64(); } while (0)
 #else
 #define TRACE(lane_id, idx) do { } while (0)
@@ -200,9 +201,15 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __
 #pragma unroll
         for (int k = 0; k < 8; ++k) { sc[k] = aff[cb * 8 + k]; sh[k] = aff[64 + cb * 8 + k]; }
         uint32_t v[NLD][8];
+#ifdef MVS_TC_TRACE
+        if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[6][g_tcount & 1023] = clock64(); }
+#endif
 #pragma unroll
         for (int l = 0; l < NLD; ++l) tmem_ld8(trow + (uint32_t)(l * p.CoP + cb * 8), v[l]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef MVS_TC_TRACE
+        if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[7][g_tcount & 1023] = clock64(); g_tcount++; }
+#endif
 #pragma unroll
         for (int ov = 0; ov < NOV; ++ov) {
             float o[8];

@@ -40,3 +40,7 @@ t0 = min(v for v in t[0][:8] if v)
 print("step: producer_issue | issuer: at_wait, past_wait, issued | epilogue: start, done   (cycles since first TMA)")
 for i in range(40):
     print("%3d: %8d | %8d %8d %8d | %8d %8d" % (i, t[0][i] - t0, t[1][i] - t0, t[2][i] - t0, t[3][i] - t0, t[4][i] - t0, t[5][i] - t0))
+
+print("epilogue rows of warp 6 (per M-tile): skip loads issued -> TMEM data ready, and gap to the next M-tile")
+for i in range(4, 24):
+    print("%3d: issued %8d  tmem_ready +%6d  next_mtile +%6d" % (i, t[6][i] - t0, t[7][i] - t[6][i], t[6][i + 1] - t[7][i]))
