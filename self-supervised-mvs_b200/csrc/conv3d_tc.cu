@@ -176,30 +176,33 @@ __device__ int g_tcount;
 // TMEM read of a channel block is issued before the first use, so their latencies overlap instead of adding up.
 //   NOV = 8 : transposed stride 2, column block ov = output parity (pd, ph, pw) of the 2x2x2 voxel block of this input voxel
 //   KWFOLD  : stride 1, column blocks 0,1,2 hold the taps reading input column (lane): output j = blk0[j] + blk1[j+1] + blk2[j+2]
-template <typename T, int NOV, bool KWFOLD>
-__device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
-                                              int oh0, int ow0, int CoB, int64_t HWo) {
+template <typename T, int NOV, bool KWFOLD, bool C1, bool SKIP>
+__device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
+                                                int oh0, int ow0, int CoB, int64_t HWo) {
     constexpr int NLD = KWFOLD ? 3 : NOV;
+    constexpr int64_t vs = C1 ? 1 : 8;
     const int64_t plane = HWo, row = p.Wo;
+    const float floor_ = p.relu ? 0.f : -INFINITY;          // branch-free optional ReLU
     for (int cb = 0; cb < CoB; ++cb) {
         // element offset of the row's first output voxel; the other voxels of a 2x2x2 block are +pd*plane +ph*row +pw
-        const int64_t off0 = p.Cout == 1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)oh0 * row + ow0
-                                         : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)oh0 * row + ow0) * 8;
-        const int64_t vs = p.Cout == 1 ? 1 : 8;
+        const int64_t off0 = C1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)oh0 * row + ow0
+                                : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)oh0 * row + ow0) * 8;
         uint4 sk[NOV];
+        if (SKIP) {
 #pragma unroll
-        for (int ov = 0; ov < NOV; ++ov) {
-            sk[ov] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && p.skip) {
+            for (int ov = 0; ov < NOV; ++ov) {
+                sk[ov] = make_uint4(0u, 0u, 0u, 0u);
                 const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
-                if (p.Cout == 1) sk[ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
-                else sk[ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
+                if (valid) {
+                    if (C1) sk[ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
+                    else sk[ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
+                }
             }
         }
         // folded-BN affine of this channel block: read once (the asm memory clobbers below would force re-reads per voxel)
         float sc[8], sh[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sc[k] = aff[cb * 8 + k]; sh[k] = aff[64 + cb * 8 + k]; }
+        for (int k = 0; k < (C1 ? 1 : 8); ++k) { sc[k] = aff[cb * 8 + k]; sh[k] = aff[64 + cb * 8 + k]; }
         uint32_t v[NLD][8];
 #ifdef MVS_TC_TRACE
         if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[6][g_tcount & 1023] = clock64(); }
@@ -214,34 +217,41 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __
         for (int ov = 0; ov < NOV; ++ov) {
             float o[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < (C1 ? 1 : 8); ++k) {
                 if (KWFOLD) o[k] = __uint_as_float(v[0][k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[1][k]), 1) +
                                    __shfl_down_sync(0xffffffffu, __uint_as_float(v[2][k]), 2);
                 else o[k] = __uint_as_float(v[ov][k]);
             }
-            if (!valid) continue;
             const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
-            if (p.Cout == 1) {
-                float x = o[0] * sc[0] + sh[0];
-                if (p.relu) x = fmaxf(x, 0.f);
-                if (p.skip) x += __uint_as_float(sk[ov].x);
-                reinterpret_cast<float*>(p.y)[off] = x;
+            if (C1) {
+                float x = fmaxf(o[0] * sc[0] + sh[0], floor_);
+                if (SKIP) x += __uint_as_float(sk[ov].x);
+                if (valid) reinterpret_cast<float*>(p.y)[off] = x;
                 continue;
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float x = o[k] * sc[k] + sh[k];
-                if (p.relu) x = fmaxf(x, 0.f);
-                o[k] = x;
-            }
-            if (p.skip) {
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k] * sc[k] + sh[k], floor_);
+            if (SKIP) {
                 float sv[8];
                 unpack8<T>(sk[ov], sv);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] += sv[k];
             }
-            V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
+            if (valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
         }
+    }
+}
+
+// Runtime (warp-uniform) selection of the specialised epilogue: single-channel output or C8, with or without a skip tensor.
+template <typename T, int NOV, bool KWFOLD>
+__device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
+                                              int oh0, int ow0, int CoB, int64_t HWo) {
+    if (p.Cout == 1) {
+        if (p.skip) epilogue_rows_v<T, NOV, KWFOLD, true, true>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
+        else epilogue_rows_v<T, NOV, KWFOLD, true, false>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
+    } else {
+        if (p.skip) epilogue_rows_v<T, NOV, KWFOLD, false, true>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
+        else epilogue_rows_v<T, NOV, KWFOLD, false, false>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
     }
 }
 

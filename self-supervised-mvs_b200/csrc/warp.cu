@@ -239,8 +239,8 @@ template <> struct Pack2<__nv_bfloat16> {
     static __device__ __forceinline__ __nv_bfloat162 from_f2(float2 v) { return __float22bfloat162_rn(v); }
 };
 
-template <typename T, int CPT, int NS>   // NS = compile-time bound on the source count (register arrays are sized by it)
-__global__ void __launch_bounds__(128, NS <= 4 ? 5 : 3)
+template <typename T, int CPT, int NS, int MINB>   // NS = compile-time bound on the source count (register arrays are sized by it)
+__global__ void __launch_bounds__(128, MINB)
 warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
                          const float* __restrict__ depth, int per_pixel, T* __restrict__ var, int B, int CB, int D, int H,
                          int W, int dper, int align_corners, int ref_sq_in_sum) {
@@ -277,6 +277,7 @@ warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, cons
     // ix = u * sx + ox : align_corners ? u : u * W/(W-1) - 0.5
     const float sx = align_corners ? 1.f : (float)W / (float)(W - 1), sy = align_corners ? 1.f : (float)H / (float)(H - 1);
     const float oxy = align_corners ? 0.f : -0.5f;
+    const float fW = (float)W, fH = (float)H;
     const float inv_n = 1.f / (float)(nsrc + 1);
     const float2 inv_n2 = make_float2(inv_n, inv_n);
 
@@ -292,24 +293,26 @@ warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, cons
         for (int s = 0; s < NS; ++s) {
             if (s < nsrc) {
                 const float pz = ray[s][2] * dv + tr[s][2];
-                const float iz = 1.f / pz;                       // pz == 0 -> inf -> NaN/inf coordinates -> every tap rejected
-                const float ix = (ray[s][0] * dv + tr[s][0]) * iz * sx + oxy;
-                const float iy = (ray[s][1] * dv + tr[s][1]) * iz * sy + oxy;
+                float iz;                                        // pz == 0 -> inf -> NaN/inf coordinates -> every tap rejected
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(pz));
+                // coordinates clamped to [-1, W] x [-1, H]: outside that range every tap is out of the map anyway, and the
+                // clamp (fmaxf drops a NaN) keeps the magic-number floor below exact
+                const float ix = fminf(fmaxf((ray[s][0] * dv + tr[s][0]) * iz * sx + oxy, -1.f), fW);
+                const float iy = fminf(fmaxf((ray[s][1] * dv + tr[s][1]) * iz * sy + oxy, -1.f), fH);
                 // floor and float->int without the conversion (XU) pipe: adding 1.5 * 2^23 with round-down leaves floor(ix)
-                // in the low mantissa bits (exact for |ix| < 2^22; larger or NaN coordinates fail the range tests below)
+                // in the low mantissa bits
                 const float kMagic = 12582912.f;
                 const float tx = __fadd_rd(ix, kMagic), ty = __fadd_rd(iy, kMagic);
-                const float x0 = tx - kMagic, y0 = ty - kMagic;
-                const float x1 = x0 + 1.f, y1 = y0 + 1.f;
-                const bool vx0 = (x0 >= 0.f) && (x0 <= (float)(W - 1)), vx1 = (x1 >= 0.f) && (x1 <= (float)(W - 1));
-                const bool vy0 = (y0 >= 0.f) && (y0 <= (float)(H - 1)), vy1 = (y1 >= 0.f) && (y1 <= (float)(H - 1));
-                const float wx0 = x1 - ix, wx1 = ix - x0, wy0 = y1 - iy, wy1 = iy - y0;
-                // invalid taps read pixel (clamped) with weight exactly 0, so there is no divergent load
                 const int xi = __float_as_int(tx) - 0x4B400000, yi = __float_as_int(ty) - 0x4B400000;
-                const int xa = vx0 ? xi : 0, xb = vx1 ? xi + 1 : 0, ya = vy0 ? yi : 0, yb = vy1 ? yi + 1 : 0;
+                const float wx1 = ix - (tx - kMagic), wy1 = iy - (ty - kMagic);     // exact
+                const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;                       // = (x0 + 1) - ix, correctly rounded
+                // taps outside the map get weight exactly 0 and read a clamped (in-map) pixel, so there is no divergent load
+                const float mx0 = (unsigned)xi < (unsigned)W ? wx0 : 0.f, mx1 = (unsigned)(xi + 1) < (unsigned)W ? wx1 : 0.f;
+                const float my0 = (unsigned)yi < (unsigned)H ? wy0 : 0.f, my1 = (unsigned)(yi + 1) < (unsigned)H ? wy1 : 0.f;
+                const int xa = min(max(xi, 0), W - 1), xb = min(xi + 1, W - 1), ya = min(max(yi, 0), H - 1), yb = min(yi + 1, H - 1);
                 const int o0 = ya * W + xa, o1 = ya * W + xb, o2 = yb * W + xa, o3 = yb * W + xb;
-                const T2 w0 = Pack2<T>::splat((vx0 && vy0) ? wx0 * wy0 : 0.f), w1 = Pack2<T>::splat((vx1 && vy0) ? wx1 * wy0 : 0.f);
-                const T2 w2 = Pack2<T>::splat((vx0 && vy1) ? wx0 * wy1 : 0.f), w3 = Pack2<T>::splat((vx1 && vy1) ? wx1 * wy1 : 0.f);
+                const T2 w0 = Pack2<T>::splat(mx0 * my0), w1 = Pack2<T>::splat(mx1 * my0);
+                const T2 w2 = Pack2<T>::splat(mx0 * my1), w3 = Pack2<T>::splat(mx1 * my1);
                 const T* base = reinterpret_cast<const T*>(srcs.p[s]) + map_off;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
@@ -384,10 +387,11 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
         // 16-bit storage: packed-math kernel, 2 channel blocks per thread, source-count bound in {2,4,6,8}
         const int dperf = depth_chunk(D, HW, B, CB / 2);
         const dim3 gridf(mvs_cdiv(HW, 128), (unsigned)(B * (CB / 2) * ((D + dperf - 1) / dperf)));
-#define MVS_WV_LAUNCH(T, NS) warp_var_fwd_fast_kernel<T, 2, NS><<<gridf, 128, 0, (cudaStream_t)stream>>>( \
+        static const int mb4 = [] { const char* e = getenv("MVS_WARP_MINB"); return e ? atoi(e) : 4; }();   // tuning knob: 4 blocks/SM (122 registers, no spills) measured faster than 5 (96, spills)
+#define MVS_WV_LAUNCH(T, NS, MB) warp_var_fwd_fast_kernel<T, 2, NS, MB><<<gridf, 128, 0, (cudaStream_t)stream>>>( \
             (const T*)ref, sp, nsrc, rt, depth, per_pixel, (T*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum)
-#define MVS_WV_BY_NS(T) do { if (nsrc <= 2) MVS_WV_LAUNCH(T, 2); else if (nsrc <= 4) MVS_WV_LAUNCH(T, 4); \
-                             else if (nsrc <= 6) MVS_WV_LAUNCH(T, 6); else MVS_WV_LAUNCH(T, 8); } while (0)
+#define MVS_WV_BY_NS(T) do { if (nsrc <= 2) MVS_WV_LAUNCH(T, 2, 5); else if (nsrc <= 4) { if (mb4 == 4) MVS_WV_LAUNCH(T, 4, 4); else MVS_WV_LAUNCH(T, 4, 5); } \
+                             else if (nsrc <= 6) MVS_WV_LAUNCH(T, 6, 3); else MVS_WV_LAUNCH(T, 8, 3); } while (0)
         if (dtype_in == MVS_F16) MVS_WV_BY_NS(__half); else MVS_WV_BY_NS(__nv_bfloat16);
 #undef MVS_WV_BY_NS
 #undef MVS_WV_LAUNCH
