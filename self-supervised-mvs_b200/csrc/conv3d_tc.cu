@@ -176,82 +176,95 @@ __device__ int g_tcount;
 // TMEM read of a channel block is issued before the first use, so their latencies overlap instead of adding up.
 //   NOV = 8 : transposed stride 2, column block ov = output parity (pd, ph, pw) of the 2x2x2 voxel block of this input voxel
 //   KWFOLD  : stride 1, column blocks 0,1,2 hold the taps reading input column (lane): output j = blk0[j] + blk1[j+1] + blk2[j+2]
-template <typename T, int NOV, bool KWFOLD, bool C1, bool SKIP>
-__device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
-                                                int oh0, int ow0, int CoB, int64_t HWo) {
+// One lane's output row of NT M-tiles at once (NT = 2: the TMEM and skip loads of both tiles are in flight together, which
+// halves the exposed latency of this otherwise serial, single-warp code).
+struct RowAt { uint32_t trow; bool valid; int oh, ow; };
+
+template <typename T, int NOV, bool KWFOLD, bool C1, bool SKIP, int NT>
+__device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* __restrict__ aff, const RowAt (&ra)[NT], int b, int od0,
+                                                int CoB, int64_t HWo) {
     constexpr int NLD = KWFOLD ? 3 : NOV;
     constexpr int64_t vs = C1 ? 1 : 8;
     const int64_t plane = HWo, row = p.Wo;
     const float floor_ = p.relu ? 0.f : -INFINITY;          // branch-free optional ReLU
     for (int cb = 0; cb < CoB; ++cb) {
         // element offset of the row's first output voxel; the other voxels of a 2x2x2 block are +pd*plane +ph*row +pw
-        const int64_t off0 = C1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)oh0 * row + ow0
-                                : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)oh0 * row + ow0) * 8;
-        uint4 sk[NOV];
+        int64_t off0[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            off0[t] = C1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)ra[t].oh * row + ra[t].ow
+                         : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)ra[t].oh * row + ra[t].ow) * 8;
+        uint4 sk[NT][NOV];
         if (SKIP) {
 #pragma unroll
-            for (int ov = 0; ov < NOV; ++ov) {
-                sk[ov] = make_uint4(0u, 0u, 0u, 0u);
-                const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
-                if (valid) {
-                    if (C1) sk[ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
-                    else sk[ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int ov = 0; ov < NOV; ++ov) {
+                    sk[t][ov] = make_uint4(0u, 0u, 0u, 0u);
+                    const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
+                    if (ra[t].valid) {
+                        if (C1) sk[t][ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
+                        else sk[t][ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
+                    }
                 }
-            }
         }
         // folded-BN affine of this channel block: read once (the asm memory clobbers below would force re-reads per voxel)
         float sc[8], sh[8];
 #pragma unroll
         for (int k = 0; k < (C1 ? 1 : 8); ++k) { sc[k] = aff[cb * 8 + k]; sh[k] = aff[64 + cb * 8 + k]; }
-        uint32_t v[NLD][8];
+        uint32_t v[NT][NLD][8];
 #ifdef MVS_TC_TRACE
         if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[6][g_tcount & 1023] = clock64(); }
 #endif
 #pragma unroll
-        for (int l = 0; l < NLD; ++l) tmem_ld8(trow + (uint32_t)(l * p.CoP + cb * 8), v[l]);
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int l = 0; l < NLD; ++l) tmem_ld8(ra[t].trow + (uint32_t)(l * p.CoP + cb * 8), v[t][l]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #ifdef MVS_TC_TRACE
         if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[7][g_tcount & 1023] = clock64(); g_tcount++; }
 #endif
 #pragma unroll
-        for (int ov = 0; ov < NOV; ++ov) {
-            float o[8];
+        for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int k = 0; k < (C1 ? 1 : 8); ++k) {
-                if (KWFOLD) o[k] = __uint_as_float(v[0][k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[1][k]), 1) +
-                                   __shfl_down_sync(0xffffffffu, __uint_as_float(v[2][k]), 2);
-                else o[k] = __uint_as_float(v[ov][k]);
-            }
-            const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
-            if (C1) {
-                float x = fmaxf(o[0] * sc[0] + sh[0], floor_);
-                if (SKIP) x += __uint_as_float(sk[ov].x);
-                if (valid) reinterpret_cast<float*>(p.y)[off] = x;
-                continue;
-            }
+            for (int ov = 0; ov < NOV; ++ov) {
+                float o[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k] * sc[k] + sh[k], floor_);
-            if (SKIP) {
-                float sv[8];
-                unpack8<T>(sk[ov], sv);
+                for (int k = 0; k < (C1 ? 1 : 8); ++k) {
+                    if (KWFOLD) o[k] = __uint_as_float(v[t][0][k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[t][1][k]), 1) +
+                                       __shfl_down_sync(0xffffffffu, __uint_as_float(v[t][2][k]), 2);
+                    else o[k] = __uint_as_float(v[t][ov][k]);
+                }
+                const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
+                if (C1) {
+                    float x = fmaxf(o[0] * sc[0] + sh[0], floor_);
+                    if (SKIP) x += __uint_as_float(sk[t][ov].x);
+                    if (ra[t].valid) reinterpret_cast<float*>(p.y)[off] = x;
+                    continue;
+                }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] += sv[k];
+                for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k] * sc[k] + sh[k], floor_);
+                if (SKIP) {
+                    float sv[8];
+                    unpack8<T>(sk[t][ov], sv);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += sv[k];
+                }
+                if (ra[t].valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
             }
-            if (valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
-        }
     }
 }
 
 // Runtime (warp-uniform) selection of the specialised epilogue: single-channel output or C8, with or without a skip tensor.
-template <typename T, int NOV, bool KWFOLD>
-__device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __restrict__ aff, uint32_t trow, bool valid, int b, int od0,
-                                              int oh0, int ow0, int CoB, int64_t HWo) {
+template <typename T, int NOV, bool KWFOLD, int NT>
+__device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __restrict__ aff, const RowAt (&ra)[NT], int b, int od0,
+                                              int CoB, int64_t HWo) {
     if (p.Cout == 1) {
-        if (p.skip) epilogue_rows_v<T, NOV, KWFOLD, true, true>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
-        else epilogue_rows_v<T, NOV, KWFOLD, true, false>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
+        if (p.skip) epilogue_rows_v<T, NOV, KWFOLD, true, true, NT>(p, aff, ra, b, od0, CoB, HWo);
+        else epilogue_rows_v<T, NOV, KWFOLD, true, false, NT>(p, aff, ra, b, od0, CoB, HWo);
     } else {
-        if (p.skip) epilogue_rows_v<T, NOV, KWFOLD, false, true>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
-        else epilogue_rows_v<T, NOV, KWFOLD, false, false>(p, aff, trow, valid, b, od0, oh0, ow0, CoB, HWo);
+        if (p.skip) epilogue_rows_v<T, NOV, KWFOLD, false, true, NT>(p, aff, ra, b, od0, CoB, HWo);
+        else epilogue_rows_v<T, NOV, KWFOLD, false, false, NT>(p, aff, ra, b, od0, CoB, HWo);
     }
 }
 
@@ -512,18 +525,30 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
             const Work k = decode(t);
             const int b = k.b, w0 = k.w0, h0 = k.h0, d0 = k.d0;
+            // accumulator row (= lane) of M-tile m: one h-row of the tile per warp, lane = w position
+            auto row_at = [&](int m, uint32_t trow) {
+                const int r = m * 128 + quad * 32 + lane;
+                const int hh = r >> 5, ww = r & 31;
+                RowAt a;
+                a.trow = trow; a.oh = h0 + hh; a.ow = w0 + ww;
+                a.valid = (m < p.nM) && (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+                return a;
+            };
             for (int i = 0; i < k.nsteps; ++i, ++I) {
                 if (p.kdfold) {    // output plane I sits in ring slot I % kAccRing of every M-tile (kPG columns, kw blocks at +0, +8, +16)
                     const int rsl = I % kAccRing;
                     mbar_wait(acc_full + rsl, (I / kAccRing) & 1);
                     if (warp == 6 && lane == 0) TRACE(4, I);
                     tc_fence_after();
-                    for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
-                        const int r = m * 128 + quad * 32 + lane;
-                        const int hh = r >> 5, ww = r & 31;
-                        const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
-                        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((m * kAccRing + rsl) * kPG);
-                        epilogue_rows<T, 1, true>(p, aff, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                    {
+                        const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
+                        RowAt ra[2];
+                        for (int u = 0; u < 2; ++u) {
+                            const int m = mpar + 2 * u;
+                            ra[u] = row_at(m, tq + (uint32_t)((m * kAccRing + rsl) * kPG));
+                        }
+                        if (mpar + 2 < p.nM) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo);
+                        else if (mpar < p.nM) { const RowAt r1[1] = {ra[0]}; epilogue_rows<T, 1, true, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -545,14 +570,25 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 mbar_wait(acc_full + buf, (I >> 1) & 1);
                 if (warp == 6 && lane == 0) TRACE(4, I);
                 tc_fence_after();
-                for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
-                    const int r = m * 128 + quad * 32 + lane;
-                    const int hh = r >> 5, ww = r & 31;     // a warp is one h-row of the tile: lane = w position
-                    const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
-                    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.nM + m) * p.N);
-                    if (p.mode == MODE_T2) epilogue_rows<T, 8, false>(p, aff, trow, valid, b, 2 * (d0 + i), 2 * (h0 + hh), 2 * (w0 + ww), CoB, HWo);
-                    else if (kwfold) epilogue_rows<T, 1, true>(p, aff, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
-                    else epilogue_rows<T, 1, false>(p, aff, trow, valid, b, d0 + i, h0 + hh, w0 + ww, CoB, HWo);
+                {
+                    const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
+                    RowAt ra[2];
+                    for (int u = 0; u < 2; ++u) {
+                        const int m = mpar + 2 * u;
+                        ra[u] = row_at(m, tq + (uint32_t)((buf * p.nM + m) * p.N));
+                    }
+                    const bool two = mpar + 2 < p.nM;
+                    if (p.mode == MODE_T2) {
+                        for (int u = 0; u < 2 && mpar + 2 * u < p.nM; ++u) {
+                            RowAt r1[1] = {ra[u]};
+                            r1[0].oh *= 2; r1[0].ow *= 2;
+                            epilogue_rows<T, 8, false, 1>(p, aff, r1, b, 2 * (d0 + i), CoB, HWo);
+                        }
+                    } else if (mpar < p.nM) {
+                        const RowAt r1[1] = {ra[0]};
+                        if (kwfold) { if (two) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo); else epilogue_rows<T, 1, true, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
+                        else { if (two) epilogue_rows<T, 1, false, 2>(p, aff, ra, b, d0 + i, CoB, HWo); else epilogue_rows<T, 1, false, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -783,10 +819,24 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     p.tmem_cols = cols;
     // depth segments: enough CTAs for >= ~3 waves of 148 SMs, but >= 4 steps each (halo slots are reloaded per segment)
     const int64_t tiles = (int64_t)p.B * p.nwt * p.nht;
-    int LD = p.Dt;
-    const int min_ld = p.kdfold ? 8 : 4;   // the kd-folded program pays two extra input planes per item
-    while (LD > min_ld && tiles * ((p.Dt + LD - 1) / LD) < 148 * 3) LD = (LD + 1) / 2;
-    p.LD = LD; p.nseg = (p.Dt + LD - 1) / LD;
+    // Work items = tiles x depth segments, dealt round-robin to the persistent CTAs.  The kernel time is the busiest CTA's
+    // rounds x (steps per item + the halo planes every item reloads + ~1 step of pipeline bubble), so pick the segment count
+    // that minimises exactly that: e.g. 48 tiles x 12 segments = 576 items fill 148 CTAs to 97 % in 4 rounds, where a
+    // power-of-two split (16 segments, 768 items) leaves the 6th round 19 % full.
+    const int min_ld = p.kdfold ? 4 : 2;
+    const int extra = (p.mode == MODE_S1 ? 2 : 1) + 1;
+    const char* fseg = getenv("MVS_TC_NSEG");               // test / tuning knob
+    int best_nseg = 1;
+    int64_t best_cost = -1;
+    for (int nseg = 1; nseg <= max(1, p.Dt / min_ld); ++nseg) {
+        const int ld = (p.Dt + nseg - 1) / nseg;
+        if ((int64_t)(nseg - 1) * ld >= p.Dt) continue;          // an empty last segment
+        const int64_t rounds = (tiles * nseg + 147) / 148;
+        const int64_t cost = rounds * (ld + extra);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nseg = nseg; }
+    }
+    if (fseg && atoi(fseg) >= 1 && atoi(fseg) <= p.Dt) best_nseg = atoi(fseg);
+    p.LD = (p.Dt + best_nseg - 1) / best_nseg; p.nseg = (p.Dt + p.LD - 1) / p.LD;
     return tiles * p.nseg < (1ll << 31);
 }
 
