@@ -71,46 +71,85 @@ def make_model(dtype):
 
 
 class ClockSampler:
-    """nvidia-smi SM clock / throttle reasons while the timed region runs."""
+    """SM clock / throttle reasons sampled WHILE the timed region runs: NVML polled from a thread every few ms (the timed
+    region is tens of ms, too short for `nvidia-smi -lms`), with an nvidia-smi loop as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period = index, period_s
+        self.sm, self.mx, self.reasons, self.how = [], 0.0, set(), None
+        self.stop = threading.Event()
+        self.t = None
+        self.proc = None
 
-    def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout.readlines()), daemon=True)
-            self.t.start()
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may renumber devices: find ours by UUID
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
         except Exception:
-            self.proc = None
-        return self
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
-    def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            self.t.join(timeout=2)
+    def _poll_nvml(self, nv, h):
+        bits = ((nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for b, n in bits:
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
-    def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+    def _poll_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
+                self.sm.append(float(f[0]))
+                self.mx = max(self.mx, float(f[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
+            for n, v in zip(self.NAMES, f[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    self.reasons.add(n)
+
+    def __enter__(self):
+        try:
+            nv, h = self._nvml_handle()
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.how = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+        except Exception:
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                              "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+                self.how = "nvidia-smi"
+                self.t = threading.Thread(target=self._poll_smi, daemon=True)
+            except Exception:
+                self.t = None
+        if self.t is not None:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.t is not None:
+            self.t.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
 def cpu_forward_timer(steps: int, warmup: int):
@@ -211,14 +250,32 @@ def main():
             return graphed(*graphed.static_in)      # inputs already resident in the graph's static buffers
         return model(res["imgs"], res["proj_matrices"], res["depth_values"])
 
-    def step_e2e():
-        if graphed is not None:
-            o = graphed(pinned["imgs"], pinned["proj_matrices"], pinned["depth_values"])   # H2D copies into the static buffers
-        else:
-            d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-            o = model(d["imgs"], d["proj_matrices"], d["depth_values"])
-        out_host["depth"].copy_(o["depth"], non_blocking=True)
-        out_host["conf"].copy_(o["photometric_confidence"], non_blocking=True)
+    pipe = None
+    if graphed is not None:
+        from ssmvs_b200.graph import StreamedForward
+        pipe = StreamedForward(graphed, ("depth", "photometric_confidence"))
+    host_batch = [pinned["imgs"], pinned["proj_matrices"], pinned["depth_values"]]
+
+    def e2e_loop(steps):
+        """K steps through the public host-to-host pipeline: every step uploads its inputs from pinned host memory and reads
+        depth + confidence back to the host; upload i+1 overlaps the kernels of step i.  One event pair around the K steps
+        (no L2 flush needed: a step streams > 1 GB of fresh inputs and intermediates through the 126 MB L2)."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            a.record(stream)
+            if pipe is not None:
+                pipe.copy.wait_event(a)
+                for _ in pipe.run(host_batch for _ in range(steps)):
+                    pass
+            else:
+                for _ in range(steps):
+                    d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+                    o = model(d["imgs"], d["proj_matrices"], d["depth_values"])
+                    out_host["depth"].copy_(o["depth"], non_blocking=True)
+                    out_host["conf"].copy_(o["photometric_confidence"], non_blocking=True)
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+        return a.elapsed_time(b)
 
     def timed(fn, steps, warmup):
         """per-step CUDA-event pairs on the launching stream, L2 flushed between steps (outside the pairs)."""
@@ -249,8 +306,11 @@ def main():
 
     with ClockSampler(local) as clk:
         ms_total, wall, launches = timed(step_resident, args.steps, args.warmup)
+        e2e_loop(3)
+        torch.cuda.synchronize(dev)
+        parallel.barrier()
+        ms_e2e = parallel.max_over_ranks(e2e_loop(args.steps), dev)
     clocks = clk.summary()
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 3)
     if args.ncu_range:
         return
 
@@ -268,16 +328,12 @@ def main():
                     f = model.feature.forward_folded(xin, dtype)
                 else:
                     f = model.feature(xin)
-                feats = list(f.reshape(VIEWS, PB, CHANNELS, HF, WF).unbind(0))
                 e[1].record(stream)
                 rt = ops.compose_proj(res["proj_matrices"])
-                ref8 = ops.pack_c8(feats[0], dtype)
-                src8 = [ops.pack_c8(s, dtype) for s in feats[1:]]
-                var = torch.empty(PB, CHANNELS // 8, NDEPTH, HF, WF, 8, dtype=dtype, device=dev)
+                maps = ops.pack_c8_padded(f, dtype)
+                maps = maps.view(VIEWS, PB, *maps.shape[1:])
                 flush.zero_(); e[2].record(stream)
-                ssmvs_b200._lib.call("mvs_warp_var_fwd", ref8, ref8.data_ptr(), ops._ptr_array(src8), len(src8), rt.data_ptr(),
-                                     res["depth_values"].data_ptr(), 0, var.data_ptr(), PB, CHANNELS, NDEPTH, HF, WF,
-                                     ssmvs_b200._lib.dtype_code(dtype), ssmvs_b200._lib.dtype_code(dtype), 0, 0)
+                var = ops.warp_variance_maps(maps, rt, res["depth_values"], dtype)
                 e[3].record(stream)
                 flush.zero_(); e[4].record(stream)
                 model.cost_regularization.act_dtype = dtype
@@ -335,7 +391,8 @@ def main():
                            "wall_s_incl_flush": wall},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "depth-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "how": "StreamedForward.run: pinned host batch -> H2D (copy stream, one step ahead) -> graph replay -> D2H of depth + confidence, every step; one event pair around the K steps, max over ranks"},
                 "roofline": dominant, "roofline_warp_var": roof_wv, "roofline_conv0": roof_conv0, "roofline_reg3d": roof_reg,
                 "stage_ms": stages}
         if world == 1 and not args.no_cpu_baseline:

@@ -45,6 +45,10 @@ int mvs_is_emulation(void);
 int mvs_pack_c8(const float* src, void* dst, int B, int C, int64_t S, int dtype, void* stream);
 /* channels-last [B][S][C] in `dtype` (the layout the library 2-D feature extractor emits) -> C8 [B][C/8][S][8], same dtype */
 int mvs_nhwc_to_c8(const void* src, void* dst, int B, int C, int64_t S, int dtype, void* stream);
+/* Zero-bordered maps "C8P" for the plane-sweep gather: dst [M][C/8][H+3][W+2][8] in `dtype`, pixel (y,x) at row y+1, column x+1,
+ * zeros elsewhere (so that grid_sample's zero padding becomes a plain load).  src_layout: 0 = fp32 [M][C][H][W],
+ * 1 = channels-last `dtype` [M][H][W][C], 2 = C8 `dtype` [M][C/8][H][W][8]. */
+int mvs_pack_c8_padded(const void* src, void* dst, int M, int C, int H, int W, int src_layout, int dtype, void* stream);
 /* inverse of mvs_pack_c8 */
 int mvs_unpack_c8(const void* src, float* dst, int B, int C, int64_t S, int dtype, void* stream);
 
@@ -68,19 +72,20 @@ int mvs_homo_warp_bwd(const float* grad_out, const float* rt, const float* depth
                       int B, int C, int D, int H, int W, int align_corners, void* stream);
 
 /* ---- a1+a3+a4: fused warp + bilinear gather + running variance ------------------------------------------------
- * ref, srcs[i]: C8 maps [B][C/8][H][W][8] (dtype_in); var: C8 volume [B][C/8][D][H][W][8] (dtype_out).
+ * ref, srcs[i]: C8 maps [B][C/8][H][W][8] (pad=0) or zero-bordered C8P maps [B][C/8][H+3][W+2][8] (pad=1, the fast path
+ * for 16-bit storage) in dtype_in; var: C8 volume [B][C/8][D][H][W][8] (dtype_out).
  * srcs = HOST array of nsrc device pointers; rt = [nsrc][B][12].
  * var = S2/N - (S1/N)^2, N = nsrc+1, S1 = ref + sum warped, S2 = ref^2 + sum warped^2;
  * ref_sq_in_sum=1 starts S1 from ref^2 (CVP aliasing, jdacs-ms/models/network.py:114-116).
  * Replaces jdacs/models/mvsnet.py:120-136, jdacs-ms/models/network.py:114-137, modules.py:209-261. */
 int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int nsrc, const float* rt, const float* depth,
                      int per_pixel, void* var, int B, int C, int D, int H, int W, int dtype_in, int dtype_out,
-                     int align_corners, int ref_sq_in_sum, void* stream);
-/* grad_var: C8 volume (dtype_out).  grad_ref and grad_srcs[i]: fp32 C8 maps, zero-initialised by the caller. */
+                     int align_corners, int ref_sq_in_sum, int pad, void* stream);
+/* grad_var: C8 volume (dtype_out).  grad_ref and grad_srcs[i]: fp32 C8 maps (never padded), zero-initialised by the caller. */
 int mvs_warp_var_bwd(const void* grad_var, const void* ref, const void* const* srcs, int nsrc, const float* rt,
                      const float* depth, int per_pixel, float* grad_ref, float* const* grad_srcs, int B, int C,
                      int D, int H, int W, int dtype_in, int dtype_out, int align_corners, int ref_sq_in_sum,
-                     void* stream);
+                     int pad, void* stream);
 
 /* ---- a5/a6: 3-D convolution stack ------------------------------------------------------------------------------ */
 typedef struct {

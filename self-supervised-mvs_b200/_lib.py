@@ -38,8 +38,9 @@ _SIGS = {
     "mvs_compose_proj_ke": ([_P, _P, _P, _P, _F, _P, _I, _I, _P], _I),
     "mvs_homo_warp_fwd": ([_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "mvs_homo_warp_bwd": ([_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),
-    "mvs_warp_var_fwd": ([_P, C.POINTER(_P), _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
-    "mvs_warp_var_bwd": ([_P, _P, C.POINTER(_P), _I, _P, _P, _I, _P, C.POINTER(_P), _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "mvs_pack_c8_padded": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "mvs_warp_var_fwd": ([_P, C.POINTER(_P), _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "mvs_warp_var_bwd": ([_P, _P, C.POINTER(_P), _I, _P, _P, _I, _P, C.POINTER(_P), _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "mvs_pack_conv3d_weight": ([_P, _P, _I, _I, _I, _P], _I),
     "mvs_conv3d_fwd": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "mvs_conv3d_workspace_bytes": ([C.POINTER(Conv3dDesc)], _L),

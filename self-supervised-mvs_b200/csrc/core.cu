@@ -98,6 +98,47 @@ extern "C" int mvs_unpack_c8(const void* src, float* dst, int B, int C, int64_t 
     return MVS_CHECK_LAUNCH("mvs_unpack_c8");
 }
 
+// Zero-bordered C8 maps ("C8P") for the plane-sweep gather: dst [M][C/8][H + 3][W + 2][8], pixel (y, x) at row y + 1,
+// column x + 1, zeros elsewhere.  One thread writes one (map, channel block, padded pixel) vector; src_layout selects the
+// reader: 0 = fp32 [M][C][H][W], 1 = channels-last `T` [M][H][W][C], 2 = C8 `T` [M][C/8][H][W][8].
+template <typename T>
+__global__ void pack_c8_padded_kernel(const void* __restrict__ src, T* __restrict__ dst, int CB, int H, int W, int layout, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // ((m * CB + cb) * (H + 3) + yp) * (W + 2) + xp
+    if (i >= total) return;
+    const int Wp = W + 2, Hp = H + 3;
+    const int xp = (int)(i % Wp);
+    int64_t r = i / Wp;
+    const int yp = (int)(r % Hp); r /= Hp;
+    const int cb = (int)(r % CB);
+    const int64_t m = r / CB;
+    const int x = xp - 1, y = yp - 1;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+        const int64_t S = (int64_t)H * W, s = (int64_t)y * W + x;
+        if (layout == 0) {
+            const float* p = reinterpret_cast<const float*>(src) + (m * CB * 8 + (int64_t)cb * 8) * S + s;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (int64_t)k * S);
+        } else if (layout == 1) {
+            V8<T>::load(reinterpret_cast<const T*>(src) + ((m * S + s) * CB + cb) * 8, v);
+        } else {
+            V8<T>::load(reinterpret_cast<const T*>(src) + ((m * CB + cb) * S + s) * 8, v);
+        }
+    }
+    V8<T>::store(dst + i * 8, v);
+}
+
+extern "C" int mvs_pack_c8_padded(const void* src, void* dst, int M, int C, int H, int W, int src_layout, int dtype, void* stream) {
+    MVS_REQUIRE(src && dst, MVS_E_ARG, "mvs_pack_c8_padded: null pointer");
+    MVS_REQUIRE(M > 0 && C > 0 && H > 0 && W > 0 && C % 8 == 0, MVS_E_SHAPE, "mvs_pack_c8_padded: C=%d must be a positive multiple of 8", C);
+    MVS_REQUIRE(src_layout >= 0 && src_layout <= 2, MVS_E_ARG, "mvs_pack_c8_padded: src_layout must be 0 (fp32 NCHW), 1 (NHWC) or 2 (C8)");
+    const int64_t total = (int64_t)M * (C / 8) * (H + 3) * (W + 2);
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(pack_c8_padded_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, src, (T*)dst, C / 8, H, W, src_layout, total));
+    return MVS_CHECK_LAUNCH("mvs_pack_c8_padded");
+}
+
 // ---------------------------------------------------------------------------------------------- projections
 __device__ static void rel_rt(const double* src, const double* ref, float* rt) {
     double inv[16];

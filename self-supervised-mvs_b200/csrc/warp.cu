@@ -40,7 +40,8 @@ __device__ __forceinline__ void source_coord(const float (&ray)[3], const float*
 // The four bilinear taps of (ix, iy): pixel offset y*W+x (or -1 when the tap is outside the map; NaN and
 // inf coordinates fail every comparison and drop all taps) and weight, in ATen order nw, ne, sw, se.
 struct Taps { int off[4]; float w[4]; };
-__device__ __forceinline__ void bilinear_taps(float ix, float iy, int H, int W, Taps& t) {
+__device__ __forceinline__ void bilinear_taps(float ix, float iy, int H, int W, Taps& t, int pitch = 0) {
+    if (pitch == 0) pitch = W;
     const float x0 = floorf(ix), y0 = floorf(iy);
     const float x1 = x0 + 1.f, y1 = y0 + 1.f;
     const bool vx0 = (x0 >= 0.f) && (x0 <= (float)(W - 1)), vx1 = (x1 >= 0.f) && (x1 <= (float)(W - 1));
@@ -48,11 +49,11 @@ __device__ __forceinline__ void bilinear_taps(float ix, float iy, int H, int W, 
     const float wx0 = x1 - ix, wx1 = ix - x0, wy0 = y1 - iy, wy1 = iy - y0;
     const int xi = vx0 ? (int)x0 : (vx1 ? (int)x1 - 1 : 0);
     const int yi = vy0 ? (int)y0 : (vy1 ? (int)y1 - 1 : 0);
-    const int base = yi * W + xi;
-    t.off[0] = (vx0 && vy0) ? base : -1;          t.w[0] = wx0 * wy0;
-    t.off[1] = (vx1 && vy0) ? base + 1 : -1;      t.w[1] = wx1 * wy0;
-    t.off[2] = (vx0 && vy1) ? base + W : -1;      t.w[2] = wx0 * wy1;
-    t.off[3] = (vx1 && vy1) ? base + W + 1 : -1;  t.w[3] = wx1 * wy1;
+    const int base = yi * pitch + xi;
+    t.off[0] = (vx0 && vy0) ? base : -1;              t.w[0] = wx0 * wy0;
+    t.off[1] = (vx1 && vy0) ? base + 1 : -1;          t.w[1] = wx1 * wy0;
+    t.off[2] = (vx0 && vy1) ? base + pitch : -1;      t.w[2] = wx0 * wy1;
+    t.off[3] = (vx1 && vy1) ? base + pitch + 1 : -1;  t.w[3] = wx1 * wy1;
 }
 
 template <typename T>
@@ -77,7 +78,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(128)
 warp_var_fwd_kernel(const TI* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
                     const float* __restrict__ depth, int per_pixel, TO* __restrict__ var, int B, int CB, int D, int H,
-                    int W, int dper, int align_corners, int ref_sq_in_sum) {
+                    int W, int dper, int align_corners, int ref_sq_in_sum, int pad) {
     const int HW = H * W;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
@@ -87,10 +88,13 @@ warp_var_fwd_kernel(const TI* __restrict__ ref, SrcPtrs srcs, int nsrc, const fl
     const int cb = y % CB;
     const int b = y / CB;
     const float fx = (float)(p % W), fy = (float)(p / W);
-    const int64_t map_off = ((int64_t)b * CB + cb) * HW * 8;
+    // zero-bordered maps (pad): rows of W + 2 pixels, H + 3 rows, pixel (0, 0) at row 1, column 1
+    const int pitch = pad ? W + 2 : W, org = pad ? pitch + 1 : 0;
+    const int64_t map_off = (((int64_t)b * CB + cb) * (pad ? (int64_t)(H + 3) * pitch : (int64_t)HW) + org) * 8;
+    const int pp = (p / W) * pitch + (p % W);
 
     float r[8], r2[8];
-    V8<TI>::load(ref + map_off + (int64_t)p * 8, r);
+    V8<TI>::load(ref + map_off + (int64_t)pp * 8, r);
 #pragma unroll
     for (int k = 0; k < 8; ++k) r2[k] = r[k] * r[k];
 
@@ -112,7 +116,7 @@ warp_var_fwd_kernel(const TI* __restrict__ ref, SrcPtrs srcs, int nsrc, const fl
                 float ix, iy;
                 source_coord(ray[s], rt + ((int64_t)s * B + b) * 12, dv, H, W, align_corners, ix, iy);
                 Taps t;
-                bilinear_taps(ix, iy, H, W, t);
+                bilinear_taps(ix, iy, H, W, t, pitch);
                 float wv[8];
                 gather8<TI>(reinterpret_cast<const TI*>(srcs.p[s]) + map_off, t, wv);
 #pragma unroll
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(128)
 warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, SrcPtrs srcs, int nsrc,
                     const float* __restrict__ rt, const float* __restrict__ depth, int per_pixel,
                     float* __restrict__ gref, GradPtrs gsrcs, int B, int CB, int D, int H, int W, int dper,
-                    int align_corners, int ref_sq_in_sum) {
+                    int align_corners, int ref_sq_in_sum, int pad) {
     const int HW = H * W;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
@@ -145,10 +149,14 @@ warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, Src
     const int cb = y % CB;
     const int b = y / CB;
     const float fx = (float)(p % W), fy = (float)(p / W);
-    const int64_t map_off = ((int64_t)b * CB + cb) * HW * 8;
+    // feature maps may be zero-bordered (pad, see the forward kernel); gradient maps never are
+    const int pitch = pad ? W + 2 : W, org = pad ? pitch + 1 : 0;
+    const int64_t map_off = (((int64_t)b * CB + cb) * (pad ? (int64_t)(H + 3) * pitch : (int64_t)HW) + org) * 8;
+    const int64_t grad_off = ((int64_t)b * CB + cb) * HW * 8;
+    const int pp = (p / W) * pitch + (p % W);
 
     float r[8];
-    V8<TI>::load(ref + map_off + (int64_t)p * 8, r);
+    V8<TI>::load(ref + map_off + (int64_t)pp * 8, r);
     float ray[MVS_MAX_SRC][3];
 #pragma unroll
     for (int s = 0; s < MVS_MAX_SRC; ++s)
@@ -174,7 +182,7 @@ warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, Src
                 float ix, iy;
                 source_coord(ray[s], rt + ((int64_t)s * B + b) * 12, dv, H, W, align_corners, ix, iy);
                 Taps t;
-                bilinear_taps(ix, iy, H, W, t);
+                bilinear_taps(ix, iy, H, W, t, pitch);
                 float wv[8];
                 gather8<TI>(reinterpret_cast<const TI*>(srcs.p[s]) + map_off, t, wv);
 #pragma unroll
@@ -194,19 +202,20 @@ warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, Src
             if (s < nsrc && gsrcs.p[s] != nullptr) {
                 float ix, iy;
                 source_coord(ray[s], rt + ((int64_t)s * B + b) * 12, dv, H, W, align_corners, ix, iy);
-                Taps t;
-                bilinear_taps(ix, iy, H, W, t);
+                Taps t, tg;
+                bilinear_taps(ix, iy, H, W, t, pitch);    // gather offsets (feature maps)
+                bilinear_taps(ix, iy, H, W, tg, W);       // scatter offsets (gradient maps)
                 float wv[8];
                 gather8<TI>(reinterpret_cast<const TI*>(srcs.p[s]) + map_off, t, wv);
                 float c[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) c[k] = g[k] * (2.f * wv[k] * inv_n - m2[k]);
-                float* gs = gsrcs.p[s] + map_off;
+                float* gs = gsrcs.p[s] + grad_off;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (t.off[i] >= 0) {
+                    if (tg.off[i] >= 0) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) atomicAdd(gs + (int64_t)t.off[i] * 8 + k, c[k] * t.w[i]);
+                        for (int k = 0; k < 8; ++k) atomicAdd(gs + (int64_t)tg.off[i] * 8 + k, c[k] * tg.w[i]);
                     }
                 }
             }
@@ -214,7 +223,7 @@ warp_var_bwd_kernel(const TO* __restrict__ gvar, const TI* __restrict__ ref, Src
     }
     if (gref != nullptr) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(gref + map_off + (int64_t)p * 8 + k, gr[k]);
+        for (int k = 0; k < 8; ++k) atomicAdd(gref + grad_off + (int64_t)p * 8 + k, gr[k]);
     }
 }
 
@@ -231,12 +240,16 @@ template <> struct Pack2<__half> {
     static __device__ __forceinline__ __half2 splat(float w) { return __float2half2_rn(w); }
     static __device__ __forceinline__ float2 to_f2(__half2 v) { return __half22float2(v); }
     static __device__ __forceinline__ __half2 from_f2(float2 v) { return __float22half2_rn(v); }
+    static __device__ __forceinline__ __half2 lo(__half2 v) { return __low2half2(v); }
+    static __device__ __forceinline__ __half2 hi(__half2 v) { return __high2half2(v); }
 };
 template <> struct Pack2<__nv_bfloat16> {
     typedef __nv_bfloat162 type;
     static __device__ __forceinline__ __nv_bfloat162 splat(float w) { return __float2bfloat162_rn(w); }
     static __device__ __forceinline__ float2 to_f2(__nv_bfloat162 v) { return __bfloat1622float2(v); }
     static __device__ __forceinline__ __nv_bfloat162 from_f2(float2 v) { return __float22bfloat162_rn(v); }
+    static __device__ __forceinline__ __nv_bfloat162 lo(__nv_bfloat162 v) { return __low2bfloat162(v); }
+    static __device__ __forceinline__ __nv_bfloat162 hi(__nv_bfloat162 v) { return __high2bfloat162(v); }
 };
 
 template <typename T, int CPT, int NS, int MINB>   // NS = compile-time bound on the source count (register arrays are sized by it)
@@ -352,6 +365,133 @@ warp_var_fwd_fast_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, cons
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------ fused forward, 16-bit, zero-bordered maps
+// The production kernel.  Maps are "C8P": [M][C/8][H + 3][W + 2][8] with pixel (y, x) at row y + 1, column x + 1 and zeros
+// around it (mvs_pack_c8_padded).  With sampling coordinates clamped to the border, grid_sample's zero padding needs no tap
+// validity tests, no index clamps and no per-tap offsets: the four taps are base, +16 B, +row, +row + 16 B, and every tap
+// outside the map reads a stored zero.  A thread owns ALL channels of its pixel (CPT channel blocks), so the homography,
+// floor and weights are computed once per (voxel, source) instead of once per 16 channels; that halves the instruction count
+// of this issue-bound kernel (SASS: 147 -> ~95 instructions per source and 16 channels).
+template <typename T, int CPT, int NS, int MINB, bool REFSQ>
+__global__ void __launch_bounds__(128, MINB)
+warp_var_fwd_pad_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
+                        const float* __restrict__ depth, int per_pixel, T* __restrict__ var, int B, int CB, int D, int H,
+                        int W, int dper, int align_corners, int dzl) {
+    typedef typename Pack2<T>::type T2;
+    const int HW = H * W;
+    // A warp covers (32 >> dzl) consecutive pixels x (1 << dzl) consecutive depth planes: neighbouring planes sample
+    // neighbouring source pixels (the sweep moves a fraction of a pixel per plane), so the lanes of one gather instruction
+    // fall into 2-3 cache lines instead of 5, and the kernel is bound by exactly those L1 wavefronts.  Stores stay whole
+    // lines (8 pixels x 16 B = 128 B per plane at dzl = 2).
+    const int lane = threadIdx.x & 31, pxw = 32 >> dzl;
+    const int p = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * pxw + (lane & (pxw - 1));
+    const int dz = lane >> (5 - dzl), dstep = 1 << dzl;
+    if (p >= HW) return;
+    const int nchunk = (D + dper - 1) / dper;
+    const int CG = CB / CPT;
+    int y = blockIdx.y;
+    const int dc = y % nchunk; y /= nchunk;
+    const int cg = y % CG;
+    const int b = y / CG;
+    const int py = p / W, px = p - py * W;
+    const int pitch = W + 2;
+    const uint32_t row_b = (uint32_t)pitch * 16u;                 // bytes per map row
+    const uint32_t plane_b = (uint32_t)(H + 3) * row_b;           // bytes per channel block of a map
+    const int64_t map_b = ((int64_t)b * CB + (int64_t)cg * CPT) * plane_b;
+
+    uint4 rq[CPT];                                                // reference feature, kept packed
+    {
+        const char* rp = reinterpret_cast<const char*>(ref) + map_b + (uint32_t)((py + 1) * pitch + px + 1) * 16u;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) rq[c] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)c * plane_b));
+    }
+    // ix = u * sx + ox with u = (ray0 d + t0) / (ray2 d + t2): align_corners ? u : u * W/(W-1) - 0.5, plus 1 for the border;
+    // the scale is folded into the ray and the translation
+    const float sx = align_corners ? 1.f : (float)W / (float)(W - 1), sy = align_corners ? 1.f : (float)H / (float)(H - 1);
+    const float oxy = (align_corners ? 0.f : -0.5f) + 1.f;
+    float rx[NS], ry[NS], rz[NS], tx[NS], ty[NS], tz[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if (s < nsrc) {
+            const float* m = rt + ((int64_t)s * B + b) * 12;
+            float ray[3];
+            pixel_ray(m, (float)px, (float)py, ray);
+            rx[s] = ray[0] * sx; ry[s] = ray[1] * sy; rz[s] = ray[2];
+            tx[s] = __ldg(m + 9) * sx; ty[s] = __ldg(m + 10) * sy; tz[s] = __ldg(m + 11);
+        }
+    const float xmax = (float)(W + 1), ymax = (float)(H + 1);
+    const float inv_n = 1.f / (float)(nsrc + 1);
+    const float2 inv_n2 = make_float2(inv_n, inv_n);
+
+    const int d_end = min(D, (dc + 1) * dper);
+    for (int d = dc * dper + dz; d < d_end; d += dstep) {
+        const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+        // running sums over the SOURCES only (source 0 initialises them); the reference feature joins in the epilogue
+        float2 s1[CPT][4], s2[CPT][4];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (s < nsrc) {
+                const float pz = fmaf(rz[s], dv, tz[s]);
+                float iz;                                        // pz == 0 -> inf -> NaN / inf coordinates -> clamped to the zero border
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(pz));
+                // clamp to the border ring (fmaxf drops a NaN): beyond it every tap is outside the map and reads zeros anyway
+                const float ix = fminf(fmaxf(fmaf(fmaf(rx[s], dv, tx[s]), iz, oxy), 0.f), xmax);
+                const float iy = fminf(fmaxf(fmaf(fmaf(ry[s], dv, ty[s]), iz, oxy), 0.f), ymax);
+                // floor + float->int without the conversion pipe: adding 1.5 * 2^23 rounding down leaves floor() in the mantissa
+                const float kMagic = 12582912.f;
+                const float fxm = __fadd_rd(ix, kMagic), fym = __fadd_rd(iy, kMagic);
+                const int xi = __float_as_int(fxm) - 0x4B400000, yi = __float_as_int(fym) - 0x4B400000;
+                const float wx = ix - (fxm - kMagic), wy = iy - (fym - kMagic);      // exact fractional parts
+                const float w11 = wx * wy, w10 = wx - w11, w01 = wy - w11, w00 = (1.f - wx) - w01;
+                const T2 wa = Pack2<T>::from_f2(make_float2(w00, w10)), wb = Pack2<T>::from_f2(make_float2(w01, w11));
+                const T2 w0 = Pack2<T>::lo(wa), w1 = Pack2<T>::hi(wa), w2 = Pack2<T>::lo(wb), w3 = Pack2<T>::hi(wb);
+                const char* base = reinterpret_cast<const char*>(srcs.p[s]) + map_b + (uint32_t)(yi * pitch + xi) * 16u;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const char* m = base + (size_t)c * plane_b;
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(m));
+                    const uint4 bq = __ldg(reinterpret_cast<const uint4*>(m + 16));
+                    const uint4 cq = __ldg(reinterpret_cast<const uint4*>(m + row_b));
+                    const uint4 dq = __ldg(reinterpret_cast<const uint4*>(m + row_b + 16));
+                    const T2* ha = reinterpret_cast<const T2*>(&a);
+                    const T2* hb = reinterpret_cast<const T2*>(&bq);
+                    const T2* hc = reinterpret_cast<const T2*>(&cq);
+                    const T2* hd = reinterpret_cast<const T2*>(&dq);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        T2 v = __hmul2(ha[j], w0);
+                        v = __hfma2(hb[j], w1, v);
+                        v = __hfma2(hc[j], w2, v);
+                        v = __hfma2(hd[j], w3, v);
+                        const float2 f = Pack2<T>::to_f2(v);
+                        if (s == 0) { s1[c][j] = f; s2[c][j] = __fmul2_rn(f, f); }
+                        else { s1[c][j] = __fadd2_rn(s1[c][j], f); s2[c][j] = __ffma2_rn(f, f, s2[c][j]); }
+                    }
+                }
+            }
+        }
+        T* vp = var + ((((int64_t)b * CB + cg * CPT) * D + d) * HW + p) * 8;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            uint4 out;
+            T2* ho = reinterpret_cast<T2*>(&out);
+#pragma unroll
+            const T2* h = reinterpret_cast<const T2*>(&rq[c]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // var = (S2 + r^2) / N - ((S1 + r) / N)^2 = ((S2 + r^2) - (S1 + r)^2 / N) / N     (S1 + r^2 when REFSQ, hazard H2)
+                const float2 r = Pack2<T>::to_f2(h[j]);
+                float2 t, u;
+                if (REFSQ) { const float2 r2 = __fmul2_rn(r, r); t = __fadd2_rn(s1[c][j], r2); u = __fadd2_rn(s2[c][j], r2); }
+                else { t = __fadd2_rn(s1[c][j], r); u = __ffma2_rn(r, r, s2[c][j]); }
+                const float2 v = __ffma2_rn(__fmul2_rn(t, t), make_float2(-inv_n, -inv_n), u);
+                ho[j] = Pack2<T>::from_f2(__fmul2_rn(v, inv_n2));
+            }
+            *reinterpret_cast<uint4*>(vp + (int64_t)c * D * HW * 8) = out;
+        }
+    }
+}
 #endif  // !MVS_CPU_EMU
 
 static int depth_chunk(int D, int HW, int B, int CB) {
@@ -375,7 +515,7 @@ static int check_warp_var(const void* ref, const void* const* srcs, int nsrc, co
 
 extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int nsrc, const float* rt, const float* depth,
                                 int per_pixel, void* var, int B, int C, int D, int H, int W, int dtype_in, int dtype_out,
-                                int align_corners, int ref_sq_in_sum, void* stream) {
+                                int align_corners, int ref_sq_in_sum, int pad, void* stream) {
     int rc = check_warp_var(ref, srcs, nsrc, rt, depth, B, C, D, H, W);
     if (rc) return rc;
     MVS_REQUIRE(var, MVS_E_ARG, "mvs_warp_var_fwd: null output");
@@ -383,8 +523,37 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     for (int s = 0; s < MVS_MAX_SRC; ++s) sp.p[s] = s < nsrc ? srcs[s] : nullptr;
     const int CB = C / 8, HW = H * W;
 #ifndef MVS_CPU_EMU
-    if (dtype_in == dtype_out && dtype_in != MVS_F32 && CB % 2 == 0) {
-        // 16-bit storage: packed-math kernel, 2 channel blocks per thread, source-count bound in {2,4,6,8}
+    if (dtype_in == dtype_out && dtype_in != MVS_F32 && pad && CB % 2 == 0) {
+        // 16-bit storage, zero-bordered maps: packed-math kernel, all channels of a pixel in one thread when C % 32 == 0
+        MVS_REQUIRE((int64_t)(H + 3) * (W + 2) * 16 < (1ll << 31), MVS_E_SHAPE, "mvs_warp_var_fwd: maps too large");
+        static const int cpt_knob = [] { const char* e = getenv("MVS_WARP_CPT"); return e ? atoi(e) : 2; }();     // tuning knobs; measured at N=5, C=32, D=192, 128x160 x4 items:
+        // CPT 2 / 4 blocks per SM 0.76 ms, CPT 4 / 3 blocks 0.91 ms (fewer instructions but too few warps to hide the gathers)
+        static const int minb4 = [] { const char* e = getenv("MVS_WARP_MINB"); return e ? atoi(e) : 3; }();
+        static const int dz_knob = [] { const char* e = getenv("MVS_WARP_DZ"); return e ? atoi(e) : 1; }();     // measured: 0 -> 0.795, 1 -> 0.759, 2 -> 0.768, 3 -> 0.813 ms
+        const int cpt = (CB % 4 == 0 && cpt_knob == 4) ? 4 : 2;
+        int dzl = dz_knob < 0 ? 0 : (dz_knob > 3 ? 3 : dz_knob);
+        while (dzl > 0 && (1 << dzl) > D) --dzl;
+        // a block = 4 warps = (128 >> dzl) pixels x (1 << dzl) planes per step; chunks of >= 8 steps, >= ~4 waves of blocks
+        const int ptiles = (int)mvs_cdiv(HW, 128 >> dzl);
+        int dperf = D;
+        while (dperf > (8 << dzl) && (int64_t)ptiles * B * (CB / cpt) * ((D + dperf - 1) / dperf) < 148 * 8 * 4) dperf = (dperf + 1) / 2;
+        dperf = (dperf + (1 << dzl) - 1) >> dzl << dzl;
+        const dim3 gridf((unsigned)ptiles, (unsigned)(B * (CB / cpt) * ((D + dperf - 1) / dperf)));
+#define MVS_WP_ARGS(T) (const T*)ref, sp, nsrc, rt, depth, per_pixel, (T*)var, B, CB, D, H, W, dperf, align_corners, dzl
+#define MVS_WP_LAUNCH(T, CPT, NS, MB) do { if (ref_sq_in_sum) warp_var_fwd_pad_kernel<T, CPT, NS, MB, true><<<gridf, 128, 0, (cudaStream_t)stream>>>(MVS_WP_ARGS(T)); \
+                                           else warp_var_fwd_pad_kernel<T, CPT, NS, MB, false><<<gridf, 128, 0, (cudaStream_t)stream>>>(MVS_WP_ARGS(T)); } while (0)
+#define MVS_WP_BY_NS(T, CPT, MB) do { if (nsrc <= 2) MVS_WP_LAUNCH(T, CPT, 2, MB); else if (nsrc <= 4) MVS_WP_LAUNCH(T, CPT, 4, MB); \
+                                      else if (nsrc <= 6) MVS_WP_LAUNCH(T, CPT, 6, MB); else MVS_WP_LAUNCH(T, CPT, 8, MB); } while (0)
+#define MVS_WP_BY_CPT(T) do { if (cpt == 4 && minb4 == 2) MVS_WP_BY_NS(T, 4, 2); else if (cpt == 4) MVS_WP_BY_NS(T, 4, 3); else MVS_WP_BY_NS(T, 2, 4); } while (0)
+        if (dtype_in == MVS_F16) MVS_WP_BY_CPT(__half); else MVS_WP_BY_CPT(__nv_bfloat16);
+#undef MVS_WP_BY_CPT
+#undef MVS_WP_BY_NS
+#undef MVS_WP_LAUNCH
+#undef MVS_WP_ARGS
+        return MVS_CHECK_LAUNCH("mvs_warp_var_fwd");
+    }
+    if (dtype_in == dtype_out && dtype_in != MVS_F32 && CB % 2 == 0 && !pad) {
+        // 16-bit storage, plain C8 maps: packed-math kernel, 2 channel blocks per thread, source-count bound in {2,4,6,8}
         const int dperf = depth_chunk(D, HW, B, CB / 2);
         const dim3 gridf(mvs_cdiv(HW, 128), (unsigned)(B * (CB / 2) * ((D + dperf - 1) / dperf)));
         static const int mb4 = [] { const char* e = getenv("MVS_WARP_MINB"); return e ? atoi(e) : 4; }();   // tuning knob: 4 blocks/SM (122 registers, no spills) measured faster than 5 (96, spills)
@@ -402,14 +571,14 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     const dim3 grid(mvs_cdiv(HW, 128), (unsigned)(B * CB * ((D + dper - 1) / dper)));
     MVS_DISPATCH_DTYPE(dtype_in, TI, MVS_DISPATCH_DTYPE(dtype_out, TO,
         MVS_LAUNCH((warp_var_fwd_kernel<TI, TO>), grid, dim3(128), stream, (const TI*)ref, sp, nsrc, rt, depth, per_pixel,
-                   (TO*)var, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum)));
+                   (TO*)var, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum, pad)));
     return MVS_CHECK_LAUNCH("mvs_warp_var_fwd");
 }
 
 extern "C" int mvs_warp_var_bwd(const void* grad_var, const void* ref, const void* const* srcs, int nsrc, const float* rt,
                                 const float* depth, int per_pixel, float* grad_ref, float* const* grad_srcs, int B, int C,
                                 int D, int H, int W, int dtype_in, int dtype_out, int align_corners, int ref_sq_in_sum,
-                                void* stream) {
+                                int pad, void* stream) {
     int rc = check_warp_var(ref, srcs, nsrc, rt, depth, B, C, D, H, W);
     if (rc) return rc;
     MVS_REQUIRE(grad_var && grad_srcs, MVS_E_ARG, "mvs_warp_var_bwd: null pointer");
@@ -421,7 +590,7 @@ extern "C" int mvs_warp_var_bwd(const void* grad_var, const void* ref, const voi
     const dim3 grid(mvs_cdiv(HW, 128), (unsigned)(B * CB * ((D + dper - 1) / dper)));
     MVS_DISPATCH_DTYPE(dtype_in, TI, MVS_DISPATCH_DTYPE(dtype_out, TO,
         MVS_LAUNCH((warp_var_bwd_kernel<TI, TO>), grid, dim3(128), stream, (const TO*)grad_var, (const TI*)ref, sp, nsrc, rt,
-                   depth, per_pixel, grad_ref, gp, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum)));
+                   depth, per_pixel, grad_ref, gp, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum, pad)));
     return MVS_CHECK_LAUNCH("mvs_warp_var_bwd");
 }
 

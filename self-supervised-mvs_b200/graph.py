@@ -44,3 +44,71 @@ class GraphedForward:
         self.graph.replay()
         _lib.launches += self.launches_per_replay
         return self.static_out
+
+
+class StreamedForward:
+    """Host-to-host inference pipeline around a `GraphedForward`: pinned host batch -> device -> forward -> pinned host result,
+    double-buffered so that the upload of batch i+1 (copy stream) overlaps the kernels of batch i (compute stream).
+
+        pipe = StreamedForward(graphed, ("depth", "photometric_confidence"))
+        for out in pipe.run(host_batches):      # out: dict of pinned host tensors, valid until two batches later
+            ...
+
+    Every batch is copied host->device and every result device->host; nothing is cached between batches."""
+
+    def __init__(self, graphed: GraphedForward, out_keys: Sequence[str]):
+        self.g = graphed
+        self.keys = tuple(out_keys)
+        self.copy = torch.cuda.Stream()
+        self.stage = [[torch.empty_like(t) for t in graphed.static_in] for _ in range(2)]
+        self.uploaded = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.out_host = [{k: torch.empty(graphed.static_out[k].shape, dtype=graphed.static_out[k].dtype).pin_memory() for k in self.keys}
+                         for _ in range(2)]
+        self.out_done = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in graphed.static_in)
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.out_host[0].values())
+
+    def upload(self, i: int, host_inputs: Sequence[torch.Tensor]) -> None:
+        s = i & 1
+        self.copy.wait_event(self.consumed[s])          # the forward of batch i-2 has read this staging set
+        with torch.cuda.stream(self.copy):
+            for dst, src in zip(self.stage[s], host_inputs):
+                dst.copy_(src, non_blocking=True)
+            self.uploaded[s].record(self.copy)
+
+    def forward(self, i: int) -> Dict[str, torch.Tensor]:
+        s = i & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.uploaded[s])
+        for dst, src in zip(self.g.static_in, self.stage[s]):
+            dst.copy_(src, non_blocking=True)           # device-to-device into the graph's static inputs
+        self.consumed[s].record(cur)
+        self.g.graph.replay()
+        _lib.launches += self.g.launches_per_replay
+        for k in self.keys:
+            self.out_host[s][k].copy_(self.g.static_out[k], non_blocking=True)
+        self.out_done[s].record(cur)
+        return self.out_host[s]
+
+    def run(self, host_batches):
+        """Yield the host result of every batch, in order.  One forward stays in flight behind the one being handed out and
+        one upload ahead of it, so the GPU never waits for the host; a yielded dict is valid until the next iteration."""
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self.upload(0, nxt)
+        i, pending = 0, None
+        while nxt is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                self.upload(i + 1, nxt)
+            out = self.forward(i)
+            if pending is not None:
+                self.out_done[(i - 1) & 1].synchronize()
+                yield pending
+            pending = out
+            i += 1
+        self.out_done[(i - 1) & 1].synchronize()
+        yield pending

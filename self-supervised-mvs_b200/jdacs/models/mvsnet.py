@@ -163,8 +163,11 @@ class MVSNet(nn.Module):
         # step 1. feature extraction (library code).  In eval mode all views share one batched call; in training
         # each view is its own call, because BatchNorm2d statistics are per call in the reference (:115).
         dt = torch.float32 if self.training else self.volume_dtype
+        rt = ops.compose_proj(proj_matrices)
         if self.training:
             features = [self.feature(imgs[:, v]) for v in range(n)]
+            # step 2. plane sweep: warp + variance, fused (:120-136)
+            variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
         else:
             x = imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:])
             if dt != torch.float32 and x.is_cuda and self.feature_autocast:
@@ -172,10 +175,9 @@ class MVSNet(nn.Module):
                 f = self.feature.forward_folded(x, dt)
             else:
                 f = self.feature(x)
-            features = list(f.reshape(n, b, *f.shape[1:]).unbind(0))
-        # step 2. plane sweep: warp + variance, fused (:120-136)
-        rt = ops.compose_proj(proj_matrices)
-        variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
+            # step 2. all views go to the zero-bordered gather layout in one launch, then the fused plane sweep
+            maps = ops.pack_c8_padded(f, dt)
+            variance = ops.warp_variance_maps(maps.view(n, b, *maps.shape[1:]), rt, depth_values, dt, self.align_corners, False)
         # step 3. regularisation (:139-141)
         self.cost_regularization.act_dtype = None if self.training else dt
         cost_reg = self.cost_regularization(variance)

@@ -43,6 +43,31 @@ def pack_c8(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
     return out
 
 
+def pack_c8_padded(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
+    """[M,C,H,W] (fp32 NCHW, or channels-last `dtype`) or C8 [M,C/8,H,W,8] `dtype` -> zero-bordered C8P [M,C/8,H+3,W+2,8] `dtype`:
+    pixel (y, x) sits at row y+1, column x+1 (the layout the fused warp+variance kernel gathers from)."""
+    x = x.detach()
+    if x.dim() == 5:
+        if x.dtype != dtype:
+            raise ValueError("a C8 input must already be in the target dtype")
+        x = x.contiguous()
+        m, cb, h, w, _ = x.shape
+        c, layout = cb * 8, 2
+    elif x.dim() == 4:
+        m, c, h, w = x.shape
+        if c % 8:
+            raise ValueError("C8 layout needs a channel count divisible by 8, got %d" % c)
+        if x.dtype == dtype and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+            layout = 1
+        else:
+            x, layout = _f32c(x), 0
+    else:
+        raise ValueError("expected [M,C,H,W] or C8 [M,C/8,H,W,8], got %s" % (tuple(x.shape),))
+    out = torch.empty(m, c // 8, h + 3, w + 2, 8, dtype=dtype, device=x.device)
+    call("mvs_pack_c8_padded", x, ptr(x), ptr(out), m, c, h, w, layout, dtype_code(dtype))
+    return out
+
+
 def unpack_c8(x: Tensor) -> Tensor:
     """C8 [B,C/8,*spatial,8] -> fp32 [B,C,*spatial]."""
     x = x.detach().contiguous()
@@ -118,15 +143,15 @@ class _WarpVariance(torch.autograd.Function):
     def forward(ctx, rt: Tensor, depth: Tensor, dtype: torch.dtype, align_corners: bool, ref_sq_in_sum: bool,
                 ref_fea: Tensor, *src_feas: Tensor) -> Tensor:
         fdt = torch.float32 if dtype == torch.float32 else dtype
-        ref8 = pack_c8(ref_fea, fdt)
-        src8 = [pack_c8(s, fdt) for s in src_feas]
+        ref8 = pack_c8_padded(ref_fea, fdt)
+        src8 = [pack_c8_padded(s, fdt) for s in src_feas]
         depth = _f32c(depth)
         b, c, h, w = ref_fea.shape
         d = depth.shape[1]
         per_pixel = int(depth.dim() == 4)
         var = torch.empty(b, c // 8, d, h, w, 8, dtype=dtype, device=ref_fea.device)
         call("mvs_warp_var_fwd", ref8, ptr(ref8), _ptr_array(src8), len(src8), ptr(rt), ptr(depth), per_pixel, ptr(var),
-             b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), int(align_corners), int(ref_sq_in_sum))
+             b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), int(align_corners), int(ref_sq_in_sum), 1)
         ctx.save_for_backward(rt, depth, ref8, *src8)
         ctx.meta = (b, c, d, h, w, per_pixel, fdt, dtype, int(align_corners), int(ref_sq_in_sum))
         return var
@@ -141,17 +166,37 @@ class _WarpVariance(torch.autograd.Function):
         gsrc = [torch.zeros(b, c // 8, h, w, 8, dtype=torch.float32, device=g.device) if need[6 + i] else None
                 for i in range(len(src8))]
         call("mvs_warp_var_bwd", g, ptr(g), ptr(ref8), _ptr_array(src8), len(src8), ptr(rt), ptr(depth), per_pixel,
-             ptr(gref), _ptr_array(gsrc), b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), ac, rsq)
+             ptr(gref), _ptr_array(gsrc), b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), ac, rsq, 1)
         outs = [None if t is None else unpack_c8(t) for t in [gref] + gsrc]
         return (None, None, None, None, None, *outs)
 
 
 def warp_variance(ref_fea: Tensor, src_feas: Sequence[Tensor], rt: Tensor, depth: Tensor,
                   dtype: torch.dtype = torch.float32, align_corners: bool = False, ref_sq_in_sum: bool = False) -> Tensor:
-    """Variance cost volume (C8, `dtype`) of the reference map and nsrc warped source maps ([B,C,H,W] fp32 each)."""
+    """Variance cost volume (C8, `dtype`) of the reference map and nsrc warped source maps ([B,C,H,W] each; fp32, or
+    channels-last `dtype` as the library feature extractor emits them)."""
     if len(src_feas) < 1 or len(src_feas) > _lib.MAX_SRC:
         raise ValueError("need 1..%d source views, got %d" % (_lib.MAX_SRC, len(src_feas)))
     return _WarpVariance.apply(rt.contiguous(), depth, dtype, align_corners, ref_sq_in_sum, ref_fea, *src_feas)
+
+
+def warp_variance_maps(maps: Tensor, rt: Tensor, depth: Tensor, dtype: torch.dtype, align_corners: bool = False,
+                       ref_sq_in_sum: bool = False) -> Tensor:
+    """Inference form (no autograd): `maps` = zero-bordered C8P maps of ALL views, [N,B,C/8,H+3,W+2,8] in `dtype`
+    (pack_c8_padded of the stacked features), view 0 = reference.  Returns the C8 variance volume [B,C/8,D,H,W,8]."""
+    n, b, cb, hp, wp, _ = maps.shape
+    if n < 2 or n - 1 > _lib.MAX_SRC:
+        raise ValueError("need 2..%d views, got %d" % (_lib.MAX_SRC + 1, n))
+    if maps.dtype != dtype or not maps.is_contiguous():
+        raise ValueError("maps must be contiguous and stored in the volume dtype")
+    h, w = hp - 3, wp - 2
+    depth = _f32c(depth)
+    d = depth.shape[1]
+    var = torch.empty(b, cb, d, h, w, 8, dtype=dtype, device=maps.device)
+    call("mvs_warp_var_fwd", maps, ptr(maps[0]), _ptr_array([maps[v] for v in range(1, n)]), n - 1, ptr(rt.contiguous()), ptr(depth),
+         int(depth.dim() == 4), ptr(var), b, cb * 8, d, h, w, dtype_code(dtype), dtype_code(dtype), int(align_corners),
+         int(ref_sq_in_sum), 1)
+    return var
 
 
 # ------------------------------------------------------------------------------------------------ 3-D convolution

@@ -113,6 +113,65 @@ def test_warp_variance_odd_sizes(be, oracle):
     assert rel_err(ops.unpack_c8(v), want) < TOL
 
 
+def test_pack_c8_padded_layouts(be):
+    """Zero-bordered gather layout from the three source layouts: interior = the map, border = zeros."""
+    ops = _ops()
+    torch.manual_seed(5)
+    x = torch.randn(3, 16, 5, 9)
+    want = F.pad(x, (1, 1, 1, 2)).reshape(3, 2, 8, 8, 11).permute(0, 1, 3, 4, 2)
+    a = ops.pack_c8_padded(be.to(x))                                                        # fp32 NCHW
+    b = ops.pack_c8_padded(be.to(x).contiguous(memory_format=torch.channels_last))          # channels-last
+    c = ops.pack_c8_padded(ops.pack_c8(be.to(x)))                                           # C8
+    for got in (a, b, c):
+        assert got.shape == (3, 2, 8, 11, 8) and torch.equal(got.cpu(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("channels,nsrc,ref_sq,per_pixel", [(32, 4, False, False), (16, 2, True, True), (32, 3, False, True),
+                                                           (16, 6, False, False), (8, 2, False, False), (64, 1, True, False)])
+def test_warp_variance_16bit_padded(gpu, oracle, dtype, tol, channels, nsrc, ref_sq, per_pixel):
+    """The production kernel (16-bit storage, zero-bordered maps; 4 / 2 channel blocks per thread; every source-count
+    bucket) against the oracle on features rounded to the storage type: agreement to the storage rounding."""
+    ops = _ops()
+    from ssmvs_b200 import synth
+    inp = synth.feature_inputs(2, nsrc + 1, channels, 21, 37, 12, seed=7)
+    f = [t.to(dtype).float() for t in inp["features"]]
+    P = inp["proj_matrices"]
+    depth = inp["depth_values"]
+    if per_pixel:
+        depth = depth.view(2, -1, 1, 1) + 3.0 * torch.randn(2, depth.shape[1], 21, 37)
+    rt = ops.compose_proj(gpu.to(P))
+    maps = ops.pack_c8_padded(gpu.to(torch.stack(f, 0).flatten(0, 1)), dtype)
+    v = ops.warp_variance_maps(maps.view(nsrc + 1, 2, *maps.shape[1:]), rt, gpu.to(depth), dtype, False, ref_sq)
+    want = oracle.variance_volume(f[0], f[1:], P[:, 0], [P[:, s] for s in range(1, nsrc + 1)], depth, ref_sq, False)
+    got = ops.unpack_c8(v).cpu()
+    assert (got - want).abs().max().item() < tol * want.abs().max().item()
+    # the autograd entry takes the same kernel
+    v2 = ops.warp_variance(gpu.to(f[0]), [gpu.to(t) for t in f[1:]], rt, gpu.to(depth), dtype, False, ref_sq)
+    assert torch.equal(v2, v)
+
+
+@pytest.mark.gpu
+def test_warp_variance_16bit_padded_degenerate(gpu):
+    """Planes behind / through the source camera and non-finite depths: finite output, exact zeros where every tap is
+    outside the map (variance of (ref, 0) = ref^2 / 4), no out-of-bounds access at the clamped borders."""
+    ops = _ops()
+    torch.manual_seed(2)
+    feats = torch.randn(2, 1, 16, 10, 14)
+    P = torch.eye(4).reshape(1, 1, 4, 4).repeat(1, 2, 1, 1)
+    P[0, 1, 2, 3] = -10.0  # source camera: z = depth - 10
+    P[0, 1, 0, 3] = 3.0
+    depth = torch.tensor([[10.0, 5.0, float("nan"), float("inf"), 1e30, 1e-30, 10.0001, 11.0]])
+    rt = ops.compose_proj(gpu.to(P))
+    maps = ops.pack_c8_padded(gpu.to(feats.flatten(0, 1)), torch.float16)
+    v = ops.unpack_c8(ops.warp_variance_maps(maps.view(2, 1, *maps.shape[1:]), rt, gpu.to(depth), torch.float16)).cpu()
+    assert torch.isfinite(v).all()
+    r = feats[0].half().float()
+    for d in (0, 2, 3):
+        assert torch.allclose(v[:, :, d], r * r / 4, rtol=2e-3, atol=1e-4)
+
+
 def test_soft_argmin(be, oracle, golden):
     ops = _ops()
     g = golden("jdacs_mvsnet")
