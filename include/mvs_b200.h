@@ -118,6 +118,28 @@ int64_t mvs_conv3d_workspace_bytes(const mvs_conv3d_desc* d);
  * packed under the opposite `transposed` flag, exactly how ATen defines conv_transpose3d.) */
 int mvs_conv3d_bwd_weight(const mvs_conv3d_desc* d, const void* x, const float* grad_y, float* grad_w, void* stream);
 
+/* ---- f1 (next row): the 2-D feature extractors on the same tcgen05 kernel ---------------------------------------------------
+ * A stack of M images is convolved as a volume whose depth axis is the image index (no taps across images):
+ *   x: C8 stack [Cin/8][M][Hin][Win][8];  y: C8 stack [Cout/8][M][Hout][Wout][8], or (out_padded) the zero-bordered
+ *   image-major maps [M][Cout/8][Hout+3][Wout+2][8] that mvs_warp_var_fwd(pad=1) gathers from (border pre-zeroed by the caller).
+ *   y = [relu](conv(x) * scale + shift);  g = gather-form weights G[ksize*ksize][Cin][CoutPad] fp32 (tap = kh * ksize + kw).
+ * ksize/stride: 3/1 (pad 1) or 5/2 (pad 2, even Hin/Win).  Replaces ConvBnReLU / Conv2d of FeatureNet
+ * (jdacs/models/mvsnet.py:17-34, module.py:13-32) in eval mode with 16-bit storage. */
+typedef struct {
+    int M, Cin, Cout;      /* Cin in {8,16,32,48,64} (3-channel images are zero-padded to 8), Cout in {8,..,64} */
+    int Hin, Win, Hout, Wout;
+    int ksize, stride;
+    int dtype;             /* MVS_F16 | MVS_BF16 */
+    int relu;
+    int out_padded;
+    int ws_packed;         /* 1: `ws` already holds the weight tiles of an earlier call with the same g (frozen weights) */
+} mvs_conv2d_desc;
+int64_t mvs_conv2d_workspace_bytes(const mvs_conv2d_desc* d);
+int mvs_conv2d_fwd(const mvs_conv2d_desc* d, const void* x, const float* g, const float* scale, const float* shift, void* y,
+                   void* ws, void* stream);
+/* fp32 images [B][N][3][H][W] -> C8 stack [1][M = N*B][H][W][8] in `dtype`, image index m = v * B + b, channels 3..7 zero. */
+int mvs_pack_images_c8(const float* imgs, void* dst, int B, int N, int H, int W, int dtype, void* stream);
+
 /* batch-norm helpers for training mode (statistics over B*D*H*W per channel), C8 fp32 volumes.
  * sums = [2][C] (sum, sum of squares), zero-initialised by the caller.  jdacs/models/module.py:39-42. */
 int mvs_bn_stats(const float* x, float* sums, int B, int C, int64_t S, void* stream);

@@ -26,6 +26,11 @@ class Conv3dDesc(C.Structure):
                                        "transposed", "dtype_in", "dtype_out", "relu", "algo")]
 
 
+class Conv2dDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("M", "Cin", "Cout", "Hin", "Win", "Hout", "Wout", "ksize", "stride", "dtype", "relu",
+                                       "out_padded", "ws_packed")]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _SIGS = {
     "mvs_version": ([], _I),
@@ -45,6 +50,9 @@ _SIGS = {
     "mvs_conv3d_fwd": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "mvs_conv3d_workspace_bytes": ([C.POINTER(Conv3dDesc)], _L),
     "mvs_conv3d_bwd_weight": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P], _I),
+    "mvs_conv2d_workspace_bytes": ([C.POINTER(Conv2dDesc)], _L),
+    "mvs_conv2d_fwd": ([C.POINTER(Conv2dDesc), _P, _P, _P, _P, _P, _P, _P], _I),
+    "mvs_pack_images_c8": ([_P, _P, _I, _I, _I, _I, _I, _P], _I),
     "mvs_bn_stats": ([_P, _P, _I, _I, _L, _P], _I),
     "mvs_bn_act_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P], _I),
     "mvs_bn_act_bwd_reduce": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P], _I),
@@ -62,9 +70,12 @@ _emulation = False
 launches = 0  # kernel-launching C-ABI calls made through this module (bench.py reports it)
 
 
-def bind(path: str = DEFAULT_PATH) -> C.CDLL:
-    """Load the shared library at `path` and type every export.  Raises if anything is missing."""
+def bind(path: Optional[str] = None) -> C.CDLL:
+    """Load the shared library at `path` (default: the in-tree build; MVS_B200_LIB overrides it for A/B builds of the same
+    sources) and type every export.  Raises if anything is missing."""
     global _lib, _emulation
+    if path is None:
+        path = os.environ.get("MVS_B200_LIB", DEFAULT_PATH)
     if not os.path.exists(path):
         raise RuntimeError(
             "libmvs_b200.so not found at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -144,7 +144,33 @@ int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, c
                       const void* skip, void* y, void* ws, void* stream);  // conv3d_tc.cu
 int mvs_conv3d_tc_supported(const mvs_conv3d_desc* d);
 int64_t mvs_conv3d_tc_workspace_bytes(const mvs_conv3d_desc* d);
+int64_t mvs_conv2d_tc_workspace_bytes(const mvs_conv2d_desc* d);
+int mvs_conv2d_fwd_tc(const mvs_conv2d_desc* d, const void* x, const float* g, const float* scale, const float* shift, void* y,
+                      void* ws, void* stream);
 #endif
+
+// 2-D feature-extractor layers: tcgen05 only (eval mode, 16-bit storage); training keeps the library 2-D convolutions.
+extern "C" int64_t mvs_conv2d_workspace_bytes(const mvs_conv2d_desc* d) {
+#ifndef MVS_CPU_EMU
+    if (d) return mvs_conv2d_tc_workspace_bytes(d);
+#endif
+    (void)d;
+    return 0;
+}
+
+extern "C" int mvs_conv2d_fwd(const mvs_conv2d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
+                              void* y, void* ws, void* stream) {
+    MVS_REQUIRE(d && x && g && y, MVS_E_ARG, "mvs_conv2d_fwd: null pointer");
+    MVS_REQUIRE(d->M > 0 && d->Hin > 0 && d->Win > 0, MVS_E_SHAPE, "mvs_conv2d_fwd: bad dims");
+    MVS_REQUIRE(d->stride == 1 ? (d->Hout == d->Hin && d->Wout == d->Win) : (d->Hout * 2 == d->Hin && d->Wout * 2 == d->Win), MVS_E_SHAPE,
+                "mvs_conv2d_fwd: output extent %dx%d does not match input %dx%d at stride %d", d->Hout, d->Wout, d->Hin, d->Win, d->stride);
+#ifndef MVS_CPU_EMU
+    return mvs_conv2d_fwd_tc(d, x, g, scale, shift, y, ws, stream);
+#else
+    (void)scale; (void)shift; (void)ws; (void)stream;
+    return mvs_set_error(MVS_E_UNSUPPORTED, "mvs_conv2d_fwd: the tcgen05 path does not exist in the emulation build");
+#endif
+}
 
 extern "C" int64_t mvs_conv3d_workspace_bytes(const mvs_conv3d_desc* d) {
 #ifndef MVS_CPU_EMU

@@ -33,7 +33,14 @@
 
 namespace {
 
-constexpr int kEpiWarps = 8;      // two warps per TMEM lane quadrant, taking alternate M-tiles
+#ifndef MVS_TC_EPIWARPS
+#define MVS_TC_EPIWARPS 8
+#endif
+// 8: two warps per TMEM lane quadrant taking alternate M-tiles; 16: one warp per (quadrant, M-tile).  Measured equal (2.48 vs 2.51 ms
+// per 4-item step): a step is bound by the MMA issue pattern, not by the epilogue (tools/umma_pattern.cu, and the trace with the
+// epilogue body compiled out keeps the same step period), so the smaller block with 96 registers and no spills is kept.
+constexpr int kEpiWarps = MVS_TC_EPIWARPS;
+constexpr int kMStride = kEpiWarps / 4;      // M-tiles are dealt round-robin to the warps of a quadrant
 constexpr int kThreads = (6 + kEpiWarps) * 32;   // producer | 4 MMA issuers | weight loader | epilogue warps
 constexpr int kPW = 32;          // staged tile width (30 positions + halo)
 constexpr int kTW = 30;
@@ -67,6 +74,8 @@ struct TcParams {
     int TH, PH, nM, nwt, nht, LD, nseg;
     int nsub, stages, sps, live, groups, nentries, bstages, nwork;
     int b_resident, relu, is_bf16, kdfold;
+    int d_mul, d_org;                // depth coordinate of slot j of an item: d_mul * d0 + d_org + j
+    int64_t ys_b, ys_cb, ys_d, ys_h, y_org;   // output (and skip) addressing in voxels: b, channel block, d, h strides + origin
     uint32_t chunk_bytes, sub_bytes, slot_bytes, btile_bytes, tmem_cols;
     Entry prog[kMaxEntries];
 };
@@ -86,11 +95,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
+#ifdef MVS_TC_TESTWAIT
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// (Measured and rejected: one lane polling + __syncwarp() for the warp-uniform roles is ~40 % SLOWER than all 32 lanes executing
+// the try_wait: conv0 391 -> 575 us, prob 199 -> 318 us at 4 items.)
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -185,73 +200,81 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
                                                 int CoB, int64_t HWo) {
     constexpr int NLD = KWFOLD ? 3 : NOV;
     constexpr int64_t vs = C1 ? 1 : 8;
-    const int64_t plane = HWo, row = p.Wo;
+    const int64_t plane = p.ys_d, row = p.ys_h;
     const float floor_ = p.relu ? 0.f : -INFINITY;          // branch-free optional ReLU
     for (int cb = 0; cb < CoB; ++cb) {
         // element offset of the row's first output voxel; the other voxels of a 2x2x2 block are +pd*plane +ph*row +pw
         int64_t off0[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-            off0[t] = C1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)ra[t].oh * row + ra[t].ow
-                         : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)ra[t].oh * row + ra[t].ow) * 8;
-        uint4 sk[NT][NOV];
-        if (SKIP) {
-#pragma unroll
-            for (int t = 0; t < NT; ++t)
-#pragma unroll
-                for (int ov = 0; ov < NOV; ++ov) {
-                    sk[t][ov] = make_uint4(0u, 0u, 0u, 0u);
-                    const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
-                    if (ra[t].valid) {
-                        if (C1) sk[t][ov].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
-                        else sk[t][ov] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
-                    }
-                }
-        }
+            off0[t] = ((int64_t)b * p.ys_b + (int64_t)cb * p.ys_cb + (int64_t)od0 * plane + (int64_t)ra[t].oh * row + ra[t].ow + p.y_org) * vs;
         // folded-BN affine of this channel block: read once (the asm memory clobbers below would force re-reads per voxel)
         float sc[8], sh[8];
 #pragma unroll
         for (int k = 0; k < (C1 ? 1 : 8); ++k) { sc[k] = aff[cb * 8 + k]; sh[k] = aff[64 + cb * 8 + k]; }
-        uint32_t v[NT][NLD][8];
-#ifdef MVS_TC_TRACE
-        if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[6][g_tcount & 1023] = clock64(); }
-#endif
+        // the 8 voxels of a transposed stride-2 row go in two batches of 4 (one output depth plane each): half the registers
+        constexpr int NB = NOV == 8 ? 4 : NOV, NLB = KWFOLD ? 3 : NB;
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
+        for (int o0 = 0; o0 < NOV; o0 += NB) {
+            uint4 sk[NT][NB];
+            if (SKIP) {
 #pragma unroll
-            for (int l = 0; l < NLD; ++l) tmem_ld8(ra[t].trow + (uint32_t)(l * p.CoP + cb * 8), v[t][l]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#ifdef MVS_TC_TRACE
-        if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0) { g_trace[7][g_tcount & 1023] = clock64(); g_tcount++; }
-#endif
+                for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-#pragma unroll
-            for (int ov = 0; ov < NOV; ++ov) {
-                float o[8];
-#pragma unroll
-                for (int k = 0; k < (C1 ? 1 : 8); ++k) {
-                    if (KWFOLD) o[k] = __uint_as_float(v[t][0][k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[t][1][k]), 1) +
-                                       __shfl_down_sync(0xffffffffu, __uint_as_float(v[t][2][k]), 2);
-                    else o[k] = __uint_as_float(v[t][ov][k]);
-                }
-                const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
-                if (C1) {
-                    float x = fmaxf(o[0] * sc[0] + sh[0], floor_);
-                    if (SKIP) x += __uint_as_float(sk[t][ov].x);
-                    if (ra[t].valid) reinterpret_cast<float*>(p.y)[off] = x;
-                    continue;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k] * sc[k] + sh[k], floor_);
-                if (SKIP) {
-                    float sv[8];
-                    unpack8<T>(sk[t][ov], sv);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) o[k] += sv[k];
-                }
-                if (ra[t].valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
+                    for (int q = 0; q < NB; ++q) {
+                        const int ov = o0 + q;
+                        sk[t][q] = make_uint4(0u, 0u, 0u, 0u);
+                        const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
+                        if (ra[t].valid) {
+                            if (C1) sk[t][q].x = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.skip) + off));
+                            else sk[t][q] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.skip) + off));
+                        }
+                    }
             }
+            uint32_t v[NT][NLB][8];
+#ifdef MVS_TC_TRACE
+    #ifndef MVS_TC_TRACE2
+        if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0 && o0 == 0) { g_trace[6][g_tcount & 1023] = clock64(); }
+#endif
+#endif
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int l = 0; l < NLB; ++l) tmem_ld8(ra[t].trow + (uint32_t)((KWFOLD ? l : o0 + l) * p.CoP + cb * 8), v[t][l]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef MVS_TC_TRACE
+            if (blockIdx.x == 0 && threadIdx.x == 192 && cb == 0 && o0 == 0) { g_trace[7][g_tcount & 1023] = clock64(); g_tcount++; }
+#endif
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int ov = o0 + q;
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < (C1 ? 1 : 8); ++k) {
+                        if (KWFOLD) o[k] = __uint_as_float(v[t][0][k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[t][1][k]), 1) +
+                                           __shfl_down_sync(0xffffffffu, __uint_as_float(v[t][2][k]), 2);
+                        else o[k] = __uint_as_float(v[t][q][k]);
+                    }
+                    const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
+                    if (C1) {
+                        float x = fmaxf(o[0] * sc[0] + sh[0], floor_);
+                        if (SKIP) x += __uint_as_float(sk[t][q].x);
+                        if (ra[t].valid) reinterpret_cast<float*>(p.y)[off] = x;
+                        continue;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k] * sc[k] + sh[k], floor_);
+                    if (SKIP) {
+                        float sv[8];
+                        unpack8<T>(sk[t][q], sv);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] += sv[k];
+                    }
+                    if (ra[t].valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
+                }
+        }
     }
 }
 
@@ -274,11 +297,10 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, const float* __
 template <typename T, int NOV>
 __device__ __forceinline__ void prefetch_skip_rows(const TcParams& p, bool valid, int b, int od0, int oh0, int ow0, int CoB, int64_t HWo) {
     if (!valid || !p.skip) return;
-    const int64_t plane = HWo, row = p.Wo;
+    const int64_t plane = p.ys_d, row = p.ys_h;
     for (int cb = 0; cb < CoB; ++cb) {
-        const int64_t off0 = p.Cout == 1 ? ((int64_t)b * p.Do + od0) * plane + (int64_t)oh0 * row + ow0
-                                         : ((((int64_t)b * CoB + cb) * p.Do + od0) * plane + (int64_t)oh0 * row + ow0) * 8;
         const int64_t vs = p.Cout == 1 ? 1 : 8;
+        const int64_t off0 = ((int64_t)b * p.ys_b + (int64_t)cb * p.ys_cb + (int64_t)od0 * plane + (int64_t)oh0 * row + ow0 + p.y_org) * vs;
 #pragma unroll
         for (int ov = 0; ov < NOV; ov += (NOV == 8 ? 2 : 1)) {   // the two w-parity voxels share a 32-byte sector
             const int64_t off = off0 + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row) * vs : 0);
@@ -363,9 +385,10 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     uint8_t* dst = slots + (size_t)st * p.slot_bytes;
                     for (int s = 0; s < p.nsub; ++s)
                         for (int cb = 0; cb < p.CiB; ++cb, dst += p.chunk_bytes) {
-                            if (p.mode == MODE_S1) tma_load_4d(&maps.m[0], slot_full + st, dst, (k.w0 - 1) * 8, k.h0 - 1, k.d0 - 1 + j, k.b * p.CiB + cb);
-                            else if (p.mode == MODE_T2) tma_load_4d(&maps.m[0], slot_full + st, dst, k.w0 * 8, k.h0, k.d0 + j, k.b * p.CiB + cb);
-                            else tma_load_5d(&maps.m[s], slot_full + st, dst, 0, k.w0 - 1, k.h0 - 1, 2 * k.d0 - 1 + j, k.b * p.CiB + cb);
+                            const int dcoord = p.d_mul * k.d0 + p.d_org + j;
+                            if (p.mode == MODE_S1) tma_load_4d(&maps.m[0], slot_full + st, dst, (k.w0 - 1) * 8, k.h0 - 1, dcoord, k.b * p.CiB + cb);
+                            else if (p.mode == MODE_T2) tma_load_4d(&maps.m[0], slot_full + st, dst, k.w0 * 8, k.h0, dcoord, k.b * p.CiB + cb);
+                            else tma_load_5d(&maps.m[s], slot_full + st, dst, 0, k.w0 - 1, k.h0 - 1, dcoord, k.b * p.CiB + cb);
                         }
                     TRACE(0, J);
                 }
@@ -459,8 +482,14 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                                 if (v2 && !join12) umma_f16_elect(dg2, ad, desc_hi | (b_lo + 2 * kPG), id1, first ? 0u : 1u);
                             }
                         }
+#ifdef MVS_TC_TRACE2
+                        if (m == 0 && lane == 0) TRACE(6, Qb + 2 * (t / gridDim.x) + j);
+#endif
                         umma_commit_elect(slot_empty + st);
                         if (j >= 2) umma_commit_elect(acc_full + ((Qb + j - 2) & (kAccRing - 1)));      // output plane j-2 has all three contributions
+#ifdef MVS_DIAG_EXTRA_COMMITS   // diagnostic: what does a tcgen05.commit cost?  (dummy barrier nobody waits on)
+                        umma_commit_elect(b_empty + kBStages - 1); umma_commit_elect(b_empty + kBStages - 1);
+#endif
                         if (m == 0 && lane == 0) TRACE(3, Qb + 2 * (t / gridDim.x) + j);
                         if (++st == stages) { st = 0; sph ^= 1; }
                     }
@@ -517,7 +546,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     } else {
         // ===================== epilogue: TMEM -> affine / ReLU / skip -> C8 store =====================
         const int quad = warp & 3;                 // TMEM lanes [32 quad, 32 quad + 32) belong to this warp
-        const int mpar = (warp - 6) >> 2;          // the two warps of a quadrant take alternate M-tiles
+        const int mpar = (warp - 6) >> 2;          // the warps of a quadrant take M-tiles mpar, mpar + kMStride, ...
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
         const bool kwfold = p.mode == MODE_S1;
@@ -544,11 +573,13 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                         const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
                         RowAt ra[2];
                         for (int u = 0; u < 2; ++u) {
-                            const int m = mpar + 2 * u;
+                            const int m = mpar + kMStride * u;
                             ra[u] = row_at(m, tq + (uint32_t)((m * kAccRing + rsl) * kPG));
                         }
-                        if (mpar + 2 < p.nM) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo);
+#ifndef MVS_DIAG_NO_EPI   // diagnostic: with the epilogue body removed, what bounds a step?
+                        if (kMStride == 2 && mpar + 2 < p.nM) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo);
                         else if (mpar < p.nM) { const RowAt r1[1] = {ra[0]}; epilogue_rows<T, 1, true, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
+#endif
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -559,7 +590,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 const int buf = I & 1;
                 if (p.skip) {   // next step's skip rows (this step's at i = 0 as well) go to L2 while the MMAs run
                     for (int ii = (i == 0 ? 0 : i + 1); ii <= i + 1 && ii < k.nsteps; ++ii)
-                        for (int m = mpar; m < p.nM; m += kEpiWarps / 4) {
+                        for (int m = mpar; m < p.nM; m += kMStride) {
                             const int r = m * 128 + quad * 32 + lane;
                             const int hh = r >> 5, ww = r & 31;
                             const bool valid = (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
@@ -574,12 +605,12 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
                     RowAt ra[2];
                     for (int u = 0; u < 2; ++u) {
-                        const int m = mpar + 2 * u;
+                        const int m = mpar + kMStride * u;
                         ra[u] = row_at(m, tq + (uint32_t)((buf * p.nM + m) * p.N));
                     }
-                    const bool two = mpar + 2 < p.nM;
+                    const bool two = kMStride == 2 && mpar + 2 < p.nM;
                     if (p.mode == MODE_T2) {
-                        for (int u = 0; u < 2 && mpar + 2 * u < p.nM; ++u) {
+                        for (int u = 0; u < (kMStride == 2 ? 2 : 1) && mpar + kMStride * u < p.nM; ++u) {
                             RowAt r1[1] = {ra[u]};
                             r1[0].oh *= 2; r1[0].ow *= 2;
                             epilogue_rows<T, 8, false, 1>(p, aff, r1, b, 2 * (d0 + i), CoB, HWo);
@@ -650,27 +681,48 @@ EncodeTiledFn encode_tiled() {
 // ------------------------------------------------------------------------------------------------ tap programs
 struct Plan { TcParams p; TileSrc src; size_t smem; int stages_chosen; };
 
-int mode_of(const mvs_conv3d_desc* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
+// What a launch convolves: a 3-D layer (mvs_conv3d_desc as is), or a stack of M images treated as a volume whose "depth" axis
+// is the image index (two_d: Din = Dout = M, one live plane per step, no taps across images) with a ksize x ksize filter:
+// 3x3 stride 1 (kw folded into N like the 3-D stride-1 program) or 5x5 stride 2 (parity-staged like the 3-D stride-2 one).
+// out_pad: write the zero-bordered image-major C8P layout the plane-sweep gather reads instead of the stack layout.
+struct Spec : mvs_conv3d_desc { int two_d, ksize, out_pad; };
 
-int cop_of(const mvs_conv3d_desc* d) { return d->Cout == 1 ? 8 : d->Cout; }
+int mode_of(const Spec* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
+
+int cop_of(const Spec* d) { return d->Cout == 1 ? 8 : d->Cout; }
 // kd-fold (stride 1, <= 8 output channels): the 9 (kd, kw) taps of one kh share an MMA; see the issuer.  MVS_TC_KDFOLD=0 disables.
-bool kdfold_of(const mvs_conv3d_desc* d) {
+bool kdfold_of(const Spec* d) {
     const char* e = getenv("MVS_TC_KDFOLD");
-    return mode_of(d) == MODE_S1 && cop_of(d) == 8 && !(e && atoi(e) == 0);
+    return !d->two_d && mode_of(d) == MODE_S1 && cop_of(d) == 8 && !(e && atoi(e) == 0);
 }
-int nblk_of(const mvs_conv3d_desc* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : 3) : (mode_of(d) == MODE_T2 ? 8 : 1); }
-int n_of(const mvs_conv3d_desc* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
+int nblk_of(const Spec* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : 3) : (mode_of(d) == MODE_T2 ? 8 : 1); }
+int n_of(const Spec* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 
 // A "fold tap": one A view (slot, sub-plane, row shift) and, per column block, the filter tap it multiplies (-1 = none).
 struct FoldTap { int slot, sub, shift, tap[12]; };
 
 // Build the entry list + weight-tile sources.  Returns the number of entries.
-int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
+int build_program(const Spec* d, TcParams& p, TileSrc& src) {
     const int mode = mode_of(d);
     memset(&src, -1, sizeof(src));
     FoldTap ft[27];
     int nft = 0;
-    if (mode == MODE_S1 && kdfold_of(d)) {
+    if (d->two_d && mode == MODE_S1) {
+        // 3x3 over one image plane: one fold tap per kh, column block c = input column offset c; gather form G[kh * 3 + kw]
+        for (int kh = 0; kh < 3; ++kh) {
+            FoldTap& t = ft[nft++];
+            t.slot = 0; t.sub = 0; t.shift = kh * kPW;
+            for (int c = 0; c < 12; ++c) t.tap[c] = c < 3 ? kh * 3 + c : -1;
+        }
+    } else if (d->two_d) {
+        // 5x5 stride 2, pad 2: out o reads x[2o - 2 + k] = parity (k & 1) plane at index o - 1 + (k >> 1); the tile origin is o - 1
+        for (int kh = 0; kh < 5; ++kh)
+            for (int kw = 0; kw < 5; ++kw) {
+                FoldTap& t = ft[nft++];
+                t.slot = 0; t.sub = (kh & 1) * 2 + (kw & 1); t.shift = (kh >> 1) * kPW + (kw >> 1);
+                for (int c = 0; c < 12; ++c) t.tap[c] = c == 0 ? kh * 5 + kw : -1;
+            }
+    } else if (mode == MODE_S1 && kdfold_of(d)) {
         // one fold tap per kh; column block g * 4 + c: plane group g (output plane p - 1 + g of input plane p) x input column offset c
         for (int kh = 0; kh < 3; ++kh) {
             FoldTap& t = ft[nft++];
@@ -754,7 +806,7 @@ int build_program(const mvs_conv3d_desc* d, TcParams& p, TileSrc& src) {
     return ne;
 }
 
-bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
+bool make_plan(const Spec* d, Plan& pl) {
     TcParams& p = pl.p;
     memset(&p, 0, sizeof(p));
     p.mode = mode_of(d);
@@ -765,17 +817,30 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     if (p.mode == MODE_T2) { p.Dt = p.Di; p.Ht = p.Hi; p.Wt = p.Wi; } else { p.Dt = p.Do; p.Ht = p.Ho; p.Wt = p.Wo; }
     p.relu = d->relu; p.is_bf16 = d->dtype_in == MVS_BF16;
     p.nsub = p.mode == MODE_S2 ? 4 : 1;
-    p.sps = p.mode == MODE_S2 ? 2 : 1;
-    p.live = p.mode == MODE_T2 ? 2 : 3;
+    p.sps = d->two_d ? 1 : (p.mode == MODE_S2 ? 2 : 1);
+    p.live = d->two_d ? 1 : (p.mode == MODE_T2 ? 2 : 3);
+    p.d_mul = (!d->two_d && p.mode == MODE_S2) ? 2 : 1;
+    p.d_org = (d->two_d || p.mode == MODE_T2) ? 0 : -1;
     p.groups = 1;
     p.kdfold = kdfold_of(d) ? 1 : 0;
+    // output addressing (voxels): C8 volume [B][CoB][Do][Ho][Wo], plain [B][Do][Ho][Wo] for one channel, or (out_pad) the
+    // zero-bordered image-major C8P maps [Do = image][CoB][Ho + 3][Wo + 2] with pixel (0, 0) at row 1, column 1
+    {
+        const int64_t CoB = (d->Cout + 7) / 8;
+        if (d->out_pad) {
+            p.ys_h = p.Wo + 2; p.ys_cb = (int64_t)(p.Ho + 3) * p.ys_h; p.ys_d = CoB * p.ys_cb; p.ys_b = 0; p.y_org = p.ys_h + 1;
+        } else {
+            p.ys_h = p.Wo; p.ys_d = (int64_t)p.Ho * p.Wo; p.ys_cb = d->Cout == 1 ? 0 : (int64_t)p.Do * p.ys_d;
+            p.ys_b = (d->Cout == 1 ? 1 : CoB) * (int64_t)p.Do * p.ys_d; p.y_org = 0;
+        }
+    }
     // ring depth = live slots + the slots of one step prefetched while the current step computes
-    p.stages = p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 4));   // minimum; make_plan adds what fits
+    p.stages = d->two_d ? 2 : (p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 4)));   // minimum; make_plan adds what fits
     p.nentries = build_program(d, p, pl.src);
     p.btile_bytes = (uint32_t)p.kchunks * p.N * 16;
     int max_reach = 0;   // furthest row an A descriptor touches beyond its 128-row window
     for (int e = 0; e < p.nentries; ++e) max_reach = max(max_reach, (int)p.prog[e].row_shift + (int)p.prog[e].lbo_rows);
-    const int halo = p.mode == MODE_S1 ? 2 : 1;
+    const int halo = (p.mode == MODE_S1 || d->two_d) ? 2 : 1;
     const uint32_t all_b = (uint32_t)p.nentries * p.btile_bytes;
     // largest tile (nM M-tiles of 128 rows = 4 nM x 30 positions) whose slot ring fits beside the weights with 2 accumulator
     // sets in TMEM -- but small volumes take smaller tiles so that at least ~2 waves of CTAs exist
@@ -823,8 +888,8 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
     // rounds x (steps per item + the halo planes every item reloads + ~1 step of pipeline bubble), so pick the segment count
     // that minimises exactly that: e.g. 48 tiles x 12 segments = 576 items fill 148 CTAs to 97 % in 4 rounds, where a
     // power-of-two split (16 segments, 768 items) leaves the 6th round 19 % full.
-    const int min_ld = p.kdfold ? 4 : 2;
-    const int extra = (p.mode == MODE_S1 ? 2 : 1) + 1;
+    const int min_ld = p.kdfold ? 4 : (d->two_d ? 1 : 2);
+    const int extra = (d->two_d ? 0 : (p.mode == MODE_S1 ? 2 : 1)) + 1;
     const char* fseg = getenv("MVS_TC_NSEG");               // test / tuning knob
     int best_nseg = 1;
     int64_t best_cost = -1;
@@ -842,26 +907,67 @@ bool make_plan(const mvs_conv3d_desc* d, Plan& pl) {
 
 }  // namespace
 
-int mvs_conv3d_tc_supported(const mvs_conv3d_desc* d) {
+static Spec spec3d(const mvs_conv3d_desc* d) {
+    Spec sp;
+    static_cast<mvs_conv3d_desc&>(sp) = *d;
+    sp.two_d = 0; sp.ksize = 3; sp.out_pad = 0;
+    return sp;
+}
+
+// A stack of M images as a volume: B = 1, D = M.
+static Spec spec2d(const mvs_conv2d_desc* d) {
+    Spec sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.B = 1; sp.Cin = d->Cin; sp.Cout = d->Cout;
+    sp.Din = d->M; sp.Hin = d->Hin; sp.Win = d->Win; sp.Dout = d->M; sp.Hout = d->Hout; sp.Wout = d->Wout;
+    sp.stride = d->stride; sp.transposed = 0; sp.dtype_in = d->dtype; sp.dtype_out = d->dtype; sp.relu = d->relu; sp.algo = d->ws_packed ? 3 : 2;
+    sp.two_d = 1; sp.ksize = d->ksize; sp.out_pad = d->out_padded;
+    return sp;
+}
+
+static int tc_supported(const Spec* d) {
     if (d->dtype_in != MVS_F16 && d->dtype_in != MVS_BF16) return 0;
     if (d->Cout != 1 && d->dtype_out != d->dtype_in) return 0;
     if (d->Cin != 8 && (d->Cin % 16 != 0 || d->Cin > 64)) return 0;
     if (d->Cout != 1 && (d->Cout % 8 != 0 || d->Cout > 64)) return 0;
     if (mode_of(d) == MODE_T2 && (d->Cout == 1 || 8 * d->Cout > 256)) return 0;
-    if (mode_of(d) == MODE_S2 && ((d->Win & 1) || (d->Hin & 1) || (d->Din & 1))) return 0;
+    if (mode_of(d) == MODE_S2 && ((d->Win & 1) || (d->Hin & 1) || (!d->two_d && (d->Din & 1)))) return 0;
+    if (d->two_d && !((d->ksize == 3 && d->stride == 1) || (d->ksize == 5 && d->stride == 2))) return 0;
+    if (d->two_d && d->Cout == 1) return 0;
     return 1;
 }
 
-int64_t mvs_conv3d_tc_workspace_bytes(const mvs_conv3d_desc* d) {
-    if (!mvs_conv3d_tc_supported(d)) return 0;
+static int64_t tc_workspace_bytes(const Spec* d) {
+    if (!tc_supported(d)) return 0;
     const int kchunks = d->Cin == 8 ? 2 : d->Cin / 8;
-    const int nentries = mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27);   // upper bounds (Cin = 8 pairs need fewer)
+    // upper bounds on the entry count (Cin = 8 pairs need fewer)
+    const int nentries = d->two_d ? (d->ksize == 3 ? 3 : 25) : (mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27));
     return (int64_t)nentries * kchunks * n_of(d) * 16;  // weight tiles [entry][kchunk][N][8] in the storage dtype
 }
 
+static int conv_fwd_tc(const Spec* d, const void* x, const float* g, const float* scale, const float* shift,
+                       const void* skip, void* y, void* ws, void* stream);
+
+int mvs_conv3d_tc_supported(const mvs_conv3d_desc* d) { const Spec sp = spec3d(d); return tc_supported(&sp); }
+int64_t mvs_conv3d_tc_workspace_bytes(const mvs_conv3d_desc* d) { const Spec sp = spec3d(d); return tc_workspace_bytes(&sp); }
 int mvs_conv3d_fwd_tc(const mvs_conv3d_desc* d, const void* x, const float* g, const float* scale, const float* shift,
                       const void* skip, void* y, void* ws, void* stream) {
-    MVS_REQUIRE(mvs_conv3d_tc_supported(d), MVS_E_UNSUPPORTED,
+    const Spec sp = spec3d(d);
+    return conv_fwd_tc(&sp, x, g, scale, shift, skip, y, ws, stream);
+}
+
+int64_t mvs_conv2d_tc_workspace_bytes(const mvs_conv2d_desc* d) { const Spec sp = spec2d(d); return tc_workspace_bytes(&sp); }
+int mvs_conv2d_fwd_tc(const mvs_conv2d_desc* d, const void* x, const float* g, const float* scale, const float* shift, void* y,
+                      void* ws, void* stream) {
+    const Spec sp = spec2d(d);
+    MVS_REQUIRE(tc_supported(&sp), MVS_E_UNSUPPORTED,
+                "mvs_conv2d_fwd: needs fp16/bf16 storage, Cin in {8,16,32,48,64}, Cout in {8..64}, 3x3 stride 1 or 5x5 stride 2 (even H, W)");
+    return conv_fwd_tc(&sp, x, g, scale, shift, nullptr, y, ws, stream);
+}
+
+static int conv_fwd_tc(const Spec* d, const void* x, const float* g, const float* scale, const float* shift,
+                       const void* skip, void* y, void* ws, void* stream) {
+    MVS_REQUIRE(tc_supported(d), MVS_E_UNSUPPORTED,
                 "mvs_conv3d_fwd: tcgen05 path needs fp16/bf16 storage, Cin in {8,16,32,48,64}, Cout in {1,8..64} (<= 32 transposed stride 2)");
     MVS_REQUIRE(ws, MVS_E_ARG, "mvs_conv3d_fwd: the tcgen05 path needs a workspace of mvs_conv3d_workspace_bytes() bytes");
     EncodeTiledFn enc = encode_tiled();

@@ -67,6 +67,31 @@ class FeatureNet(nn.Module):
         return y
 
 
+    def forward_maps(self, imgs, dtype):
+        """Eval-mode path on the repo's own tcgen05 kernel: imgs [B,N,3,H,W] fp32 -> zero-bordered C8P feature maps of all
+        views [N,B,C/8,H/4+3,W/4+2,8] in `dtype`, the layout the fused plane sweep gathers from.  Every layer is one
+        mvs_conv2d_fwd launch (BatchNorm folded to the epilogue affine, ReLU fused); nothing goes through cuDNN."""
+        dev = imgs.device
+        sig = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        key = ("tc", dtype, dev)
+        hit = self.__dict__.setdefault("_folded", {}).get(key)
+        if hit is None or hit[0] != sig:
+            layers = []
+            for blk in (self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6):
+                scale, shift = ops.fold_bn(blk.bn)
+                layers.append((ops.pack_conv2d_weight(blk.conv.weight), blk.conv.out_channels, blk.conv.kernel_size[0], blk.conv.stride[0],
+                               scale, shift, True))
+            layers.append((ops.pack_conv2d_weight(self.feature.weight), self.feature.out_channels, 3, 1, None,
+                           self.feature.bias.detach().float().contiguous(), False))
+            hit = (sig, layers, {})
+            self._folded[key] = hit
+        b, n = imgs.shape[0], imgs.shape[1]
+        x = ops.pack_images_c8(imgs, dtype)
+        for i, (g, cout, k, stride, scale, shift, relu) in enumerate(hit[1]):
+            x = ops.conv2d_raw(x, g, cout, k, stride, scale, shift, relu, out_padded=(i == len(hit[1]) - 1), tile_cache=hit[2])
+        return x.view(n, b, *x.shape[1:])
+
+
 class CostRegNet(nn.Module):
     """jdacs/models/mvsnet.py:37-74.  forward takes the variance volume (C8 or [B,32,D,H,W]) and returns
     cost_reg: [B,D,H,W] fp32 for a C8 input (internal), [B,1,D,H,W] for a plain input (reference shape).
@@ -155,7 +180,8 @@ class MVSNet(nn.Module):
             self.refine_network = RefineNet()
         self.volume_dtype = volume_dtype
         self.align_corners = align_corners
-        self.feature_autocast = True   # eval + 16-bit volume: FeatureNet (library code) runs under torch.autocast
+        self.feature_autocast = True   # eval + 16-bit volume, feature_tc off: FeatureNet as folded 16-bit library convolutions
+        self.feature_tc = True         # eval + 16-bit volume: FeatureNet on the repo's tcgen05 convolution kernel
 
     def forward(self, imgs, proj_matrices, depth_values):
         assert imgs.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
@@ -169,15 +195,21 @@ class MVSNet(nn.Module):
             # step 2. plane sweep: warp + variance, fused (:120-136)
             variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
         else:
-            x = imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:])
-            if dt != torch.float32 and x.is_cuda and self.feature_autocast:
-                # the features are stored in `dt` by the sweep anyway: let the library run its tensor-core kernels
-                f = self.feature.forward_folded(x, dt)
+            if dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0:
+                # the feature extractor on the tcgen05 convolution kernel, emitting the gather layout directly
+                maps = self.feature.forward_maps(imgs, dt)
             else:
-                f = self.feature(x)
-            # step 2. all views go to the zero-bordered gather layout in one launch, then the fused plane sweep
-            maps = ops.pack_c8_padded(f, dt)
-            variance = ops.warp_variance_maps(maps.view(n, b, *maps.shape[1:]), rt, depth_values, dt, self.align_corners, False)
+                x = imgs.transpose(0, 1).reshape(n * b, *imgs.shape[2:])
+                if dt != torch.float32 and x.is_cuda and self.feature_autocast:
+                    # the features are stored in `dt` by the sweep anyway: let the library run its tensor-core kernels
+                    f = self.feature.forward_folded(x, dt)
+                else:
+                    f = self.feature(x)
+                # all views go to the zero-bordered gather layout in one launch
+                maps = ops.pack_c8_padded(f, dt)
+                maps = maps.view(n, b, *maps.shape[1:])
+            # step 2. the fused plane sweep
+            variance = ops.warp_variance_maps(maps, rt, depth_values, dt, self.align_corners, False)
         # step 3. regularisation (:139-141)
         self.cost_regularization.act_dtype = None if self.training else dt
         cost_reg = self.cost_regularization(variance)

@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import Conv3dDesc, call, dtype_code, ptr
+from ._lib import Conv2dDesc, Conv3dDesc, call, dtype_code, ptr
 
 Tensor = torch.Tensor
 
@@ -259,6 +259,55 @@ def conv3d_raw(x: Tensor, g: Tensor, cout: int, stride: int = 1, transposed: boo
                     tile_cache.clear()
                 tile_cache[key] = ws
     call("mvs_conv3d_fwd", x, C.byref(d), ptr(x), ptr(g), ptr(scale), ptr(shift), ptr(skip), ptr(y), ptr(ws))
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ 2-D feature layers (tcgen05)
+def pack_images_c8(imgs: Tensor, dtype: torch.dtype) -> Tensor:
+    """fp32 images [B,N,3,H,W] -> C8 image stack [1, N*B, H, W, 8] (`dtype`; image m = v*B + b; channels 3..7 zero)."""
+    x = _f32c(imgs)
+    b, n, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("expected 3-channel images, got %d channels" % c)
+    out = torch.empty(1, n * b, h, w, 8, dtype=dtype, device=x.device)
+    call("mvs_pack_images_c8", x, ptr(x), ptr(out), b, n, h, w, dtype_code(dtype))
+    return out
+
+
+def pack_conv2d_weight(weight: Tensor) -> Tensor:
+    """torch Conv2d weight [Cout,Cin,k,k] -> gather form G[k*k, CinPad, CoutPad] fp32 (tap = kh*k + kw; pads are zero)."""
+    w = _f32c(weight)
+    cout, cin, k, _ = w.shape
+    cinp, coutp = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+    g = torch.zeros(k * k, cinp, coutp, dtype=torch.float32, device=w.device)
+    g[:, :cin, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+    return g
+
+
+def conv2d_raw(x: Tensor, g: Tensor, cout: int, ksize: int, stride: int, scale: Optional[Tensor], shift: Optional[Tensor],
+               relu: bool, out_padded: bool = False, tile_cache: Optional[dict] = None) -> Tensor:
+    """y = [relu](conv2d(x) * scale + shift) over a C8 image stack [Cin/8, M, H, W, 8] (16-bit storage, tcgen05 kernel).
+    Returns the stack [Cout/8, M, Ho, Wo, 8], or with out_padded the zero-bordered image-major maps [M, Cout/8, Ho+3, Wo+2, 8]."""
+    x = x.contiguous()
+    cib, m, h, w, _ = x.shape
+    ho, wo = (h, w) if stride == 1 else (h // 2, w // 2)
+    d = Conv2dDesc(m, cib * 8, cout, h, w, ho, wo, ksize, stride, dtype_code(x.dtype), int(relu), int(out_padded), 0)
+    if out_padded:
+        y = torch.zeros(m, cout // 8, ho + 3, wo + 2, 8, dtype=x.dtype, device=x.device)
+    else:
+        y = torch.empty(cout // 8, m, ho, wo, 8, dtype=x.dtype, device=x.device)
+    nws = _lib.lib().mvs_conv2d_workspace_bytes(C.byref(d))
+    if nws <= 0:
+        raise RuntimeError("conv2d_raw: unsupported layer (Cin=%d Cout=%d k=%d stride=%d %s)" % (cib * 8, cout, ksize, stride, x.dtype))
+    key = (g.data_ptr(), g._version, d.dtype, ksize, stride, str(x.device))
+    ws = tile_cache.get(key) if tile_cache is not None else None
+    if ws is not None:
+        d.ws_packed = 1
+    else:
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+        if tile_cache is not None:
+            tile_cache[key] = ws
+    call("mvs_conv2d_fwd", x, C.byref(d), ptr(x), ptr(g), ptr(scale), ptr(shift), ptr(y), ptr(ws))
     return y
 
 

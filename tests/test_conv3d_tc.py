@@ -88,3 +88,79 @@ def test_tc_is_selected_automatically(gpu):
     x8 = ops.pack_c8(torch.randn(1, 32, 8, 16, 32, device=gpu.device), torch.float16)
     g = ops.pack_conv3d_weight(0.1 * torch.randn(8, 32, 3, 3, 3, device=gpu.device), False)
     assert torch.equal(ops.conv3d_raw(x8, g, 8, algo=0), ops.conv3d_raw(x8, g, 8, algo=2))
+
+
+# ---------------------------------------------------------------------------------------------- 2-D feature layers
+CASES_2D = [
+    # cin (real), cout, ksize, stride, (M, H, W), out_padded, relu
+    (3, 8, 3, 1, (2, 16, 30), False, True),       # FeatureNet conv0: 3 input channels padded to 8, exactly one tile
+    (3, 8, 3, 1, (3, 37, 70), False, True),       # ragged
+    (8, 8, 3, 1, (5, 64, 96), False, True),       # conv1
+    (8, 16, 5, 2, (3, 44, 68), False, True),      # conv2: 5x5 stride 2, Cin = 8 (paired taps)
+    (16, 16, 3, 1, (2, 33, 47), False, True),     # conv3 / conv4
+    (16, 32, 5, 2, (3, 40, 92), False, True),     # conv5
+    (32, 32, 3, 1, (2, 21, 35), False, True),     # conv6
+    (32, 32, 3, 1, (5, 32, 40), True, False),     # feature: bias only, zero-bordered image-major output
+    (32, 32, 3, 1, (10, 128, 160), True, False),  # headline feature-map size, two items x 5 views
+    (3, 8, 3, 1, (5, 128, 160), False, True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("cin,cout,k,stride,shape,padded,relu", CASES_2D)
+def test_tc_conv2d_matches_aten(gpu, cin, cout, k, stride, shape, padded, relu, dtype):
+    """The 2-D mode of the tcgen05 kernel (image stack as a volume, no taps across images) against F.conv2d on inputs and
+    weights rounded to the storage type."""
+    from ssmvs_b200 import ops
+    torch.manual_seed(cin * 7 + cout + k)
+    m, h, w = shape
+    dev = gpu.device
+    cinp = (cin + 7) // 8 * 8
+    x = torch.randn(m, cin, h, w, device=dev).to(dtype).float()
+    wt = (0.2 * torch.randn(cout, cin, k, k, device=dev)).to(dtype).float()
+    scale = (torch.rand(cout, device=dev) + 0.5) if relu else None
+    shift = torch.randn(cout, device=dev)
+    xs = torch.zeros(cinp // 8, m, h, w, 8, device=dev, dtype=dtype)           # C8 image stack [Cin/8][M][H][W][8]
+    xp = torch.zeros(m, cinp, h, w, device=dev)
+    xp[:, :cin] = x
+    xs.copy_(xp.view(m, cinp // 8, 8, h, w).permute(1, 0, 3, 4, 2))
+    y = ops.conv2d_raw(xs, ops.pack_conv2d_weight(wt), cout, k, stride, scale, shift, relu, out_padded=padded)
+    torch.cuda.synchronize()
+    want = F.conv2d(x, wt, None, stride, k // 2)
+    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) if relu else want + shift.view(1, -1, 1, 1)
+    if relu:
+        want = F.relu(want)
+    ho, wo = want.shape[2:]
+    if padded:
+        assert y.shape == (m, cout // 8, ho + 3, wo + 2, 8)
+        yf = y.float()
+        got = yf[:, :, 1:ho + 1, 1:wo + 1].permute(0, 1, 4, 2, 3).reshape(m, cout, ho, wo)
+        border = yf.clone()
+        border[:, :, 1:ho + 1, 1:wo + 1] = 0
+        assert torch.count_nonzero(border) == 0
+    else:
+        assert y.shape == (cout // 8, m, ho, wo, 8)
+        got = y.float().permute(1, 0, 4, 2, 3).reshape(m, cout, ho, wo)
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert rel_err(got, want) < 2 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 6e-2)])
+def test_feature_net_on_tcgen05(gpu, oracle, dtype, tol):
+    """FeatureNet.forward_maps (8 launches of the tcgen05 kernel) against the oracle's fp32 FeatureNet (jdacs/models/mvsnet.py:17-34)."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False).eval()
+    with torch.no_grad():
+        for mod in model.feature.modules():          # non-trivial BatchNorm statistics
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5); mod.weight.uniform_(0.7, 1.3); mod.bias.normal_(0, 0.2)
+    inp = synth.mvsnet_inputs(2, 3, 64, 96, 8, seed=3)
+    sd = {k[len("feature."):]: v.detach().clone() for k, v in model.state_dict().items() if k.startswith("feature.")}
+    with torch.no_grad():
+        want = torch.stack([oracle.feature_net(inp["imgs"][:, v], sd) for v in range(3)], 0)      # [N,B,32,16,24]
+        maps = model.to(gpu.device).feature.forward_maps(inp["imgs"].to(gpu.device), dtype)
+    assert maps.shape == (3, 2, 4, 16 + 3, 24 + 2, 8)
+    got = maps.float()[:, :, :, 1:17, 1:25].permute(0, 1, 2, 5, 3, 4).reshape(3, 2, 32, 16, 24).cpu()
+    assert rel_err(got, want) < tol

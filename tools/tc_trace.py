@@ -8,11 +8,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = os.path.join(ROOT, "self-supervised-mvs_b200")
-lib = os.path.join(pkg, "libmvs_b200_trace.so")
+lib = os.environ.get("MVS_TRACE_LIB", os.path.join(pkg, "libmvs_b200_trace.so"))
 srcs = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "conv3d_tc.cu", "invwarp.cu"]
 if "--build" in sys.argv:
     subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-                           "-DMVS_TC_TRACE", "-shared", "-o", lib] + [os.path.join(pkg, "csrc", s) for s in srcs] + ["-lcudart"])
+                           "-DMVS_TC_TRACE"] + [a for a in sys.argv if a.startswith("-D")] + ["-shared", "-o", lib] + [os.path.join(pkg, "csrc", s) for s in srcs] + ["-lcudart"])
     sys.exit(0)
 import torch
 import ssmvs_b200
@@ -39,7 +39,7 @@ t = [[buf[r * 1024 + i] for i in range(1024)] for r in range(8)]
 t0 = min(v for v in t[0][:8] if v)
 print("step: producer_issue | issuer: at_wait, past_wait, issued | epilogue: start, done   (cycles since first TMA)")
 for i in range(40):
-    print("%3d: %8d | %8d %8d %8d | %8d %8d" % (i, t[0][i] - t0, t[1][i] - t0, t[2][i] - t0, t[3][i] - t0, t[4][i] - t0, t[5][i] - t0))
+    print("%3d: %8d | %8d %8d %8d | %8d %8d | mma_issued %8d" % (i, t[0][i] - t0, t[1][i] - t0, t[2][i] - t0, t[3][i] - t0, t[4][i] - t0, t[5][i] - t0, t[6][i] - t0))
 
 print("epilogue rows of warp 6 (per M-tile): skip loads issued -> TMEM data ready, and gap to the next M-tile")
 for i in range(4, 24):
