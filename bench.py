@@ -40,6 +40,11 @@ CONV0_FLOPS = 2 * 27 * 32 * 8 * SAMPLES_PER_ITEM   # conv0 of CostRegNet: 6912 M
 SOFTARGMIN_BYTES = 4 * SAMPLES_PER_ITEM + 12 * HF * WF
 
 
+def CONV0_BYTES(elem: int) -> int:
+    """conv0 of CostRegNet: read the 32-channel variance volume once, write the 8-channel activation once."""
+    return elem * (CHANNELS + 8) * SAMPLES_PER_ITEM
+
+
 def warp_var_bytes(elem: int) -> int:
     return elem * (CHANNELS * SAMPLES_PER_ITEM + VIEWS * CHANNELS * HF * WF) + 4 * NDEPTH
 
@@ -323,15 +328,14 @@ def main():
                 e = [mk() for _ in range(10)]
                 imgs = res["imgs"]
                 flush.zero_(); e[0].record(stream)
-                xin = imgs.transpose(0, 1).reshape(VIEWS * PB, 3, HEIGHT, WIDTH)
-                if dtype != torch.float32:   # same library path MVSNet.forward takes in eval mode
-                    f = model.feature.forward_folded(xin, dtype)
+                if dtype != torch.float32:   # the path MVSNet.forward takes in eval mode: FeatureNet on the tcgen05 kernel
+                    maps = model.feature.forward_maps(imgs, dtype)
                 else:
-                    f = model.feature(xin)
+                    f = model.feature(imgs.transpose(0, 1).reshape(VIEWS * PB, 3, HEIGHT, WIDTH))
+                    maps = ops.pack_c8_padded(f, dtype)
+                    maps = maps.view(VIEWS, PB, *maps.shape[1:])
                 e[1].record(stream)
                 rt = ops.compose_proj(res["proj_matrices"])
-                maps = ops.pack_c8_padded(f, dtype)
-                maps = maps.view(VIEWS, PB, *maps.shape[1:])
                 flush.zero_(); e[2].record(stream)
                 var = ops.warp_variance_maps(maps, rt, res["depth_values"], dtype)
                 e[3].record(stream)
@@ -362,14 +366,17 @@ def main():
     wv_gbs = PB * warp_var_bytes(elem) / (stages["warp_var"] * 1e-3) / 1e9
     reg_tfs = PB * REG_FLOPS / (stages["reg3d"] * 1e-3) / 1e12
     conv0_tfs = PB * CONV0_FLOPS / (stages["conv0"] * 1e-3) / 1e12
-    roof_wv = {"kernel": "warp_var_fwd_fast_kernel (fused warp + variance)", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"],
+    roof_wv = {"kernel": "warp_var_fwd_pad_kernel (fused warp + bilinear gather + variance)", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"],
                "unit": "GB/s", "frac": wv_gbs / peaks["hbm_gbs"], "traffic": traffic.get("warp_var_fwd"), "ms": stages["warp_var"],
-               "peak_source": peaks["source"], "algorithmic_bytes": PB * warp_var_bytes(elem)}
+               "peak_source": peaks["source"], "algorithmic_bytes": PB * warp_var_bytes(elem),
+               "note": "co-limited by the L1 data pipe: 4 taps x 64 B per (voxel, source) = 31.5 M gather wavefronts per item (ncu: l1tex lsu wavefronts 72 % of peak)"}
     roof_conv0 = {"kernel": "conv3d_tc_kernel (conv0: 32->8, 3x3x3, full D x H x W)", "bound": "tensor", "achieved": conv0_tfs,
                   "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": conv0_tfs / peaks["bf16_tflops"],
                   "traffic": traffic.get("conv0"), "ms": stages["conv0"], "peak_source": peaks["source"],
                   "algorithmic_flops": PB * CONV0_FLOPS,
-                  "note": "thin layer (N = 3 taps x 8 couts per MMA): bounded by the A-operand fetch of tcgen05.mma, not by MMA rate"}
+                  "hbm": {"achieved": PB * CONV0_BYTES(elem) / (stages["conv0"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": PB * CONV0_BYTES(elem) / (stages["conv0"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": PB * CONV0_BYTES(elem)},
+                  "note": "thin layer (32 -> 8 channels): 6.9 kFLOP per 80 B of volume, below the ridge; each tcgen05.mma pays a fixed 128 x 16 A-operand fetch for N <= 96 columns (tools/umma_bench.cu: 32 + N/4 cycles), so both the HBM and the tensor fractions are reported"}
     roof_reg = {"kernel": "CostRegNet conv stack (12 launches)", "bound": "tensor", "achieved": reg_tfs, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": reg_tfs / peaks["bf16_tflops_sustained"], "traffic": None, "ms": stages["reg3d"],
                 "peak_source": peaks["source"]}
@@ -379,8 +386,8 @@ def main():
         items = world * args.steps * PB
         value = items * SAMPLES_PER_ITEM / (ms_total * 1e-3)
         e2e_value = items * SAMPLES_PER_ITEM / (ms_e2e * 1e-3)
-        h2d = sum(v.numel() * v.element_size() for v in pinned.values())
-        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        h2d = world * sum(v.numel() * v.element_size() for v in pinned.values())      # whole job: every rank uploads its own items
+        d2h = world * sum(v.numel() * v.element_size() for v in out_host.values())
         line = {"metric": METRIC, "value": value, "unit": "depth-samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " storage, f32 accumulate",

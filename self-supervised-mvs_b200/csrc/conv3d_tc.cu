@@ -179,7 +179,7 @@ struct TensorMaps { CUtensorMap m[4]; };
 
 #ifdef MVS_TC_TRACE
 // Debug build only (tools/tc_trace.py): CTA 0 records clock64() at pipeline events; 8 lanes x 1024 slots.
-__device__ long long g_trace[8][1024];
+__device__ long long g_trace[10][1024];
 __device__ int g_tcount;
 #define TRACE(lane_id, idx) do { if (blockIdx.x == 0 && (idx) < 1024) g_trace[lane_id][idx] = clock64(); } while (0)
 #else
@@ -193,7 +193,7 @@ __device__ int g_tcount;
 //   KWFOLD  : stride 1, column blocks 0,1,2 hold the taps reading input column (lane): output j = blk0[j] + blk1[j+1] + blk2[j+2]
 // One lane's output row of NT M-tiles at once (NT = 2: the TMEM and skip loads of both tiles are in flight together, which
 // halves the exposed latency of this otherwise serial, single-warp code).
-struct RowAt { uint32_t trow; bool valid; int oh, ow; };
+struct RowAt { uint32_t trow; bool valid; int64_t base; };   // base = b * ys_b + oh * ys_h + ow + y_org: constant over the depth steps of a work item
 
 template <typename T, int NOV, bool KWFOLD, bool C1, bool SKIP, int NT>
 __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* __restrict__ aff, const RowAt (&ra)[NT], int b, int od0,
@@ -202,12 +202,15 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
     constexpr int64_t vs = C1 ? 1 : 8;
     const int64_t plane = p.ys_d, row = p.ys_h;
     const float floor_ = p.relu ? 0.f : -INFINITY;          // branch-free optional ReLU
+#ifdef MVS_TC_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 192) { g_trace[8][g_tcount & 1023] = clock64(); }
+#endif
     for (int cb = 0; cb < CoB; ++cb) {
         // element offset of the row's first output voxel; the other voxels of a 2x2x2 block are +pd*plane +ph*row +pw
         int64_t off0[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-            off0[t] = ((int64_t)b * p.ys_b + (int64_t)cb * p.ys_cb + (int64_t)od0 * plane + (int64_t)ra[t].oh * row + ra[t].ow + p.y_org) * vs;
+            off0[t] = (ra[t].base + (int64_t)cb * p.ys_cb + (int64_t)od0 * plane) * vs;
         // folded-BN affine of this channel block: read once (the asm memory clobbers below would force re-reads per voxel)
         float sc[8], sh[8];
 #pragma unroll
@@ -276,6 +279,9 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
                 }
         }
     }
+#ifdef MVS_TC_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 192) { g_trace[9][(g_tcount - 1) & 1023] = clock64(); }
+#endif
 }
 
 // Runtime (warp-uniform) selection of the specialised epilogue: single-channel output or C8, with or without a skip tensor.
@@ -554,13 +560,22 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
             const Work k = decode(t);
             const int b = k.b, w0 = k.w0, h0 = k.h0, d0 = k.d0;
-            // accumulator row (= lane) of M-tile m: one h-row of the tile per warp, lane = w position
-            auto row_at = [&](int m, uint32_t trow) {
+            // accumulator row (= lane) of this warp's M-tiles: one h-row of the tile per warp, lane = w position.  Validity and the
+            // output address base are per work item, not per depth step (the 64-bit address math used to cost ~200 cycles a step).
+            bool valid_u[2];
+            int64_t base_u[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int m = mpar + kMStride * u;
                 const int r = m * 128 + quad * 32 + lane;
                 const int hh = r >> 5, ww = r & 31;
+                const int64_t mul = p.mode == MODE_T2 ? 2 : 1;       // transposed stride 2: the row's 2x2x2 output block starts at twice the input position
+                base_u[u] = (int64_t)b * p.ys_b + mul * (h0 + hh) * p.ys_h + mul * (w0 + ww) + p.y_org;
+                valid_u[u] = (m < p.nM) && (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+            }
+            auto row_at = [&](int u, uint32_t trow) {
                 RowAt a;
-                a.trow = trow; a.oh = h0 + hh; a.ow = w0 + ww;
-                a.valid = (m < p.nM) && (hh < p.TH) && (ww < kTW) && (h0 + hh < p.Ht) && (w0 + ww < p.Wt);
+                a.trow = trow; a.base = base_u[u]; a.valid = valid_u[u];
                 return a;
             };
             for (int i = 0; i < k.nsteps; ++i, ++I) {
@@ -574,7 +589,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                         RowAt ra[2];
                         for (int u = 0; u < 2; ++u) {
                             const int m = mpar + kMStride * u;
-                            ra[u] = row_at(m, tq + (uint32_t)((m * kAccRing + rsl) * kPG));
+                            ra[u] = row_at(u, tq + (uint32_t)((m * kAccRing + rsl) * kPG));
                         }
 #ifndef MVS_DIAG_NO_EPI   // diagnostic: with the epilogue body removed, what bounds a step?
                         if (kMStride == 2 && mpar + 2 < p.nM) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo);
@@ -606,20 +621,22 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                     RowAt ra[2];
                     for (int u = 0; u < 2; ++u) {
                         const int m = mpar + kMStride * u;
-                        ra[u] = row_at(m, tq + (uint32_t)((buf * p.nM + m) * p.N));
+                        ra[u] = row_at(u, tq + (uint32_t)((buf * p.nM + m) * p.N));
                     }
                     const bool two = kMStride == 2 && mpar + 2 < p.nM;
                     if (p.mode == MODE_T2) {
                         for (int u = 0; u < (kMStride == 2 ? 2 : 1) && mpar + kMStride * u < p.nM; ++u) {
-                            RowAt r1[1] = {ra[u]};
-                            r1[0].oh *= 2; r1[0].ow *= 2;
+                            const RowAt r1[1] = {ra[u]};
                             epilogue_rows<T, 8, false, 1>(p, aff, r1, b, 2 * (d0 + i), CoB, HWo);
                         }
-                    } else if (mpar < p.nM) {
+                    }
+#ifndef MVS_DIAG_NO_EPI
+                    else if (mpar < p.nM) {
                         const RowAt r1[1] = {ra[0]};
                         if (kwfold) { if (two) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo); else epilogue_rows<T, 1, true, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
                         else { if (two) epilogue_rows<T, 1, false, 2>(p, aff, ra, b, d0 + i, CoB, HWo); else epilogue_rows<T, 1, false, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
                     }
+#endif
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1028,7 +1045,7 @@ static int conv_fwd_tc(const Spec* d, const void* x, const float* g, const float
 }
 
 #ifdef MVS_TC_TRACE
-extern "C" int mvs_debug_tc_trace(long long* host_out) {   // [8][1024]
-    return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 8 * 1024) == cudaSuccess ? 0 : -1;
+extern "C" int mvs_debug_tc_trace(long long* host_out) {   // [10][1024]
+    return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 10 * 1024) == cudaSuccess ? 0 : -1;
 }
 #endif
