@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16")
     ap.add_argument("--batch", type=int, default=4, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU)")
+    ap.add_argument("--lanes", type=int, default=1, help="item groups captured on separate streams inside the CUDA graph (GraphedForward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
@@ -248,7 +249,7 @@ def main():
     graphed = None
     if not args.no_graph:
         from ssmvs_b200.graph import GraphedForward
-        graphed = GraphedForward(lambda i, pm, dv: model(i, pm, dv), [res["imgs"], res["proj_matrices"], res["depth_values"]])
+        graphed = GraphedForward(lambda i, pm, dv: model(i, pm, dv), [res["imgs"], res["proj_matrices"], res["depth_values"]], lanes=args.lanes)
 
     def step_resident():
         if graphed is not None:
@@ -394,7 +395,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * PB, "per_gpu_batch": PB, "parallelism": "dp%d (items sharded, no collective)" % world,
                            "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
-                           "launch": "python" if graphed is None else "cuda-graph replay (%d C-ABI launches per step)" % graphed.launches_per_replay,
+                           "launch": "python" if graphed is None else "cuda-graph replay (%d C-ABI launches per step, %d stream lane(s))" % (graphed.launches_per_replay, graphed.lanes),
                            "wall_s_incl_flush": wall},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "depth-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

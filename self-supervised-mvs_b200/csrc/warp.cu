@@ -7,6 +7,10 @@
 // 209-261, network.py:114-137.  Sampler semantics: ATen grid_sampler_2d bilinear / zeros padding.
 #include "mvs_rt.h"
 #include <stdlib.h>
+#include <string.h>
+#ifndef MVS_CPU_EMU
+#include <cuda.h>
+#endif
 
 struct SrcPtrs { const void* p[MVS_MAX_SRC]; };
 struct GradPtrs { float* p[MVS_MAX_SRC]; };
@@ -492,6 +496,245 @@ warp_var_fwd_pad_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------ fused forward, 16-bit, TMA-staged source tiles
+// A block owns an 8 x 16 pixel tile of the reference frustum x a chunk of DC depth planes x all channels.  The pixels of every
+// source map that the tile can touch over the chunk form a small window (the sweep moves a fraction of a pixel per plane, the
+// homography is close to a translation over 16 pixels): its bounding box is found from the tile corners x the planes of the
+// chunk, and when it fits a kBH x kBW box the window of ALL channel blocks is fetched by one TMA per source into shared
+// memory ([cb][row][pixel][8], so a quarter-warp's gather is 128 contiguous bytes: conflict-free, exactly 4 wavefronts per
+// instruction where the L1 path pays ~5 for line straddling, 32-bit addresses, no L2 misses).  A source whose window does not
+// fit (wide baseline, plane through the camera, non-finite depth) is gathered from global memory exactly like
+// warp_var_fwd_pad_kernel, per source and per block, so the result never depends on the staging decision.
+// The maps are the zero-bordered C8P maps; TMA zero-fills whatever lies beyond them.
+constexpr int kBH = 12, kBW = 24;          // staged window (pixels); 18 KB per source at 32 channels
+constexpr int kTileH = 8, kTileW = 16;     // reference pixels per block
+
+struct WvMaps { CUtensorMap m[MVS_MAX_SRC]; };
+
+__device__ __forceinline__ uint32_t wv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 wv_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+template <typename T, int NS, bool REFSQ, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+warp_var_fwd_tma_kernel(const __grid_constant__ WvMaps maps, const T* __restrict__ ref, SrcPtrs srcs, int nsrc,
+                        const float* __restrict__ rt, const float* __restrict__ depth, T* __restrict__ var, int B, int CB, int D,
+                        int H, int W, int DC, int align_corners) {
+    typedef typename Pack2<T>::type T2;
+    extern __shared__ __align__(128) uint8_t wv_smem[];
+    __shared__ uint64_t bar;
+    __shared__ int s_min[NS][2], s_max[NS][2], s_bad[NS];     // clamped sampling coordinates of the block (float bits; all >= 0)
+    __shared__ int s_org[NS][2], s_staged[NS];
+
+    const int HW = H * W;
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const int nchunk = (D + DC - 1) / DC;
+    const int b = blockIdx.y / nchunk, dc = blockIdx.y - b * nchunk;
+    const int d_begin = dc * DC, d_end = min(D, d_begin + DC);
+    const int q = threadIdx.x & 127, cp = threadIdx.x >> 7;          // pixel of the tile, channel-block pair
+    const int py = tile_y * kTileH + (q >> 4), px = tile_x * kTileW + (q & 15);
+    const bool active = py < H && px < W;
+    const int pitch = W + 2;
+    const uint32_t row_b = (uint32_t)pitch * 16u, plane_b = (uint32_t)(H + 3) * row_b;
+    const uint32_t win_plane = kBH * kBW * 16u, win_src = (uint32_t)CB * win_plane;     // bytes per channel block / per source in smem
+
+    const float sx = align_corners ? 1.f : (float)W / (float)(W - 1), sy = align_corners ? 1.f : (float)H / (float)(H - 1);
+    const float oxy = (align_corners ? 0.f : -0.5f) + 1.f;
+    const float xmax = (float)(W + 1), ymax = (float)(H + 1);
+
+    if (threadIdx.x < NS) {
+        s_min[threadIdx.x][0] = s_min[threadIdx.x][1] = 0x7f800000; s_max[threadIdx.x][0] = s_max[threadIdx.x][1] = 0; s_bad[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wv_smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- window of every source: the 4 tile corners x every plane of the chunk, with exactly the arithmetic of the gather below
+    {
+        const int nd = d_end - d_begin;
+        const int x0 = tile_x * kTileW, x1 = min(x0 + kTileW - 1, W - 1), y0 = tile_y * kTileH, y1 = min(y0 + kTileH - 1, H - 1);
+        for (int e = threadIdx.x; e < nsrc * 4 * nd; e += blockDim.x) {
+            const int s = e / (4 * nd), r = e - s * 4 * nd, corner = r / nd, d = d_begin + (r - corner * nd);
+            const float* m = rt + ((int64_t)s * B + b) * 12;
+            float ray[3];
+            pixel_ray(m, (float)((corner & 1) ? x1 : x0), (float)((corner & 2) ? y1 : y0), ray);
+            const float dv = __ldg(depth + (int64_t)b * D + d);
+            const float pz = fmaf(ray[2], dv, __ldg(m + 11));
+            float iz;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(pz));
+            const float ix = fminf(fmaxf(fmaf(fmaf(ray[0] * sx, dv, __ldg(m + 9) * sx), iz, oxy), 0.f), xmax);
+            const float iy = fminf(fmaxf(fmaf(fmaf(ray[1] * sy, dv, __ldg(m + 10) * sy), iz, oxy), 0.f), ymax);
+            const int bad = (!(pz > 0.f) || !(fabsf(dv) < 3.0e38f)) ? 1 : 0;       // the map is not monotone across pz <= 0: no window
+            int lox = __float_as_int(ix), hix = lox, loy = __float_as_int(iy), hiy = loy;   // non-negative floats order like their bits
+            if ((4 * nd) % 32 == 0 && e - (int)(threadIdx.x & 31) + 31 < nsrc * 4 * nd) {
+                // the whole warp evaluates one source: reduce in the warp (redux), one shared-memory atomic per warp and quantity
+                lox = __reduce_min_sync(0xffffffffu, lox); hix = __reduce_max_sync(0xffffffffu, hix);
+                loy = __reduce_min_sync(0xffffffffu, loy); hiy = __reduce_max_sync(0xffffffffu, hiy);
+                const int anybad = __reduce_max_sync(0xffffffffu, bad);
+                if ((threadIdx.x & 31) == 0) {
+                    if (anybad) atomicOr(&s_bad[s], 1);
+                    atomicMin(&s_min[s][0], lox); atomicMax(&s_max[s][0], hix); atomicMin(&s_min[s][1], loy); atomicMax(&s_max[s][1], hiy);
+                }
+            } else {
+                if (bad) atomicOr(&s_bad[s], 1);
+                atomicMin(&s_min[s][0], lox); atomicMax(&s_max[s][0], hix); atomicMin(&s_min[s][1], loy); atomicMax(&s_max[s][1], hiy);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nsrc) {
+        const int s = threadIdx.x;
+        // one pixel of slack on the low side and two on the high side (the +1 tap and the rounding of interior pixels, whose
+        // coordinates are fused differently from the corners' by at most an ulp)
+        const int bx = max((int)floorf(__int_as_float(s_min[s][0]) - 0.01f), 0), by = max((int)floorf(__int_as_float(s_min[s][1]) - 0.01f), 0);
+        const int ex = (int)floorf(__int_as_float(s_max[s][0]) + 0.01f) + 1, ey = (int)floorf(__int_as_float(s_max[s][1]) + 0.01f) + 1;
+        s_org[s][0] = bx; s_org[s][1] = by;
+        s_staged[s] = (!s_bad[s] && ex - bx < kBW && ey - by < kBH) ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bytes = 0;
+        for (int s = 0; s < nsrc; ++s) bytes += s_staged[s] ? win_src : 0u;
+        if (bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wv_smem_u32(&bar)), "r"(bytes) : "memory");
+            for (int s = 0; s < nsrc; ++s)
+                if (s_staged[s])
+                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                 ::"r"(wv_smem_u32(wv_smem + (size_t)s * win_src)), "l"(&maps.m[s]), "r"(wv_smem_u32(&bar)),
+                                   "r"(s_org[s][0] * 8), "r"(s_org[s][1]), "r"(0), "r"(b) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wv_smem_u32(&bar)) : "memory");
+        }
+    }
+
+    // ---- per-thread setup while the windows land
+    const int pyc = min(py, H - 1), pxc = min(px, W - 1);            // inactive threads of a ragged tile compute on a clamped pixel, store nothing
+    const int64_t map_b = ((int64_t)b * CB + (int64_t)cp * 2) * plane_b;
+    uint4 rq[2];
+    {
+        const char* rp = reinterpret_cast<const char*>(ref) + map_b + (uint32_t)((pyc + 1) * pitch + pxc + 1) * 16u;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) rq[c] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)c * plane_b));
+    }
+    float rx[NS], ry[NS], rz[NS], tx[NS], ty[NS], tz[NS];
+    uint32_t sbase[NS];                                                // smem address of (cb pair, window origin) minus the origin offset
+    bool stg[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if (s < nsrc) {
+            const float* m = rt + ((int64_t)s * B + b) * 12;
+            float ray[3];
+            pixel_ray(m, (float)pxc, (float)pyc, ray);
+            rx[s] = ray[0] * sx; ry[s] = ray[1] * sy; rz[s] = ray[2];
+            tx[s] = __ldg(m + 9) * sx; ty[s] = __ldg(m + 10) * sy; tz[s] = __ldg(m + 11);
+            stg[s] = s_staged[s] != 0;
+            sbase[s] = wv_smem_u32(wv_smem) + (uint32_t)s * win_src + (uint32_t)cp * 2u * win_plane - (uint32_t)(s_org[s][1] * kBW + s_org[s][0]) * 16u;
+        }
+    const float inv_n = 1.f / (float)(nsrc + 1);
+    const float2 inv_n2 = make_float2(inv_n, inv_n);
+    {   // wait for the windows (phase 0)
+        asm volatile("{\n\t.reg .pred p;\n\tWV_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra WV_DONE_%=;\n\tbra WV_WAIT_%=;\n\tWV_DONE_%=:\n\t}"
+                     ::"r"(wv_smem_u32(&bar)) : "memory");
+    }
+
+    const int p = pyc * W + pxc;
+    for (int d = d_begin; d < d_end; ++d) {
+        const float dv = __ldg(depth + (int64_t)b * D + d);
+        float2 s1[2][4], s2[2][4];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (s < nsrc) {
+                const float pz = fmaf(rz[s], dv, tz[s]);
+                float iz;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(pz));
+                const float ix = fminf(fmaxf(fmaf(fmaf(rx[s], dv, tx[s]), iz, oxy), 0.f), xmax);
+                const float iy = fminf(fmaxf(fmaf(fmaf(ry[s], dv, ty[s]), iz, oxy), 0.f), ymax);
+                const float kMagic = 12582912.f;
+                const float fxm = __fadd_rd(ix, kMagic), fym = __fadd_rd(iy, kMagic);
+                const int xi = __float_as_int(fxm) - 0x4B400000, yi = __float_as_int(fym) - 0x4B400000;
+                const float wx = ix - (fxm - kMagic), wy = iy - (fym - kMagic);
+                const float w11 = wx * wy, w10 = wx - w11, w01 = wy - w11, w00 = (1.f - wx) - w01;
+                const T2 wa = Pack2<T>::from_f2(make_float2(w00, w10)), wb = Pack2<T>::from_f2(make_float2(w01, w11));
+                const T2 w0 = Pack2<T>::lo(wa), w1 = Pack2<T>::hi(wa), w2 = Pack2<T>::lo(wb), w3 = Pack2<T>::hi(wb);
+                uint4 tap[2][4];
+                if (stg[s]) {
+                    const uint32_t a = sbase[s] + (uint32_t)(yi * kBW + xi) * 16u;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        tap[c][0] = wv_lds128(a + c * win_plane);
+                        tap[c][1] = wv_lds128(a + c * win_plane + 16u);
+                        tap[c][2] = wv_lds128(a + c * win_plane + kBW * 16u);
+                        tap[c][3] = wv_lds128(a + c * win_plane + kBW * 16u + 16u);
+                    }
+                } else {
+                    const char* base = reinterpret_cast<const char*>(srcs.p[s]) + map_b + (uint32_t)(yi * pitch + xi) * 16u;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const char* m = base + (size_t)c * plane_b;
+                        tap[c][0] = __ldg(reinterpret_cast<const uint4*>(m));
+                        tap[c][1] = __ldg(reinterpret_cast<const uint4*>(m + 16));
+                        tap[c][2] = __ldg(reinterpret_cast<const uint4*>(m + row_b));
+                        tap[c][3] = __ldg(reinterpret_cast<const uint4*>(m + row_b + 16));
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const T2* ha = reinterpret_cast<const T2*>(&tap[c][0]);
+                    const T2* hb = reinterpret_cast<const T2*>(&tap[c][1]);
+                    const T2* hc = reinterpret_cast<const T2*>(&tap[c][2]);
+                    const T2* hd = reinterpret_cast<const T2*>(&tap[c][3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        T2 v = __hmul2(ha[j], w0);
+                        v = __hfma2(hb[j], w1, v);
+                        v = __hfma2(hc[j], w2, v);
+                        v = __hfma2(hd[j], w3, v);
+                        const float2 f = Pack2<T>::to_f2(v);
+                        if (s == 0) { s1[c][j] = f; s2[c][j] = __fmul2_rn(f, f); }
+                        else { s1[c][j] = __fadd2_rn(s1[c][j], f); s2[c][j] = __ffma2_rn(f, f, s2[c][j]); }
+                    }
+                }
+            }
+        }
+        T* vp = var + ((((int64_t)b * CB + cp * 2) * D + d) * HW + p) * 8;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint4 out;
+            T2* ho = reinterpret_cast<T2*>(&out);
+            const T2* h = reinterpret_cast<const T2*>(&rq[c]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 r = Pack2<T>::to_f2(h[j]);
+                float2 t, u;
+                if (REFSQ) { const float2 r2 = __fmul2_rn(r, r); t = __fadd2_rn(s1[c][j], r2); u = __fadd2_rn(s2[c][j], r2); }
+                else { t = __fadd2_rn(s1[c][j], r); u = __ffma2_rn(r, r, s2[c][j]); }
+                const float2 v = __ffma2_rn(__fmul2_rn(t, t), make_float2(-inv_n, -inv_n), u);
+                ho[j] = Pack2<T>::from_f2(__fmul2_rn(v, inv_n2));
+            }
+            if (active) *reinterpret_cast<uint4*>(vp + (int64_t)c * D * HW * 8) = out;
+        }
+    }
+}
+
+typedef CUresult (*WvEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WvEncodeTiledFn wv_encode_tiled() {
+    static WvEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<WvEncodeTiledFn>(p);
+    }
+    return fn;
+}
 #endif  // !MVS_CPU_EMU
 
 static int depth_chunk(int D, int HW, int B, int CB) {
@@ -523,6 +766,45 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     for (int s = 0; s < MVS_MAX_SRC; ++s) sp.p[s] = s < nsrc ? srcs[s] : nullptr;
     const int CB = C / 8, HW = H * W;
 #ifndef MVS_CPU_EMU
+    const char* tma_env = getenv("MVS_WARP_TMA");          // test / tuning knob, read per call: 0 = gather every source from global memory
+    const int tma_knob = tma_env ? atoi(tma_env) : 1;
+    if (dtype_in == dtype_out && dtype_in != MVS_F32 && pad && !per_pixel && (CB == 2 || CB == 4) && tma_knob) {
+        // 16-bit storage, zero-bordered maps, plane hypotheses shared by the pixels of an item: TMA-staged source windows
+        const size_t smem = (size_t)nsrc * CB * kBH * kBW * 16;
+        WvEncodeTiledFn enc = wv_encode_tiled();
+        if (enc && smem <= 200 * 1024) {
+            WvMaps maps;
+            memset(&maps, 0, sizeof(maps));
+            const CUtensorMapDataType dt = dtype_in == MVS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+            const cuuint64_t Wp = W + 2, Hp = H + 3;
+            const cuuint64_t gdim[4] = {Wp * 8, Hp, (cuuint64_t)CB, (cuuint64_t)B};
+            const cuuint64_t gstr[3] = {Wp * 16, Hp * Wp * 16, (cuuint64_t)CB * Hp * Wp * 16};
+            const cuuint32_t box[4] = {kBW * 8, kBH, (cuuint32_t)CB, 1}, estr[4] = {1, 1, 1, 1};
+            for (int s = 0; s < nsrc; ++s) {
+                const CUresult cr = enc(&maps.m[s], dt, 4, const_cast<void*>(srcs[s]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_warp_var_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+            }
+            const int DC = 16;
+            const int tiles = (int)(mvs_cdiv(H, kTileH) * mvs_cdiv(W, kTileW));
+            MVS_REQUIRE((int64_t)B * mvs_cdiv(D, DC) <= 65535, MVS_E_SHAPE, "mvs_warp_var_fwd: B*D/16 too large for the launch grid");
+            const dim3 gridt((unsigned)tiles, (unsigned)(B * mvs_cdiv(D, DC)));
+            const unsigned nthr = 128u * (unsigned)(CB / 2);
+#define MVS_WT_ARGS(T) maps, (const T*)ref, sp, nsrc, rt, depth, (T*)var, B, CB, D, H, W, DC, align_corners
+#define MVS_WT_LAUNCH1(T, NS, RS, MB) do { cudaFuncSetAttribute(warp_var_fwd_tma_kernel<T, NS, RS, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                warp_var_fwd_tma_kernel<T, NS, RS, MB><<<gridt, nthr, smem, (cudaStream_t)stream>>>(MVS_WT_ARGS(T)); } while (0)
+#define MVS_WT_LAUNCH(T, NS, MB) do { if (ref_sq_in_sum) MVS_WT_LAUNCH1(T, NS, true, MB); else MVS_WT_LAUNCH1(T, NS, false, MB); } while (0)
+            static const int tma_minb = [] { const char* e = getenv("MVS_WARP_TMA_MINB"); return e ? atoi(e) : 2; }();
+#define MVS_WT_BY_NS(T) do { if (nsrc <= 2) MVS_WT_LAUNCH(T, 2, 3); else if (nsrc <= 4) { if (tma_minb == 3) MVS_WT_LAUNCH(T, 4, 3); else MVS_WT_LAUNCH(T, 4, 2); } \
+                             else if (nsrc <= 6) MVS_WT_LAUNCH(T, 6, 1); else MVS_WT_LAUNCH(T, 8, 1); } while (0)
+            if (dtype_in == MVS_F16) MVS_WT_BY_NS(__half); else MVS_WT_BY_NS(__nv_bfloat16);
+#undef MVS_WT_BY_NS
+#undef MVS_WT_LAUNCH
+#undef MVS_WT_LAUNCH1
+#undef MVS_WT_ARGS
+            return MVS_CHECK_LAUNCH("mvs_warp_var_fwd");
+        }
+    }
     if (dtype_in == dtype_out && dtype_in != MVS_F32 && pad && CB % 2 == 0) {
         // 16-bit storage, zero-bordered maps: packed-math kernel, all channels of a pixel in one thread when C % 32 == 0
         MVS_REQUIRE((int64_t)(H + 3) * (W + 2) * 16 < (1ll << 31), MVS_E_SHAPE, "mvs_warp_var_fwd: maps too large");

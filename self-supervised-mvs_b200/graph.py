@@ -17,24 +17,52 @@ from . import _lib
 
 
 class GraphedForward:
-    def __init__(self, fn: Callable[..., Dict[str, torch.Tensor]], example_inputs: Sequence[torch.Tensor], warmup: int = 2):
+    """`lanes` > 1 splits the batch (dim 0 of every input) into that many groups of items whose forwards are captured on
+    separate streams: items are independent MVS problems, and every kernel of the path is either a persistent one-CTA-per-SM
+    kernel with an uneven tail or (the plane sweep) a small-footprint kernel that fits beside one, so a second lane fills SMs
+    the first leaves idle.  Outputs are concatenated back in item order."""
+
+    def __init__(self, fn: Callable[..., Dict[str, torch.Tensor]], example_inputs: Sequence[torch.Tensor], warmup: int = 2,
+                 lanes: int = 1):
         self.fn = fn
         self.static_in = [t.clone() for t in example_inputs]
         self.warmup = warmup
+        self.lanes = max(1, min(int(lanes), self.static_in[0].shape[0]))
         self.recapture()
 
+    def _run(self) -> Dict[str, torch.Tensor]:
+        if self.lanes == 1:
+            return self.fn(*self.static_in)
+        cur = torch.cuda.current_stream()
+        chunks = [torch.tensor_split(t, self.lanes, dim=0) for t in self.static_in]
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs = []
+        for i in range(self.lanes):
+            st = self._lane_streams[i]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                outs.append(self.fn(*[c[i] for c in chunks]))
+                done = torch.cuda.Event()
+                done.record(st)
+            cur.wait_event(done)
+        return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
     def recapture(self) -> None:
+        self._lane_streams = [torch.cuda.Stream() for _ in range(self.lanes)] if self.lanes > 1 else []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
+            self.fn(*self.static_in)          # single-lane pass first: fills the weight-tile / folded-BN caches the lanes share
+            side.synchronize()
             for _ in range(self.warmup):
-                self.fn(*self.static_in)
+                self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launches
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.static_out = self.fn(*self.static_in)
+            self.static_out = self._run()
         self.launches_per_replay = _lib.launches - before
 
     def __call__(self, *inputs: torch.Tensor) -> Dict[str, torch.Tensor]:

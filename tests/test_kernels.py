@@ -153,6 +153,35 @@ def test_warp_variance_16bit_padded(gpu, oracle, dtype, tol, channels, nsrc, ref
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("baseline", [1.0, 4.0, 25.0])
+@pytest.mark.parametrize("shape", [(32, 4, 64, 96, 40), (16, 2, 37, 53, 9)])
+def test_warp_variance_tma_staging_is_transparent(gpu, monkeypatch, shape, baseline):
+    """TMA-staged source windows vs the same kernel arithmetic gathering from global memory: bit-identical volumes, whether
+    every window fits (baseline 1), some do (4) or none does (25: the per-source fallback inside the staged kernel)."""
+    ops = _ops()
+    from ssmvs_b200 import synth
+    c, nsrc, h, w, nd = shape
+    inp = synth.feature_inputs(2, nsrc + 1, c, h, w, nd, seed=11)
+    P = inp["proj_matrices"].clone()
+    ref_inv = torch.linalg.inv(P[:, 0].double())
+    for v in range(1, nsrc + 1):                      # widen the baseline: scale the translation of the relative pose
+        rel = P[:, v].double() @ ref_inv
+        rel[:, :3, 3] *= baseline
+        P[:, v] = (rel @ P[:, 0].double()).float()
+    rt = ops.compose_proj(gpu.to(P))
+    maps = ops.pack_c8_padded(gpu.to(inp["features"].flatten(0, 1)), torch.float16)
+    maps = maps.view(nsrc + 1, 2, *maps.shape[1:])
+    dv = gpu.to(inp["depth_values"])
+    monkeypatch.setenv("MVS_WARP_TMA", "1")
+    a = ops.warp_variance_maps(maps, rt, dv, torch.float16)
+    monkeypatch.setenv("MVS_WARP_TMA", "0")
+    b = ops.warp_variance_maps(maps, rt, dv, torch.float16)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.isfinite(a.float()).all() and a.float().abs().max() > 0
+
+
+@pytest.mark.gpu
 def test_warp_variance_16bit_padded_degenerate(gpu):
     """Planes behind / through the source camera and non-finite depths: finite output, exact zeros where every tap is
     outside the map (variance of (ref, 0) = ref^2 / 4), no out-of-bounds access at the clamped borders."""
