@@ -259,7 +259,8 @@ def main():
     pipe = None
     if graphed is not None:
         from ssmvs_b200.graph import StreamedForward
-        pipe = StreamedForward(graphed, ("depth", "photometric_confidence"))
+        pipe = StreamedForward(lambda i, pm, dv: model(i, pm, dv), [res["imgs"], res["proj_matrices"], res["depth_values"]],
+                               ("depth", "photometric_confidence"))
     host_batch = [pinned["imgs"], pinned["proj_matrices"], pinned["depth_values"]]
 
     def e2e_loop(steps):
@@ -400,7 +401,7 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "depth-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps,
-                        "how": "StreamedForward.run: pinned host batch -> H2D (copy stream, one step ahead) -> graph replay -> D2H of depth + confidence, every step; one event pair around the K steps, max over ranks"},
+                        "how": "StreamedForward.run: pinned host batch -> H2D (copy stream, one step ahead, straight into the static inputs of one of two captured graphs) -> graph replay -> D2H of depth + confidence, every step; one event pair around the K steps, max over ranks"},
                 "roofline": dominant, "roofline_warp_var": roof_wv, "roofline_conv0": roof_conv0, "roofline_reg3d": roof_reg,
                 "stage_ms": stages}
         if world == 1 and not args.no_cpu_baseline:

@@ -75,47 +75,50 @@ class GraphedForward:
 
 
 class StreamedForward:
-    """Host-to-host inference pipeline around a `GraphedForward`: pinned host batch -> device -> forward -> pinned host result,
-    double-buffered so that the upload of batch i+1 (copy stream) overlaps the kernels of batch i (compute stream).
+    """Host-to-host inference pipeline: pinned host batch -> device -> forward -> pinned host result, double-buffered so that
+    the upload of batch i+1 (copy stream) overlaps the kernels of batch i (compute stream).
 
-        pipe = StreamedForward(graphed, ("depth", "photometric_confidence"))
-        for out in pipe.run(host_batches):      # out: dict of pinned host tensors, valid until two batches later
+        pipe = StreamedForward(fn, example_inputs, ("depth", "photometric_confidence"))
+        for out in pipe.run(host_batches):      # out: dict of pinned host tensors, valid until the next iteration
             ...
 
-    Every batch is copied host->device and every result device->host; nothing is cached between batches."""
+    Two CUDA graphs of the same forward are captured, one per input buffer set, so a batch is uploaded straight into the
+    static inputs of the graph that will consume it (no device-to-device staging copy).  Every batch is copied host->device
+    and every result device->host; nothing is cached between batches."""
 
-    def __init__(self, graphed: GraphedForward, out_keys: Sequence[str]):
-        self.g = graphed
+    def __init__(self, fn: Callable[..., Dict[str, torch.Tensor]], example_inputs: Sequence[torch.Tensor], out_keys: Sequence[str],
+                 warmup: int = 2):
+        self.graphs = [GraphedForward(fn, example_inputs, warmup=warmup) for _ in range(2)]
         self.keys = tuple(out_keys)
         self.copy = torch.cuda.Stream()
-        self.stage = [[torch.empty_like(t) for t in graphed.static_in] for _ in range(2)]
         self.uploaded = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
-        self.out_host = [{k: torch.empty(graphed.static_out[k].shape, dtype=graphed.static_out[k].dtype).pin_memory() for k in self.keys}
+        g = self.graphs[0]
+        self.out_host = [{k: torch.empty(g.static_out[k].shape, dtype=g.static_out[k].dtype).pin_memory() for k in self.keys}
                          for _ in range(2)]
         self.out_done = [torch.cuda.Event() for _ in range(2)]
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in graphed.static_in)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in g.static_in)
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.out_host[0].values())
+        self.launches_per_step = g.launches_per_replay
 
     def upload(self, i: int, host_inputs: Sequence[torch.Tensor]) -> None:
         s = i & 1
-        self.copy.wait_event(self.consumed[s])          # the forward of batch i-2 has read this staging set
+        self.copy.wait_event(self.consumed[s])          # the forward of batch i-2 has finished with this input set
         with torch.cuda.stream(self.copy):
-            for dst, src in zip(self.stage[s], host_inputs):
+            for dst, src in zip(self.graphs[s].static_in, host_inputs):
                 dst.copy_(src, non_blocking=True)
             self.uploaded[s].record(self.copy)
 
     def forward(self, i: int) -> Dict[str, torch.Tensor]:
         s = i & 1
+        g = self.graphs[s]
         cur = torch.cuda.current_stream()
         cur.wait_event(self.uploaded[s])
-        for dst, src in zip(self.g.static_in, self.stage[s]):
-            dst.copy_(src, non_blocking=True)           # device-to-device into the graph's static inputs
+        g.graph.replay()
+        _lib.launches += g.launches_per_replay
         self.consumed[s].record(cur)
-        self.g.graph.replay()
-        _lib.launches += self.g.launches_per_replay
         for k in self.keys:
-            self.out_host[s][k].copy_(self.g.static_out[k], non_blocking=True)
+            self.out_host[s][k].copy_(g.static_out[k], non_blocking=True)
         self.out_done[s].record(cur)
         return self.out_host[s]
 

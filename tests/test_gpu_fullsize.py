@@ -186,3 +186,53 @@ def test_cvpmvsnet_half_precision_volume(gpu):
         assert torch.isfinite(a).all()
         assert ((a - b).abs() / b).max().item() < 3e-3
     assert (got["prob_confidence"] - ref["prob_confidence"]).abs().max().item() < 3e-2
+
+
+def test_config3_cvp_three_stage_bf16_full_size(gpu):
+    """BASELINE configs[2]: CVP-MVSNet, 3 pyramid levels, 1 + 4 views of 512x640, bf16 volumes on the tensor-core path, against
+    the same network with fp32 volumes (SIMT fp32 path): every level's depth map within bf16 tolerance of the depth range."""
+    from types import SimpleNamespace
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    torch.manual_seed(0)
+    model = CVPMVSNet(SimpleNamespace(nsrc=4, nscale=3, mode="test"))
+    with torch.no_grad():
+        model.cost_reg_refine.prob0.weight.mul_(32.0)
+    model = model.eval().to(gpu.device)
+    inp = gpu.to(synth.cvp_inputs(1, 4, 512, 640, seed=5))
+    args = [inp[k] for k in ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")]
+    with torch.no_grad():
+        model.volume_dtype = torch.float32
+        want = model(*args)
+        model.volume_dtype = torch.bfloat16
+        got = model(*args)
+    assert [tuple(t.shape) for t in got["depth_est_list"]] == [(1, 512, 640), (1, 256, 320), (1, 128, 160)]
+    span = float(inp["depth_max"][0] - inp["depth_min"][0])
+    for a, b in zip(got["depth_est_list"], want["depth_est_list"]):
+        assert torch.isfinite(a).all()
+        assert (a - b).abs().mean().item() < 5e-3 * span
+    assert got["prob_confidence"].shape == (1, 512, 640)
+
+
+def test_config4_train_step_full_size(gpu):
+    """BASELINE configs[3]: one self-supervised training step (photometric loss; N = 5 views because the reference's top-3 view
+    selection needs >= 3 sources, hazard H5) at 512x640, D = 192: finite loss, gradients on every trainable parameter, an
+    Adam step that changes the weights.  (The co-segmentation term needs pretrained VGG weights: out of scope)"""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False).to(gpu.device).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    inp = gpu.to(synth.mvsnet_inputs(1, 5, 512, 640, 192, seed=2))
+    before = model.cost_regularization.conv0.conv.weight.detach().clone()
+    out = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])
+    loss = UnSupLoss()(inp["imgs"], inp["cams"], out["depth"])
+    opt.zero_grad()
+    loss.backward()
+    assert torch.isfinite(loss)
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    opt.step()
+    assert not torch.equal(before, model.cost_regularization.conv0.conv.weight.detach())
