@@ -246,6 +246,21 @@ template <> struct Pack2<__half> {
     static __device__ __forceinline__ __half2 from_f2(float2 v) { return __float22half2_rn(v); }
     static __device__ __forceinline__ __half2 lo(__half2 v) { return __low2half2(v); }
     static __device__ __forceinline__ __half2 hi(__half2 v) { return __high2half2(v); }
+    // s1 += v, s2 += v * v with the fp16 pair promoted inside the instruction (FHADD / FHFMA): same values as converting first,
+    // without the two conversion instructions per pair and without the double-issue packed-fp32 forms
+    static __device__ __forceinline__ void accumulate(__half2 v, float2& s1, float2& s2) {
+        const unsigned short l = __half_as_ushort(__low2half(v)), h = __half_as_ushort(__high2half(v));
+        asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(s1.x) : "h"(l));
+        asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(s1.y) : "h"(h));
+        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(s2.x) : "h"(l));
+        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(s2.y) : "h"(h));
+    }
+    static __device__ __forceinline__ void start(__half2 v, float2& s1, float2& s2) {
+        s1 = __half22float2(v);
+        const unsigned short l = __half_as_ushort(__low2half(v)), h = __half_as_ushort(__high2half(v));
+        asm("fma.rn.f32.f16 %0, %1, %1, %2;" : "=f"(s2.x) : "h"(l), "f"(0.f));
+        asm("fma.rn.f32.f16 %0, %1, %1, %2;" : "=f"(s2.y) : "h"(h), "f"(0.f));
+    }
 };
 template <> struct Pack2<__nv_bfloat16> {
     typedef __nv_bfloat162 type;
@@ -254,6 +269,17 @@ template <> struct Pack2<__nv_bfloat16> {
     static __device__ __forceinline__ __nv_bfloat162 from_f2(float2 v) { return __float22bfloat162_rn(v); }
     static __device__ __forceinline__ __nv_bfloat162 lo(__nv_bfloat162 v) { return __low2bfloat162(v); }
     static __device__ __forceinline__ __nv_bfloat162 hi(__nv_bfloat162 v) { return __high2bfloat162(v); }
+    static __device__ __forceinline__ void accumulate(__nv_bfloat162 v, float2& s1, float2& s2) {
+        const unsigned short l = __bfloat16_as_ushort(__low2bfloat16(v)), h = __bfloat16_as_ushort(__high2bfloat16(v));
+        asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(s1.x) : "h"(l));
+        asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(s1.y) : "h"(h));
+        asm("fma.rn.f32.bf16 %0, %1, %1, %0;" : "+f"(s2.x) : "h"(l));
+        asm("fma.rn.f32.bf16 %0, %1, %1, %0;" : "+f"(s2.y) : "h"(h));
+    }
+    static __device__ __forceinline__ void start(__nv_bfloat162 v, float2& s1, float2& s2) {
+        s1 = __bfloat1622float2(v);
+        s2 = __fmul2_rn(s1, s1);
+    }
 };
 
 template <typename T, int CPT, int NS, int MINB>   // NS = compile-time bound on the source count (register arrays are sized by it)
@@ -468,9 +494,8 @@ warp_var_fwd_pad_kernel(const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const
                         v = __hfma2(hb[j], w1, v);
                         v = __hfma2(hc[j], w2, v);
                         v = __hfma2(hd[j], w3, v);
-                        const float2 f = Pack2<T>::to_f2(v);
-                        if (s == 0) { s1[c][j] = f; s2[c][j] = __fmul2_rn(f, f); }
-                        else { s1[c][j] = __fadd2_rn(s1[c][j], f); s2[c][j] = __ffma2_rn(f, f, s2[c][j]); }
+                        if (s == 0) Pack2<T>::start(v, s1[c][j], s2[c][j]);
+                        else Pack2<T>::accumulate(v, s1[c][j], s2[c][j]);
                     }
                 }
             }
@@ -695,9 +720,8 @@ warp_var_fwd_tma_kernel(const __grid_constant__ WvMaps maps, const T* __restrict
                         v = __hfma2(hb[j], w1, v);
                         v = __hfma2(hc[j], w2, v);
                         v = __hfma2(hd[j], w3, v);
-                        const float2 f = Pack2<T>::to_f2(v);
-                        if (s == 0) { s1[c][j] = f; s2[c][j] = __fmul2_rn(f, f); }
-                        else { s1[c][j] = __fadd2_rn(s1[c][j], f); s2[c][j] = __ffma2_rn(f, f, s2[c][j]); }
+                        if (s == 0) Pack2<T>::start(v, s1[c][j], s2[c][j]);
+                        else Pack2<T>::accumulate(v, s1[c][j], s2[c][j]);
                     }
                 }
             }
