@@ -192,6 +192,27 @@ def cpu_forward_timer(steps: int, warmup: int):
     return times, threads
 
 
+def gpu_library_timer(dev, steps: int = 3):
+    """The reference's op sequence (oracle port: ATen grid_sample + elementwise variance + cuDNN conv3d + softmax, fp32, torch
+    defaults) executed by PyTorch ON THE GPU, one item per forward: the library baseline the hand-written kernels replace."""
+    from ssmvs_b200 import synth
+    oracle = load_oracle()
+    model = make_model(torch.float32)
+    sd = {k: v.detach().clone().to(dev) for k, v in model.state_dict().items()}
+    inp = {k: v.to(dev) for k, v in synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=0).items()}
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.no_grad(), torch.device(dev):
+        oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], sd)
+        torch.cuda.synchronize(dev)
+        for a, b in ev:
+            a.record()
+            oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], sd)
+            b.record()
+        torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
+    return [a.elapsed_time(b) * 1e-3 for a, b in ev]
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -408,6 +429,12 @@ def main():
             times, threads = cpu_forward_timer(3, 1)
             line["cpu_baseline"] = {"value": SAMPLES_PER_ITEM * len(times) / sum(times), "unit": "depth-samples/s", "cores": threads,
                                     "kind": "port", "sample": "3 full forward passes of 1 item after 1 warm-up (oracle port of the reference's torch-CPU path, fp32; best of the probed thread counts, host has %d cores)" % (os.cpu_count() or 1)}
+            try:
+                gt = gpu_library_timer(dev)
+                line["gpu_library_baseline"] = {"value": SAMPLES_PER_ITEM * len(gt) / sum(gt), "unit": "depth-samples/s", "kind": "port",
+                                                "sample": "3 forward passes of 1 item after 1 warm-up: the reference's op sequence (oracle port) run by PyTorch on this GPU (ATen grid_sample, cuDNN conv3d, fp32 with torch's default TF32 convolutions)"}
+            except Exception as exc:   # informational only
+                line["gpu_library_baseline"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
         print(json.dumps(line))
     parallel.barrier()
 

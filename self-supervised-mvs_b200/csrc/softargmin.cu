@@ -49,6 +49,67 @@ softargmin_fwd_kernel(const float* __restrict__ cost, const float* __restrict__ 
     }
 }
 
+#ifndef MVS_CPU_EMU
+// Same arithmetic, four times the memory-level parallelism: a block = 32 pixel columns x 4 quarters of the depth axis.  The
+// quarters read the column once from global memory into shared memory (coalesced along w) and exponentiate it there in
+// parallel (both are order-free); one warp then walks the column sequentially in shared memory for the two order-sensitive
+// sums (sum of exponentials, expectations: ascending plane order is part of the parity contract, hazard H12).  The column is
+// read from DRAM once instead of three times and expf runs once per element instead of twice, with identical results.
+__global__ void __launch_bounds__(128)
+softargmin_fwd_smem_kernel(const float* __restrict__ cost, const float* __restrict__ depth, int per_pixel,
+                           float* __restrict__ depth_out, int64_t* __restrict__ index_out, float* __restrict__ conf_out,
+                           float* __restrict__ prob_out, int B, int D, int HW) {
+    extern __shared__ float xs[];                 // [D][32]
+    __shared__ float red[4][32];
+    const int c = threadIdx.x & 31, qd = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + c;
+    const bool live = i < (int64_t)B * HW;
+    const int p = live ? (int)(i % HW) : 0;
+    const int b = live ? (int)(i / HW) : 0;
+    const float* col = cost + (int64_t)b * D * HW + p;
+    const int dq = (D + 3) / 4, d0 = qd * dq, d1 = min(D, d0 + dq);
+    float mx = -INFINITY;
+#pragma unroll 16
+    for (int d = d0; d < d1; ++d) {
+        const float x = live ? __ldg(col + (int64_t)d * HW) : 0.f;
+        xs[d * 32 + c] = x;
+        mx = fmaxf(mx, x);
+    }
+    red[qd][c] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0][c], red[1][c]), fmaxf(red[2][c], red[3][c]));
+#pragma unroll 8
+    for (int d = d0; d < d1; ++d) xs[d * 32 + c] = expf(xs[d * 32 + c] - mx);
+    __syncthreads();
+    if (qd != 0 || !live) return;
+    float sum = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) sum += xs[d * 32 + c];
+    float e_depth = 0.f, e_index = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+        const float pd = xs[d * 32 + c] / sum;
+        const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+        e_depth += pd * dv;
+        e_index += pd * (float)d;
+        if (prob_out) prob_out[((int64_t)b * D + d) * HW + p] = pd;
+    }
+    if (depth_out) depth_out[i] = e_depth;
+    if (index_out || conf_out) {
+        const long long idx = (long long)e_index;  // trunc toward zero, like .long()
+        if (index_out) index_out[i] = (int64_t)idx;
+        if (conf_out) {
+            float s = 0.f;
+            for (int k = -1; k <= 2; ++k) {
+                const long long d = idx + k;
+                if (d >= 0 && d < D) s += xs[(int)d * 32 + c] / sum;
+            }
+            conf_out[i] = 4.f * (s / 4.f);
+        }
+    }
+}
+#endif
+
 // d depth / d cost_d = p_d (depth_d - E[depth])
 __global__ void __launch_bounds__(128)
 softargmin_bwd_kernel(const float* __restrict__ cost, const float* __restrict__ depth, int per_pixel,
@@ -82,6 +143,15 @@ extern "C" int mvs_softargmin_fwd(const float* cost, const float* depth, int per
     MVS_REQUIRE(cost && depth, MVS_E_ARG, "mvs_softargmin_fwd: null pointer");
     MVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, MVS_E_SHAPE, "mvs_softargmin_fwd: bad dims");
     const int64_t total = (int64_t)B * H * W;
+#ifndef MVS_CPU_EMU
+    const size_t smem = (size_t)D * 32 * sizeof(float);
+    if (smem <= 96 * 1024) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(softargmin_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        softargmin_fwd_smem_kernel<<<mvs_cdiv(total, 32), 128, smem, (cudaStream_t)stream>>>(cost, depth, per_pixel, depth_out, index_out,
+                                                                                           conf_out, prob_out, B, D, H * W);
+        return MVS_CHECK_LAUNCH("mvs_softargmin_fwd");
+    }
+#endif
     const int bs = total < 148 * 1024 ? 32 : 128;   // few pixel columns: one warp per block spreads them over all SMs
     MVS_LAUNCH(softargmin_fwd_kernel, dim3(mvs_cdiv(total, bs)), dim3(bs), stream, cost, depth, per_pixel, depth_out,
                index_out, conf_out, prob_out, B, D, H * W);

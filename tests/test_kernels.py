@@ -220,6 +220,19 @@ def test_soft_argmin(be, oracle, golden):
     assert rel_err(d3, oracle.soft_argmin(g["cost_reg"], dpp)[1]) < 1e-6
 
 
+def test_soft_argmin_ragged(be, oracle):
+    """Depth count not a multiple of 4 and a column count not a multiple of the block: the shared-memory kernel's tails."""
+    ops = _ops()
+    torch.manual_seed(9)
+    cost = 3.0 * torch.randn(2, 13, 7, 9)
+    dv = 400.0 + 2.5 * torch.arange(13, dtype=torch.float32).repeat(2, 1)
+    depth, index, conf, prob = ops.soft_argmin(be.to(cost), be.to(dv), True)
+    p_o, d_o = oracle.soft_argmin(cost, dv)
+    i_o, c_o = oracle.photometric_confidence(p_o)
+    assert rel_err(depth, d_o) < 1e-6 and rel_err(prob, p_o) < 1e-6 and rel_err(conf, c_o) < 1e-5
+    assert (index.cpu() != i_o).sum().item() == 0
+
+
 def test_soft_argmin_index_exact_on_peaky_columns(be, oracle):
     """One-hot-like columns: expected index lands on integers; truncation must agree with the oracle everywhere."""
     ops = _ops()
