@@ -124,15 +124,17 @@ int mvs_conv3d_bwd_weight(const mvs_conv3d_desc* d, const void* x, const float* 
  *   image-major maps [M][Cout/8][Hout+3][Wout+2][8] that mvs_warp_var_fwd(pad=1) gathers from (border pre-zeroed by the caller).
  *   y = [relu](conv(x) * scale + shift);  g = gather-form weights G[ksize*ksize][Cin][CoutPad] fp32 (tap = kh * ksize + kw).
  * ksize/stride: 3/1 (pad 1) or 5/2 (pad 2, even Hin/Win).  Replaces ConvBnReLU / Conv2d of FeatureNet
- * (jdacs/models/mvsnet.py:17-34, module.py:13-32) in eval mode with 16-bit storage. */
+ * (jdacs/models/mvsnet.py:17-34, module.py:13-32) and conv + LeakyReLU of FeaturePyramid (jdacs-ms/models/network.py:16-41,
+ * modules.py:15-19) in eval mode with 16-bit storage. */
 typedef struct {
     int M, Cin, Cout;      /* Cin in {8,16,32,48,64} (3-channel images are zero-padded to 8), Cout in {8,..,64} */
     int Hin, Win, Hout, Wout;
     int ksize, stride;
     int dtype;             /* MVS_F16 | MVS_BF16 */
-    int relu;
+    int relu;              /* activation: 0 none, 1 ReLU, 2 LeakyReLU(leaky_slope) */
     int out_padded;
     int ws_packed;         /* 1: `ws` already holds the weight tiles of an earlier call with the same g (frozen weights) */
+    float leaky_slope;
 } mvs_conv2d_desc;
 int64_t mvs_conv2d_workspace_bytes(const mvs_conv2d_desc* d);
 int mvs_conv2d_fwd(const mvs_conv2d_desc* d, const void* x, const float* g, const float* scale, const float* shift, void* y,

@@ -28,7 +28,7 @@ class Conv3dDesc(C.Structure):
 
 class Conv2dDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("M", "Cin", "Cout", "Hin", "Win", "Hout", "Wout", "ksize", "stride", "dtype", "relu",
-                                       "out_padded", "ws_packed")]
+                                       "out_padded", "ws_packed")] + [("leaky_slope", C.c_float)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

@@ -75,6 +75,8 @@ struct TcParams {
     int nsub, stages, sps, live, groups, nentries, bstages, nwork;
     int b_resident, relu, is_bf16, kdfold;
     int d_mul, d_org;                // depth coordinate of slot j of an item: d_mul * d0 + d_org + j
+    int kwfold;                      // stride-1 programs: the 3 kw taps are column blocks summed by the epilogue (else 9+ shifted entries)
+    float slope;                     // activation as max(v, v * slope): 0 = ReLU, 1 = none, 0.1 = LeakyReLU(0.1)
     int64_t ys_b, ys_cb, ys_d, ys_h, y_org;   // output (and skip) addressing in voxels: b, channel block, d, h strides + origin
     uint32_t chunk_bytes, sub_bytes, slot_bytes, btile_bytes, tmem_cols;
     Entry prog[kMaxEntries];
@@ -201,7 +203,7 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
     constexpr int NLD = KWFOLD ? 3 : NOV;
     constexpr int64_t vs = C1 ? 1 : 8;
     const int64_t plane = p.ys_d, row = p.ys_h;
-    const float floor_ = p.relu ? 0.f : -INFINITY;          // branch-free optional ReLU
+    const float slope = p.slope;                            // branch-free activation: max(v, v * slope)
 #ifdef MVS_TC_TRACE
     if (blockIdx.x == 0 && threadIdx.x == 192) { g_trace[8][g_tcount & 1023] = clock64(); }
 #endif
@@ -262,13 +264,14 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
                     }
                     const int64_t off = off0[t] + (NOV == 8 ? ((ov >> 2) * plane + ((ov >> 1) & 1) * row + (ov & 1)) * vs : 0);
                     if (C1) {
-                        float x = fmaxf(o[0] * sc[0] + sh[0], floor_);
+                        float x = o[0] * sc[0] + sh[0];
+                        x = fmaxf(x, x * slope);
                         if (SKIP) x += __uint_as_float(sk[t][q].x);
                         if (ra[t].valid) reinterpret_cast<float*>(p.y)[off] = x;
                         continue;
                     }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k] * sc[k] + sh[k], floor_);
+                    for (int k = 0; k < 8; ++k) { const float a = o[k] * sc[k] + sh[k]; o[k] = fmaxf(a, a * slope); }
                     if (SKIP) {
                         float sv[8];
                         unpack8<T>(sk[t][q], sv);
@@ -555,7 +558,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
         const int mpar = (warp - 6) >> 2;          // the warps of a quadrant take M-tiles mpar, mpar + kMStride, ...
         const int CoB = (p.Cout + 7) / 8;
         const int64_t HWo = (int64_t)p.Ho * p.Wo;
-        const bool kwfold = p.mode == MODE_S1;
+        const bool kwfold = p.kwfold != 0;
         int I = 0;
         for (int t = blockIdx.x; t < p.nwork; t += gridDim.x) {
             const Work k = decode(t);
@@ -702,7 +705,7 @@ struct Plan { TcParams p; TileSrc src; size_t smem; int stages_chosen; };
 // is the image index (two_d: Din = Dout = M, one live plane per step, no taps across images) with a ksize x ksize filter:
 // 3x3 stride 1 (kw folded into N like the 3-D stride-1 program) or 5x5 stride 2 (parity-staged like the 3-D stride-2 one).
 // out_pad: write the zero-bordered image-major C8P layout the plane-sweep gather reads instead of the stack layout.
-struct Spec : mvs_conv3d_desc { int two_d, ksize, out_pad; };
+struct Spec : mvs_conv3d_desc { int two_d, ksize, out_pad; float slope; };
 
 int mode_of(const Spec* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? MODE_T2 : MODE_S2); }
 
@@ -712,7 +715,10 @@ bool kdfold_of(const Spec* d) {
     const char* e = getenv("MVS_TC_KDFOLD");
     return !d->two_d && mode_of(d) == MODE_S1 && cop_of(d) == 8 && !(e && atoi(e) == 0);
 }
-int nblk_of(const Spec* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : 3) : (mode_of(d) == MODE_T2 ? 8 : 1); }
+// Stride-1 programs fold the 3 kw taps into N (3 column blocks) unless that makes the accumulators so wide that only one
+// M-tile fits in TMEM (2-D layers with 64 output channels): those run 9 entries with shifted A views, like the stride-2 program.
+bool kwfold_of(const Spec* d) { return mode_of(d) == MODE_S1 && !(d->two_d && 3 * cop_of(d) > 128); }
+int nblk_of(const Spec* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : (kwfold_of(d) ? 3 : 1)) : (mode_of(d) == MODE_T2 ? 8 : 1); }
 int n_of(const Spec* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 
 // A "fold tap": one A view (slot, sub-plane, row shift) and, per column block, the filter tap it multiplies (-1 = none).
@@ -724,7 +730,15 @@ int build_program(const Spec* d, TcParams& p, TileSrc& src) {
     memset(&src, -1, sizeof(src));
     FoldTap ft[27];
     int nft = 0;
-    if (d->two_d && mode == MODE_S1) {
+    if (d->two_d && mode == MODE_S1 && !kwfold_of(d)) {
+        // 3x3 over one image plane, one entry per tap: row shift kh * 32 + kw from the tile origin (o - 1)
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                FoldTap& t = ft[nft++];
+                t.slot = 0; t.sub = 0; t.shift = kh * kPW + kw;
+                for (int c = 0; c < 12; ++c) t.tap[c] = c == 0 ? kh * 3 + kw : -1;
+            }
+    } else if (d->two_d && mode == MODE_S1) {
         // 3x3 over one image plane: one fold tap per kh, column block c = input column offset c; gather form G[kh * 3 + kw]
         for (int kh = 0; kh < 3; ++kh) {
             FoldTap& t = ft[nft++];
@@ -833,6 +847,7 @@ bool make_plan(const Spec* d, Plan& pl) {
     p.Di = d->Din; p.Hi = d->Hin; p.Wi = d->Win; p.Do = d->Dout; p.Ho = d->Hout; p.Wo = d->Wout;
     if (p.mode == MODE_T2) { p.Dt = p.Di; p.Ht = p.Hi; p.Wt = p.Wi; } else { p.Dt = p.Do; p.Ht = p.Ho; p.Wt = p.Wo; }
     p.relu = d->relu; p.is_bf16 = d->dtype_in == MVS_BF16;
+    p.slope = d->slope; p.kwfold = kwfold_of(d) ? 1 : 0;
     p.nsub = p.mode == MODE_S2 ? 4 : 1;
     p.sps = d->two_d ? 1 : (p.mode == MODE_S2 ? 2 : 1);
     p.live = d->two_d ? 1 : (p.mode == MODE_T2 ? 2 : 3);
@@ -927,7 +942,7 @@ bool make_plan(const Spec* d, Plan& pl) {
 static Spec spec3d(const mvs_conv3d_desc* d) {
     Spec sp;
     static_cast<mvs_conv3d_desc&>(sp) = *d;
-    sp.two_d = 0; sp.ksize = 3; sp.out_pad = 0;
+    sp.two_d = 0; sp.ksize = 3; sp.out_pad = 0; sp.slope = d->relu ? 0.f : 1.f;
     return sp;
 }
 
@@ -939,6 +954,7 @@ static Spec spec2d(const mvs_conv2d_desc* d) {
     sp.Din = d->M; sp.Hin = d->Hin; sp.Win = d->Win; sp.Dout = d->M; sp.Hout = d->Hout; sp.Wout = d->Wout;
     sp.stride = d->stride; sp.transposed = 0; sp.dtype_in = d->dtype; sp.dtype_out = d->dtype; sp.relu = d->relu; sp.algo = d->ws_packed ? 3 : 2;
     sp.two_d = 1; sp.ksize = d->ksize; sp.out_pad = d->out_padded;
+    sp.slope = d->relu == 1 ? 0.f : (d->relu == 2 ? d->leaky_slope : 1.f);
     return sp;
 }
 
@@ -958,7 +974,7 @@ static int64_t tc_workspace_bytes(const Spec* d) {
     if (!tc_supported(d)) return 0;
     const int kchunks = d->Cin == 8 ? 2 : d->Cin / 8;
     // upper bounds on the entry count (Cin = 8 pairs need fewer)
-    const int nentries = d->two_d ? (d->ksize == 3 ? 3 : 25) : (mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27));
+    const int nentries = d->two_d ? (d->ksize == 3 ? (kwfold_of(d) ? 3 : 9) : 25) : (mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27));
     return (int64_t)nentries * kchunks * n_of(d) * 16;  // weight tiles [entry][kchunk][N][8] in the storage dtype
 }
 

@@ -34,6 +34,37 @@ class FeaturePyramid(nn.Module):
         f = self.conv0aa(img)
         return self.conv0bh(self.conv0bg(self.conv0bf(self.conv0be(self.conv0bd(self.conv0bc(self.conv0bb(self.conv0ba(f))))))))
 
+    LAYERS = ("conv0aa", "conv0ba", "conv0bb", "conv0bc", "conv0bd", "conv0be", "conv0bf", "conv0bg", "conv0bh")
+
+    def forward_maps(self, imgs, scales, dtype):
+        """Eval-mode path on the repo's tcgen05 kernel: imgs [B,N,3,H,W] fp32 (view 0 = reference) -> per pyramid level the
+        zero-bordered C8P feature maps of all views [N,B,2,Hl+3,Wl+2,8] in `dtype` (finest level first), the layout the fused
+        plane sweep gathers from.  Nine mvs_conv2d_fwd launches per level (bias + LeakyReLU(0.1) in the epilogue); the image
+        pyramid itself is the reference's bilinear x0.5 resize (library code, 3 channels)."""
+        dev = imgs.device
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = ("tc", dtype, dev)
+        hit = self.__dict__.setdefault("_packed", {}).get(key)
+        if hit is None or hit[0] != sig:
+            layers = []
+            for name in self.LAYERS:
+                c = getattr(self, name)[0]
+                layers.append((ops.pack_conv2d_weight(c.weight), c.out_channels, c.bias.detach().float().contiguous()))
+            hit = (sig, layers, {})
+            self._packed[key] = hit
+        b, n = imgs.shape[0], imgs.shape[1]
+        out = []
+        cur = imgs
+        for level in range(scales):
+            if level:
+                flat = F.interpolate(cur.reshape(b * n, *cur.shape[2:]), scale_factor=0.5, mode='bilinear', align_corners=None)
+                cur = flat.reshape(b, n, *flat.shape[1:])
+            x = ops.pack_images_c8(cur, dtype)
+            for i, (g, cout, bias) in enumerate(hit[1]):
+                x = ops.conv2d_raw(x, g, cout, 3, 1, None, bias, 0.1, out_padded=(i == len(hit[1]) - 1), tile_cache=hit[2])
+            out.append(x.view(n, b, *x.shape[1:]))
+        return out
+
     def forward(self, img, scales=5):
         fp = [self._trunk(img)]
         for _ in range(scales - 1):
@@ -95,6 +126,7 @@ class CVPMVSNet(nn.Module):
         self.cost_reg_refine = CostRegNet()
         self.args = args
         self.volume_dtype = volume_dtype
+        self.feature_tc = True      # eval + 16-bit volumes: FeaturePyramid on the repo's tcgen05 convolution kernel
 
     def forward(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max):
         nsrc, nscale = self.args.nsrc, self.args.nscale
@@ -102,16 +134,28 @@ class CVPMVSNet(nn.Module):
         dt = torch.float32 if self.training else self.volume_dtype
         self.cost_reg_refine.act_dtype = None if self.training else dt
 
-        ref_pyr = self.featurePyramid(ref_img, nscale)
-        src_pyrs = [self.featurePyramid(src_imgs[:, i], nscale) for i in range(nsrc)]
-        ref_in_ms = conditionIntrinsics(ref_in, ref_img.shape, [f.shape for f in ref_pyr])
-        src_in_ms = torch.stack([conditionIntrinsics(src_in[:, i], ref_img.shape, [f.shape for f in src_pyrs[i]])
+        fast = (not self.training) and dt != torch.float32 and ref_img.is_cuda and self.feature_tc
+        if fast:
+            # eval, 16-bit volumes: the pyramid on the tcgen05 kernel, every level already in the sweep's gather layout
+            imgs = torch.cat((ref_img.unsqueeze(1), src_imgs[:, :nsrc]), 1)
+            maps = self.featurePyramid.forward_maps(imgs, nscale, dt)
+            shapes = [(m.shape[3] - 3, m.shape[4] - 2) for m in maps]
+        else:
+            ref_pyr = self.featurePyramid(ref_img, nscale)
+            src_pyrs = [self.featurePyramid(src_imgs[:, i], nscale) for i in range(nsrc)]
+            shapes = [tuple(f.shape[2:]) for f in ref_pyr]
+        fp_shapes = [(0, 0) + s for s in shapes]
+        ref_in_ms = conditionIntrinsics(ref_in, ref_img.shape, fp_shapes)
+        src_in_ms = torch.stack([conditionIntrinsics(src_in[:, i], ref_img.shape, fp_shapes)
                                  for i in range(nsrc)]).permute(1, 0, 2, 3, 4)  # [B,nsrc,nscale,3,3]
 
         # coarsest level: fronto-parallel sweep (network.py:110-148)
         depth_hypos = calSweepingDepthHypo(ref_in_ms[:, -1], src_in_ms[:, 0, -1], ref_ex, src_ex, depth_min, depth_max)
         rt = ops.compose_proj_ke(ref_in_ms[:, -1], src_in_ms[:, :, -1], ref_ex, src_ex[:, :nsrc], 1.0)
-        cost_volume = ops.warp_variance(ref_pyr[-1], [p[-1] for p in src_pyrs], rt, depth_hypos, dt, ALIGN_CORNERS, True)
+        if fast:
+            cost_volume = ops.warp_variance_maps(maps[-1], rt, depth_hypos, dt, ALIGN_CORNERS, True)
+        else:
+            cost_volume = ops.warp_variance(ref_pyr[-1], [p[-1] for p in src_pyrs], rt, depth_hypos, dt, ALIGN_CORNERS, True)
         cost_reg = self.cost_reg_refine(cost_volume)
         depth, _, conf, _ = ops.soft_argmin(cost_reg, depth_hypos)
         depth_est_list.append(depth)
@@ -121,8 +165,12 @@ class CVPMVSNet(nn.Module):
             depth_up = F.interpolate(depth[None, :], size=None, scale_factor=2, mode='bilinear', align_corners=None).squeeze(0)
             depth_hypos = calDepthHypo(self.args, depth_up, ref_in_ms[:, level], src_in_ms[:, :, level], ref_ex, src_ex,
                                        depth_min, depth_max, level)
-            cost_volume = proj_cost(self.args, ref_pyr[level], src_pyrs, level, ref_in_ms[:, level],
-                                    src_in_ms[:, :, level], ref_ex, src_ex, depth_hypos, dt, as_c8=True)
+            if fast:
+                rt = ops.compose_proj_ke(ref_in_ms[:, level], src_in_ms[:, :nsrc, level], ref_ex, src_ex[:, :nsrc], 1.0)
+                cost_volume = ops.warp_variance_maps(maps[level], rt, depth_hypos, dt, ALIGN_CORNERS, True)
+            else:
+                cost_volume = proj_cost(self.args, ref_pyr[level], src_pyrs, level, ref_in_ms[:, level],
+                                        src_in_ms[:, :, level], ref_ex, src_ex, depth_hypos, dt, as_c8=True)
             cost_reg2 = self.cost_reg_refine(cost_volume)
             depth, _, conf, _ = ops.soft_argmin(cost_reg2, depth_hypos)
             depth_est_list.append(depth)

@@ -285,13 +285,16 @@ def pack_conv2d_weight(weight: Tensor) -> Tensor:
 
 
 def conv2d_raw(x: Tensor, g: Tensor, cout: int, ksize: int, stride: int, scale: Optional[Tensor], shift: Optional[Tensor],
-               relu: bool, out_padded: bool = False, tile_cache: Optional[dict] = None) -> Tensor:
-    """y = [relu](conv2d(x) * scale + shift) over a C8 image stack [Cin/8, M, H, W, 8] (16-bit storage, tcgen05 kernel).
+               relu, out_padded: bool = False, tile_cache: Optional[dict] = None) -> Tensor:
+    """y = act(conv2d(x) * scale + shift) over a C8 image stack [Cin/8, M, H, W, 8] (16-bit storage, tcgen05 kernel);
+    relu: False / True, or a float slope for LeakyReLU.
     Returns the stack [Cout/8, M, Ho, Wo, 8], or with out_padded the zero-bordered image-major maps [M, Cout/8, Ho+3, Wo+2, 8]."""
     x = x.contiguous()
     cib, m, h, w, _ = x.shape
     ho, wo = (h, w) if stride == 1 else (h // 2, w // 2)
-    d = Conv2dDesc(m, cib * 8, cout, h, w, ho, wo, ksize, stride, dtype_code(x.dtype), int(relu), int(out_padded), 0)
+    leaky = isinstance(relu, float)
+    d = Conv2dDesc(m, cib * 8, cout, h, w, ho, wo, ksize, stride, dtype_code(x.dtype), 2 if leaky else int(bool(relu)), int(out_padded), 0,
+                   float(relu) if leaky else 0.0)
     if out_padded:
         y = torch.zeros(m, cout // 8, ho + 3, wo + 2, 8, dtype=x.dtype, device=x.device)
     else:

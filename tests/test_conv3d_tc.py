@@ -103,6 +103,12 @@ CASES_2D = [
     (32, 32, 3, 1, (5, 32, 40), True, False),     # feature: bias only, zero-bordered image-major output
     (32, 32, 3, 1, (10, 128, 160), True, False),  # headline feature-map size, two items x 5 views
     (3, 8, 3, 1, (5, 128, 160), False, True),
+    # FeaturePyramid of CVP-MVSNet: bias + LeakyReLU(0.1); 64 output channels run the unfolded 9-entry program
+    (3, 64, 3, 1, (2, 24, 40), False, 0.1),
+    (64, 64, 3, 1, (3, 37, 61), False, 0.1),
+    (64, 32, 3, 1, (2, 32, 30), False, 0.1),
+    (32, 16, 3, 1, (2, 19, 33), False, 0.1),
+    (16, 16, 3, 1, (5, 64, 80), True, 0.1),
 ]
 
 
@@ -118,7 +124,8 @@ def test_tc_conv2d_matches_aten(gpu, cin, cout, k, stride, shape, padded, relu, 
     cinp = (cin + 7) // 8 * 8
     x = torch.randn(m, cin, h, w, device=dev).to(dtype).float()
     wt = (0.2 * torch.randn(cout, cin, k, k, device=dev)).to(dtype).float()
-    scale = (torch.rand(cout, device=dev) + 0.5) if relu else None
+    leaky = isinstance(relu, float)
+    scale = (torch.rand(cout, device=dev) + 0.5) if (relu and not leaky) else None
     shift = torch.randn(cout, device=dev)
     xs = torch.zeros(cinp // 8, m, h, w, 8, device=dev, dtype=dtype)           # C8 image stack [Cin/8][M][H][W][8]
     xp = torch.zeros(m, cinp, h, w, device=dev)
@@ -127,8 +134,10 @@ def test_tc_conv2d_matches_aten(gpu, cin, cout, k, stride, shape, padded, relu, 
     y = ops.conv2d_raw(xs, ops.pack_conv2d_weight(wt), cout, k, stride, scale, shift, relu, out_padded=padded)
     torch.cuda.synchronize()
     want = F.conv2d(x, wt, None, stride, k // 2)
-    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) if relu else want + shift.view(1, -1, 1, 1)
-    if relu:
+    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) if scale is not None else want + shift.view(1, -1, 1, 1)
+    if leaky:
+        want = F.leaky_relu(want, relu)
+    elif relu:
         want = F.relu(want)
     ho, wo = want.shape[2:]
     if padded:
@@ -164,3 +173,23 @@ def test_feature_net_on_tcgen05(gpu, oracle, dtype, tol):
     assert maps.shape == (3, 2, 4, 16 + 3, 24 + 2, 8)
     got = maps.float()[:, :, :, 1:17, 1:25].permute(0, 1, 2, 5, 3, 4).reshape(3, 2, 32, 16, 24).cpu()
     assert rel_err(got, want) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 8e-2)])
+def test_feature_pyramid_on_tcgen05(gpu, oracle, dtype, tol):
+    """FeaturePyramid.forward_maps (9 launches per level) against the oracle's fp32 pyramid (jdacs-ms/models/network.py:16-41)."""
+    from types import SimpleNamespace
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    torch.manual_seed(1)
+    model = CVPMVSNet(SimpleNamespace(nsrc=2, nscale=3, mode="test")).eval()
+    imgs = torch.randn(2, 3, 3, 64, 96)
+    sd = {k[len("featurePyramid."):]: v.detach().clone() for k, v in model.state_dict().items() if k.startswith("featurePyramid.")}
+    with torch.no_grad():
+        want = [oracle.feature_pyramid(imgs[:, v], sd, 3) for v in range(3)]           # [view][level] -> [B,16,h,w]
+        maps = model.to(gpu.device).featurePyramid.forward_maps(imgs.to(gpu.device), 3, dtype)
+    for level, m in enumerate(maps):
+        h, w = 64 >> level, 96 >> level
+        assert m.shape == (3, 2, 2, h + 3, w + 2, 8)
+        got = m.float()[:, :, :, 1:h + 1, 1:w + 1].permute(0, 1, 2, 5, 3, 4).reshape(3, 2, 16, h, w).cpu()
+        ref = torch.stack([want[v][level] for v in range(3)], 0)
+        assert rel_err(got, ref) < tol, (level, rel_err(got, ref))

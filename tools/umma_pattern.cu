@@ -44,14 +44,20 @@ __global__ void __launch_bounds__(160, 1) bench(int mode, int nent, int iters, l
         const uint32_t d = tmem + warp * 128;
         long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-            if (mode & 2) { if (mode & 32) { if (lane == 0) mbar_wait(bar + 4, 1); __syncwarp(); } else mbar_wait(bar + 4, 1); }     // fresh barrier: parity-1 wait passes at once
-            if (mode & 4) { if (mode & 32) { if (lane == 0) mbar_wait(bar + 5, 1); __syncwarp(); } else mbar_wait(bar + 5, 1); }
+            if (!(mode & 64)) {
+                if (mode & 2) { if (mode & 32) { if (lane == 0) mbar_wait(bar + 4, 1); __syncwarp(); } else mbar_wait(bar + 4, 1); }     // fresh barrier: parity-1 wait passes at once
+                if (mode & 4) { if (mode & 32) { if (lane == 0) mbar_wait(bar + 5, 1); __syncwarp(); } else mbar_wait(bar + 5, 1); }
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int e = 0; e < nent; ++e) {
                 const uint64_t a = a0 + (uint64_t)(e * 32), b = b0 + (uint64_t)(e * 192);
                 if (mode & 16) mma_elect(d, a, b, id96, 1u);
                 else if (e == 0) { mma_elect(d, a, b, id64, 1u); mma_elect(d + 64, a, b + 128, id32, 0u); }
                 else mma_elect(d, a, b, id96, 1u);
+            }
+            if (mode & 64) {   // 64: the NEXT step's waits are issued behind this step's MMAs, before its commits
+                if (mode & 2) mbar_wait(bar + 4, 1);
+                if (mode & 4) mbar_wait(bar + 5, 1);
             }
             if (mode & 1) commit_elect(bar + warp);      // nobody waits on these: phases just flip
             if (mode & 8) commit_elect(bar + warp);
@@ -72,9 +78,9 @@ int main() {
     cudaMallocManaged(&out, 64);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 2000;
-    printf("mode nent : cycles per step (issuer warp 0)   [mode bits: 1 commit, 2 wait, 4 wait2, 8 commit2, 16 unsplit N=96, 32 lane-0 waits]\n");
+    printf("mode nent : cycles per step (issuer warp 0)   [mode bits: 1 commit, 2 wait, 4 wait2, 8 commit2, 16 unsplit N=96, 32 lane-0 waits, 64 waits after the MMAs]\n");
     for (int nent : {2, 6})
-        for (int mode : {0, 16, 1, 17, 3, 19, 15, 31, 47, 63}) {
+        for (int mode : {0, 16, 1, 3, 15, 31, 79, 95, 9}) {
             bench<<<148, 160, 200 * 1024>>>(mode, nent, iters, out);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
