@@ -1,7 +1,7 @@
 """BASELINE.json configs[4]: cost-volume sweep D in {48,96,192,256} x image sizes up to 1600x1200 (N=5, C=32, fp16):
 the fused warp+variance kernel (algorithmic GB/s vs the measured HBM peak) and conv0 of CostRegNet, the layer that consumes the
 volume (TFLOP/s vs the measured tensor peak, and its own GB/s).  CUDA events, L2 flushed before every timed launch.
-    python tools_cost_volume_sweep.py > profiles/r01_cost_volume_sweep.txt        (on a B200)"""
+    python tools/cost_volume_sweep.py > profiles/r01_cost_volume_sweep.txt        (on a B200)"""
 import json
 import os
 import statistics
@@ -9,7 +9,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ssmvs_b200  # noqa: E402
 from ssmvs_b200 import ops, synth  # noqa: E402

@@ -5,7 +5,7 @@ from types import SimpleNamespace
 
 import torch
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ssmvs_b200  # noqa: E402
 from ssmvs_b200 import synth  # noqa: E402
