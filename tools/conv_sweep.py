@@ -3,7 +3,7 @@ import os
 import sys
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ssmvs_b200
 from ssmvs_b200 import ops
 
