@@ -236,3 +236,27 @@ def test_config4_train_step_full_size(gpu):
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
     opt.step()
     assert not torch.equal(before, model.cost_regularization.conv0.conv.weight.detach())
+
+
+def test_streamed_forward_pipeline_matches_direct_calls(gpu):
+    """graph.StreamedForward (two captured graphs, uploads one batch ahead, one forward in flight behind the result handed out):
+    every batch's host result equals the direct module call on that batch, in order, for an odd and an even number of batches."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.graph import StreamedForward
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False, volume_dtype=torch.float16).eval().to(gpu.device)
+    with torch.no_grad():
+        model.cost_regularization.prob.weight.mul_(64.0)
+    batches = []
+    for seed in range(5):
+        inp = synth.mvsnet_inputs(2, 3, 64, 96, 16, seed=seed)
+        batches.append([inp[k].pin_memory() for k in ("imgs", "proj_matrices", "depth_values")])
+    with torch.no_grad():
+        want = [model(*[t.to(gpu.device) for t in b]) for b in batches]
+        pipe = StreamedForward(lambda i, pm, dv: model(i, pm, dv), [t.to(gpu.device) for t in batches[0]], ("depth", "photometric_confidence"))
+        for n in (5, 2, 1):
+            got = [{k: v.clone() for k, v in out.items()} for out in pipe.run(batches[:n])]
+            assert len(got) == n
+            for g, w in zip(got, want):
+                assert torch.equal(g["depth"], w["depth"].cpu()) and torch.equal(g["photometric_confidence"], w["photometric_confidence"].cpu())
