@@ -81,18 +81,31 @@ softargmin_fwd_smem_kernel(const float* __restrict__ cost, const float* __restri
 #pragma unroll 8
     for (int d = d0; d < d1; ++d) xs[d * 32 + c] = expf(xs[d * 32 + c] - mx);
     __syncthreads();
-    if (qd != 0 || !live) return;
-    float sum = 0.f;
+    // sum of exponentials: sequential in d (one warp), then the normalisation in parallel (an IEEE divide per element is the
+    // expensive part and is order-free), then the two expectations sequentially again
+    if (qd == 0) {
+        float sum = 0.f;
 #pragma unroll 8
-    for (int d = 0; d < D; ++d) sum += xs[d * 32 + c];
+        for (int d = 0; d < D; ++d) sum += xs[d * 32 + c];
+        red[0][c] = sum;
+    }
+    __syncthreads();
+    const float sum = red[0][c];
+#pragma unroll 8
+    for (int d = d0; d < d1; ++d) {
+        const float pd = xs[d * 32 + c] / sum;
+        xs[d * 32 + c] = pd;
+        if (prob_out && live) prob_out[((int64_t)b * D + d) * HW + p] = pd;
+    }
+    __syncthreads();
+    if (qd != 0 || !live) return;
     float e_depth = 0.f, e_index = 0.f;
 #pragma unroll 8
     for (int d = 0; d < D; ++d) {
-        const float pd = xs[d * 32 + c] / sum;
+        const float pd = xs[d * 32 + c];
         const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
         e_depth += pd * dv;
         e_index += pd * (float)d;
-        if (prob_out) prob_out[((int64_t)b * D + d) * HW + p] = pd;
     }
     if (depth_out) depth_out[i] = e_depth;
     if (index_out || conf_out) {
@@ -102,7 +115,7 @@ softargmin_fwd_smem_kernel(const float* __restrict__ cost, const float* __restri
             float s = 0.f;
             for (int k = -1; k <= 2; ++k) {
                 const long long d = idx + k;
-                if (d >= 0 && d < D) s += xs[(int)d * 32 + c] / sum;
+                if (d >= 0 && d < D) s += xs[(int)d * 32 + c];
             }
             conf_out[i] = 4.f * (s / 4.f);
         }
