@@ -255,6 +255,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the plane-sweep path has no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = parallel.bind_to_gpu_numa(local) if world > 1 else False    # before any pinned allocation
     ssmvs_b200._lib.bind()
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
     elem = 4 if dtype == torch.float32 else 2
@@ -418,7 +419,7 @@ def main():
                 "config": {"workload": WORKLOAD, "global_batch": world * PB, "per_gpu_batch": PB, "parallelism": "dp%d (items sharded, no collective)" % world,
                            "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
                            "launch": "python" if graphed is None else "cuda-graph replay (%d C-ABI launches per step, %d stream lane(s))" % (graphed.launches_per_replay, graphed.lanes),
-                           "wall_s_incl_flush": wall},
+                           "wall_s_incl_flush": wall, "numa_bound": numa_bound},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "depth-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps,

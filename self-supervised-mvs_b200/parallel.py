@@ -30,6 +30,30 @@ def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Pin this process to the CPU cores closest to its GPU (NVML's affinity mask) so that pinned host buffers allocated
+    afterwards are first-touched on that NUMA node: with 8 ranks uploading ~30 GB/s each, remote-node pinned memory halves
+    the host->device rate.  Best effort: returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def shard_items(n_items: int, rank: int, world: int) -> range:
     """Contiguous, balanced slice of `n_items` batch items owned by `rank` (first ranks take the remainder)."""
     base, rem = divmod(n_items, world)
