@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16")
-    ap.add_argument("--batch", type=int, default=4, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU)")
+    ap.add_argument("--batch", type=int, default=8, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU; measured 1 / 2 / 4 / 8 items: 4.4 / 5.3 / 6.3 / 6.4 G samples/s)")
     ap.add_argument("--lanes", type=int, default=1, help="item groups captured on separate streams inside the CUDA graph (GraphedForward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")

@@ -809,7 +809,8 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_warp_var_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
             }
-            const int DC = 16;
+            const char* dc_env = getenv("MVS_WARP_DC");      // tuning knob: planes per block (window size grows with it)
+            const int DC = (dc_env && atoi(dc_env) >= 4 && atoi(dc_env) <= 64) ? atoi(dc_env) : 16;
             const int tiles = (int)(mvs_cdiv(H, kTileH) * mvs_cdiv(W, kTileW));
             MVS_REQUIRE((int64_t)B * mvs_cdiv(D, DC) <= 65535, MVS_E_SHAPE, "mvs_warp_var_fwd: B*D/16 too large for the launch grid");
             const dim3 gridt((unsigned)tiles, (unsigned)(B * mvs_cdiv(D, DC)));
