@@ -46,3 +46,14 @@ def test_shard_items_covers_everything():
         for w in (1, 2, 4, 8):
             got = [i for r in range(w) for i in parallel.shard_items(n, r, w)]
             assert got == list(range(n))
+
+
+def test_numa_binding_is_best_effort():
+    """Without NVML / a GPU the binding helper must change nothing and say so."""
+    import os
+    from ssmvs_b200 import parallel
+    before = os.sched_getaffinity(0)
+    ok = parallel.bind_to_gpu_numa(0)
+    assert isinstance(ok, bool)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
