@@ -126,6 +126,24 @@ def test_pack_c8_padded_layouts(be):
         assert got.shape == (3, 2, 8, 11, 8) and torch.equal(got.cpu(), want)
 
 
+def test_pack_images_c8_and_conv2d_weight(be):
+    """Image stack for the 2-D feature layers: [B,N,3,H,W] -> [1, N*B, H, W, 8], image m = v*B + b, channels 3..7 zero; and
+    the gather form of a Conv2d weight (tap = kh*k + kw, zero padded to 8 channels)."""
+    ops = _ops()
+    torch.manual_seed(6)
+    imgs = torch.randn(2, 3, 3, 5, 7)
+    st = ops.pack_images_c8(be.to(imgs), torch.float32).cpu()
+    assert st.shape == (1, 6, 5, 7, 8)
+    for v in range(3):
+        for b in range(2):
+            assert torch.equal(st[0, v * 2 + b, :, :, :3], imgs[b, v].permute(1, 2, 0))
+    assert torch.count_nonzero(st[..., 3:]) == 0
+    w = torch.randn(16, 3, 5, 5)
+    g = ops.pack_conv2d_weight(be.to(w)).cpu()
+    assert g.shape == (25, 8, 16)
+    assert torch.equal(g[7, :3, :], w[:, :, 1, 2].t()) and torch.count_nonzero(g[:, 3:, :]) == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("channels,nsrc,ref_sq,per_pixel", [(32, 4, False, False), (16, 2, True, True), (32, 3, False, True),
