@@ -69,3 +69,22 @@ def test_error_codes_and_messages(emu):
         ops.conv3d_raw(x, g, 8, stride=2)                          # odd extent under stride 2
     with pytest.raises(RuntimeError, match="emulation"):
         ops.conv3d_raw(ops.pack_c8(torch.zeros(1, 8, 4, 4, 4)), g, 8, algo=2)
+
+
+def test_new_entry_points_validate_before_touching_the_device():
+    """Argument checks of the 2-D convolution / padded packing / image packing entry points run on a box without a GPU
+    (they return before any CUDA call): null pointers, inconsistent extents, unknown layouts."""
+    import ssmvs_b200
+    from ssmvs_b200._lib import Conv2dDesc
+    lib = ssmvs_b200._lib.bind()
+    d = Conv2dDesc(2, 8, 8, 16, 16, 16, 16, 3, 1, 1, 1, 0, 0, 0.0)
+    assert lib.mvs_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1 and b"null" in lib.mvs_last_error()
+    d.Hout = 8                                                      # stride 1 must keep the extent
+    assert lib.mvs_conv2d_fwd(ctypes.byref(d), 1, 1, None, None, 1, None, None) == -2 and b"extent" in lib.mvs_last_error()
+    assert lib.mvs_pack_c8_padded(None, None, 1, 8, 4, 4, 0, 0, None) == -1
+    assert lib.mvs_pack_c8_padded(1, 1, 1, 7, 4, 4, 0, 0, None) == -2 and b"multiple of 8" in lib.mvs_last_error()
+    assert lib.mvs_pack_c8_padded(1, 1, 1, 8, 4, 4, 5, 0, None) == -1 and b"src_layout" in lib.mvs_last_error()
+    assert lib.mvs_pack_images_c8(None, None, 1, 1, 4, 4, 1, None) == -1
+    # unsupported 2-D layer shapes are reported, not silently computed some other way
+    bad = Conv2dDesc(2, 8, 8, 16, 16, 16, 16, 7, 1, 1, 1, 0, 0, 0.0)
+    assert lib.mvs_conv2d_workspace_bytes(ctypes.byref(bad)) == 0
