@@ -368,7 +368,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
     if ((int)threadIdx.x < p.nentries) {
         const Entry en = p.prog[threadIdx.x];
         etab[threadIdx.x] = make_uint4((uint32_t)en.sub * p.sub_bytes + (uint32_t)((int)en.row_shift * 16),
-                                       (en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16, (uint32_t)en.slot_off, (uint32_t)en.first);
+                                       (en.lbo_rows ? (uint32_t)en.lbo_rows : (p.chunk_bytes >> 4)) << 16, (uint32_t)en.slot_off, (uint32_t)en.first | ((uint32_t)en.group << 8));
     }
     if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -526,10 +526,11 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                         }
                         tc_fence_after();
                         if (m == 0 && lane == 0) TRACE(2, I);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.nM + m) * p.N);
+                        const uint32_t d_tmem0 = tmem_base + (uint32_t)((buf * p.groups * p.nM + m) * p.N), d_group = (uint32_t)(p.nM * p.N);
                         uint32_t b_ent = (b_addr >> 4) | b_lbo;
                         for (int e = 0; e < nent; ++e, b_ent += btile16) {
-                            const uint4 en = etab[e];                      // x = A byte offset, y = LBO field, z = slot, w = first
+                            const uint4 en = etab[e];                      // x = A byte offset, y = LBO field, z = slot, w = first | group << 8
+                            const uint32_t d_tmem = d_tmem0 + (en.w >> 8) * d_group;
                             uint32_t b_lo = b_ent;
                             if (!p.b_resident) {
                                 mbar_wait(b_full + bst, (uint32_t)bph);
@@ -538,7 +539,7 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                             }
                             const uint32_t sa = en.z == 0 ? sa0 : (en.z == 1 ? sa1 : sa2);
                             uint32_t a_lo = ((sa + en.x) >> 4) | en.y;
-                            uint32_t acc = en.w ? 0u : 1u;
+                            uint32_t acc = (en.w & 1u) ? 0u : 1u;
                             for (int ks = 0; ks < ksteps; ++ks, a_lo += a_kstep, b_lo += b_kstep, acc = 1u)
                                 umma_f16_elect(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, acc);
                             if (!p.b_resident) { umma_commit_elect(b_empty + bst); if (++bst == p.bstages) { bst = 0; bph ^= 1; } }
@@ -619,12 +620,15 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
                 mbar_wait(acc_full + buf, (I >> 1) & 1);
                 if (warp == 6 && lane == 0) TRACE(4, I);
                 tc_fence_after();
-                {
+                for (int g = 0; g < p.groups; ++g) {
+                    // accumulator group g = image plane g of a two-plane 2-D step (output plane 2 (d0 + i) + g); one group otherwise
+                    const int od = p.groups == 1 ? d0 + i : p.groups * (d0 + i) + g;
+                    if (p.groups > 1 && od >= p.Do) continue;            // odd image count: the last step's second plane is padding
                     const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
                     RowAt ra[2];
                     for (int u = 0; u < 2; ++u) {
                         const int m = mpar + kMStride * u;
-                        ra[u] = row_at(u, tq + (uint32_t)((buf * p.nM + m) * p.N));
+                        ra[u] = row_at(u, tq + (uint32_t)(((buf * p.groups + g) * p.nM + m) * p.N));
                     }
                     const bool two = kMStride == 2 && mpar + 2 < p.nM;
                     if (p.mode == MODE_T2) {
@@ -636,8 +640,8 @@ conv3d_tc_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant_
 #ifndef MVS_DIAG_NO_EPI
                     else if (mpar < p.nM) {
                         const RowAt r1[1] = {ra[0]};
-                        if (kwfold) { if (two) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, d0 + i, CoB, HWo); else epilogue_rows<T, 1, true, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
-                        else { if (two) epilogue_rows<T, 1, false, 2>(p, aff, ra, b, d0 + i, CoB, HWo); else epilogue_rows<T, 1, false, 1>(p, aff, r1, b, d0 + i, CoB, HWo); }
+                        if (kwfold) { if (two) epilogue_rows<T, 1, true, 2>(p, aff, ra, b, od, CoB, HWo); else epilogue_rows<T, 1, true, 1>(p, aff, r1, b, od, CoB, HWo); }
+                        else { if (two) epilogue_rows<T, 1, false, 2>(p, aff, ra, b, od, CoB, HWo); else epilogue_rows<T, 1, false, 1>(p, aff, r1, b, od, CoB, HWo); }
                     }
 #endif
                 }
@@ -720,15 +724,24 @@ bool kdfold_of(const Spec* d) {
 bool kwfold_of(const Spec* d) { return mode_of(d) == MODE_S1 && !(d->two_d && 3 * cop_of(d) > 128); }
 int nblk_of(const Spec* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : (kwfold_of(d) ? 3 : 1)) : (mode_of(d) == MODE_T2 ? 8 : 1); }
 int n_of(const Spec* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
+// Thin 2-D layers (N <= 32: the 8-channel full-resolution layers of FeatureNet) take TWO image planes per step: a step costs
+// ~1 k cycles of barrier waits / commits and ~1 k of epilogue chain whatever it computes, and 2 x 2 x 4 M-tiles x 32 columns
+// still fit TMEM.  The 5x5 program only qualifies with Cin = 8 (13 paired entries per plane; 2 x 25 would not fit the table).
+int planes_per_step(const Spec* d) {
+    const char* e = getenv("MVS_TC_PLANES");        // test / tuning knob: 1 disables
+    if (e && atoi(e) == 1) return 1;
+    return (d->two_d && n_of(d) <= 32 && (d->ksize == 3 || d->Cin == 8)) ? 2 : 1;
+}
 
 // A "fold tap": one A view (slot, sub-plane, row shift) and, per column block, the filter tap it multiplies (-1 = none).
-struct FoldTap { int slot, sub, shift, tap[12]; };
+struct FoldTap { int slot, sub, shift, grp, tap[12]; };   // grp: accumulator group (image plane of a two-plane 2-D step)
 
 // Build the entry list + weight-tile sources.  Returns the number of entries.
 int build_program(const Spec* d, TcParams& p, TileSrc& src) {
     const int mode = mode_of(d);
     memset(&src, -1, sizeof(src));
-    FoldTap ft[27];
+    FoldTap ft[54];
+    memset(ft, 0, sizeof(ft));
     int nft = 0;
     if (d->two_d && mode == MODE_S1 && !kwfold_of(d)) {
         // 3x3 over one image plane, one entry per tap: row shift kh * 32 + kw from the tile origin (o - 1)
@@ -796,11 +809,18 @@ int build_program(const Spec* d, TcParams& p, TileSrc& src) {
                     }
                 }
     }
+    if (planes_per_step(d) == 2) {
+        // two image planes per step: the same taps again on the second live slot, accumulating into the second group
+        for (int i = 0; i < nft; ++i) { ft[nft + i] = ft[i]; ft[nft + i].slot = 1; ft[nft + i].grp = 1; }
+        nft *= 2;
+    }
     int ne = 0;
+    bool seen[2] = {false, false};
     auto add = [&](const FoldTap& t, int shift, int lbo_rows) {
         Entry& e = p.prog[ne];
         e.row_shift = (int16_t)shift; e.lbo_rows = (uint16_t)lbo_rows; e.slot_off = (uint8_t)t.slot; e.sub = (uint8_t)t.sub;
-        e.group = 0; e.first = ne == 0 ? 1 : 0;
+        e.group = (uint8_t)t.grp; e.first = seen[t.grp] ? 0 : 1;
+        seen[t.grp] = true;
         return ne++;
     };
     if (d->Cin != 8) {
@@ -811,7 +831,7 @@ int build_program(const Spec* d, TcParams& p, TileSrc& src) {
         return ne;
     }
     // Cin = 8: two fold taps of the same (slot, sub-plane) share one K = 16 step; LBO = their row distance
-    bool used[27] = {false};
+    bool used[54] = {false};
     for (int a = 0; a < nft; ++a) {
         if (used[a]) continue;
         used[a] = true;
@@ -848,12 +868,14 @@ bool make_plan(const Spec* d, Plan& pl) {
     if (p.mode == MODE_T2) { p.Dt = p.Di; p.Ht = p.Hi; p.Wt = p.Wi; } else { p.Dt = p.Do; p.Ht = p.Ho; p.Wt = p.Wo; }
     p.relu = d->relu; p.is_bf16 = d->dtype_in == MVS_BF16;
     p.slope = d->slope; p.kwfold = kwfold_of(d) ? 1 : 0;
+    const int npl = planes_per_step(d);                         // 2-D: image planes per step (1 or 2)
     p.nsub = p.mode == MODE_S2 ? 4 : 1;
-    p.sps = d->two_d ? 1 : (p.mode == MODE_S2 ? 2 : 1);
-    p.live = d->two_d ? 1 : (p.mode == MODE_T2 ? 2 : 3);
-    p.d_mul = (!d->two_d && p.mode == MODE_S2) ? 2 : 1;
+    p.sps = d->two_d ? npl : (p.mode == MODE_S2 ? 2 : 1);
+    p.live = d->two_d ? npl : (p.mode == MODE_T2 ? 2 : 3);
+    p.d_mul = d->two_d ? npl : (p.mode == MODE_S2 ? 2 : 1);
     p.d_org = (d->two_d || p.mode == MODE_T2) ? 0 : -1;
-    p.groups = 1;
+    p.groups = npl;
+    if (npl == 2) p.Dt = (p.Do + 1) / 2;                        // the tiles walk steps of two image planes
     p.kdfold = kdfold_of(d) ? 1 : 0;
     // output addressing (voxels): C8 volume [B][CoB][Do][Ho][Wo], plain [B][Do][Ho][Wo] for one channel, or (out_pad) the
     // zero-bordered image-major C8P maps [Do = image][CoB][Ho + 3][Wo + 2] with pixel (0, 0) at row 1, column 1
@@ -867,7 +889,7 @@ bool make_plan(const Spec* d, Plan& pl) {
         }
     }
     // ring depth = live slots + the slots of one step prefetched while the current step computes
-    p.stages = d->two_d ? 2 : (p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 4)));   // minimum; make_plan adds what fits
+    p.stages = d->two_d ? 2 * npl : (p.kdfold ? 3 : (p.mode == MODE_S1 ? 4 : (p.mode == MODE_T2 ? 3 : 4)));   // minimum; make_plan adds what fits
     p.nentries = build_program(d, p, pl.src);
     p.btile_bytes = (uint32_t)p.kchunks * p.N * 16;
     int max_reach = 0;   // furthest row an A descriptor touches beyond its 128-row window
@@ -974,7 +996,8 @@ static int64_t tc_workspace_bytes(const Spec* d) {
     if (!tc_supported(d)) return 0;
     const int kchunks = d->Cin == 8 ? 2 : d->Cin / 8;
     // upper bounds on the entry count (Cin = 8 pairs need fewer)
-    const int nentries = d->two_d ? (d->ksize == 3 ? (kwfold_of(d) ? 3 : 9) : 25) : (mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27));
+    const int nentries = d->two_d ? planes_per_step(d) * (d->ksize == 3 ? (kwfold_of(d) ? 3 : 9) : 25)
+                                  : (mode_of(d) == MODE_S1 ? 9 : (mode_of(d) == MODE_T2 ? 8 : 27));
     return (int64_t)nentries * kchunks * n_of(d) * 16;  // weight tiles [entry][kchunk][N][8] in the storage dtype
 }
 
