@@ -75,8 +75,10 @@ def test_new_entry_points_validate_before_touching_the_device():
     """Argument checks of the 2-D convolution / padded packing / image packing entry points run on a box without a GPU
     (they return before any CUDA call): null pointers, inconsistent extents, unknown layouts."""
     import ssmvs_b200
-    from ssmvs_b200._lib import Conv2dDesc
-    lib = ssmvs_b200._lib.bind()
+    from ssmvs_b200._lib import Conv2dDesc, DEFAULT_PATH, _SIGS
+    lib = ctypes.CDLL(DEFAULT_PATH)          # a private handle: the session-wide binding (emulation for the CPU tests) stays as it is
+    for name in ("mvs_conv2d_fwd", "mvs_conv2d_workspace_bytes", "mvs_pack_c8_padded", "mvs_pack_images_c8", "mvs_last_error"):
+        getattr(lib, name).argtypes, getattr(lib, name).restype = _SIGS[name]
     d = Conv2dDesc(2, 8, 8, 16, 16, 16, 16, 3, 1, 1, 1, 0, 0, 0.0)
     assert lib.mvs_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1 and b"null" in lib.mvs_last_error()
     d.Hout = 8                                                      # stride 1 must keep the extent
