@@ -57,3 +57,21 @@ def test_numa_binding_is_best_effort():
     assert isinstance(ok, bool)
     if not ok:
         assert os.sched_getaffinity(0) == before
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference` launched the way the driver launches it for N > 1: rank 0 alone runs the CPU path and prints
+    ONE JSON line with the contract's keys, the other rank exits 0 without work (no process group is created)."""
+    import json
+    import subprocess
+    env = dict(os.environ, MVS_CPU_THREADS="4", OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "depth-samples/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 4
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
