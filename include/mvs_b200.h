@@ -39,6 +39,11 @@ int mvs_version(void);
 const char* mvs_last_error(void);
 /* 1 when this library is the host-emulation build used by the CPU unit tests (tests/emu), else 0. */
 int mvs_is_emulation(void);
+/* Test / tuning knobs (kernel-variant selection for A/B parity tests and the tools/ sweeps).  The product path never needs this
+ * call and the library never reads the environment.  value < 0 restores the built-in default.  Names: warp_tma (0 = gather from
+ * global memory instead of TMA-staged windows), warp_dc, warp_tma_minb, warp_cpt, warp_minb, warp_dz, tc_kdfold (0 = off),
+ * tc_planes (1 = one image plane per step), tc_nm, tc_stages, tc_nseg. */
+int mvs_set_knob(const char* name, int value);
 
 /* ---- layout ------------------------------------------------------------------------------------------- */
 /* fp32 [B][C][S] (S = H*W or D*H*W) -> C8 [B][C/8][S][8] in `dtype`.  C % 8 == 0. */
@@ -46,7 +51,9 @@ int mvs_pack_c8(const float* src, void* dst, int B, int C, int64_t S, int dtype,
 /* channels-last [B][S][C] in `dtype` (the layout the library 2-D feature extractor emits) -> C8 [B][C/8][S][8], same dtype */
 int mvs_nhwc_to_c8(const void* src, void* dst, int B, int C, int64_t S, int dtype, void* stream);
 /* Zero-bordered maps "C8P" for the plane-sweep gather: dst [M][C/8][H+3][W+2][8] in `dtype`, pixel (y,x) at row y+1, column x+1,
- * zeros elsewhere (so that grid_sample's zero padding becomes a plain load).  src_layout: 0 = fp32 [M][C][H][W],
+ * zeros elsewhere (so that grid_sample's zero padding becomes a plain load).  A C8P buffer handed to mvs_warp_var_fwd / _bwd must be
+ * followed by 16 readable bytes holding zeros (one vector): a sample beyond the bottom-right corner reads its zero-weight fourth
+ * tap at row H+2, column W+2, which for the last plane lies one vector past the array.  src_layout: 0 = fp32 [M][C][H][W],
  * 1 = channels-last `dtype` [M][H][W][C], 2 = C8 `dtype` [M][C/8][H][W][8]. */
 int mvs_pack_c8_padded(const void* src, void* dst, int M, int C, int H, int W, int src_layout, int dtype, void* stream);
 /* inverse of mvs_pack_c8 */

@@ -36,6 +36,7 @@ _SIGS = {
     "mvs_version": ([], _I),
     "mvs_last_error": ([], C.c_char_p),
     "mvs_is_emulation": ([], _I),
+    "mvs_set_knob": ([C.c_char_p, _I], _I),
     "mvs_pack_c8": ([_P, _P, _I, _I, _L, _I, _P], _I),
     "mvs_unpack_c8": ([_P, _P, _I, _I, _L, _I, _P], _I),
     "mvs_nhwc_to_c8": ([_P, _P, _I, _I, _L, _I, _P], _I),
@@ -71,11 +72,11 @@ launches = 0  # kernel-launching C-ABI calls made through this module (bench.py 
 
 
 def bind(path: Optional[str] = None) -> C.CDLL:
-    """Load the shared library at `path` (default: the in-tree build; MVS_B200_LIB overrides it for A/B builds of the same
-    sources) and type every export.  Raises if anything is missing."""
+    """Load the shared library at `path` (default, and the only thing the package itself ever loads: the in-tree build)
+    and type every export.  Raises if anything is missing."""
     global _lib, _emulation
     if path is None:
-        path = os.environ.get("MVS_B200_LIB", DEFAULT_PATH)
+        path = DEFAULT_PATH
     if not os.path.exists(path):
         raise RuntimeError(
             "libmvs_b200.so not found at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -86,6 +87,11 @@ def bind(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes, fn.restype = args, res
     _lib, _emulation = lib, bool(lib.mvs_is_emulation())
     return lib
+
+
+def set_knob(name: str, value: int = -1) -> None:
+    """Test / tuning knob of the bound library (mvs_set_knob); value < 0 restores the default."""
+    check(lib().mvs_set_knob(name.encode(), int(value)))
 
 
 def lib() -> C.CDLL:

@@ -716,8 +716,7 @@ int mode_of(const Spec* d) { return d->stride == 1 ? MODE_S1 : (d->transposed ? 
 int cop_of(const Spec* d) { return d->Cout == 1 ? 8 : d->Cout; }
 // kd-fold (stride 1, <= 8 output channels): the 9 (kd, kw) taps of one kh share an MMA; see the issuer.  MVS_TC_KDFOLD=0 disables.
 bool kdfold_of(const Spec* d) {
-    const char* e = getenv("MVS_TC_KDFOLD");
-    return !d->two_d && mode_of(d) == MODE_S1 && cop_of(d) == 8 && !(e && atoi(e) == 0);
+    return !d->two_d && mode_of(d) == MODE_S1 && cop_of(d) == 8 && mvs_knob(MVS_KNOB_TC_KDFOLD, 1) != 0;
 }
 // Stride-1 programs fold the 3 kw taps into N (3 column blocks) unless that makes the accumulators so wide that only one
 // M-tile fits in TMEM (2-D layers with 64 output channels): those run 9 entries with shifted A views, like the stride-2 program.
@@ -728,8 +727,7 @@ int n_of(const Spec* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 // ~1 k cycles of barrier waits / commits and ~1 k of epilogue chain whatever it computes, and 2 x 2 x 4 M-tiles x 32 columns
 // still fit TMEM.  The 5x5 program only qualifies with Cin = 8 (13 paired entries per plane; 2 x 25 would not fit the table).
 int planes_per_step(const Spec* d) {
-    const char* e = getenv("MVS_TC_PLANES");        // test / tuning knob: 1 disables
-    if (e && atoi(e) == 1) return 1;
+    if (mvs_knob(MVS_KNOB_TC_PLANES, 2) == 1) return 1;        // test / tuning knob: 1 disables
     return (d->two_d && n_of(d) <= 32 && (d->ksize == 3 || d->Cin == 8)) ? 2 : 1;
 }
 
@@ -899,8 +897,7 @@ bool make_plan(const Spec* d, Plan& pl) {
     // largest tile (nM M-tiles of 128 rows = 4 nM x 30 positions) whose slot ring fits beside the weights with 2 accumulator
     // sets in TMEM -- but small volumes take smaller tiles so that at least ~2 waves of CTAs exist
     bool found = false;
-    const char* force = getenv("MVS_TC_NM");          // test knob: force the M-tile count (when it fits)
-    const int forced = force ? atoi(force) : 0;
+    const int forced = mvs_knob(MVS_KNOB_TC_NM, 0);           // test knob: force the M-tile count (when it fits)
     for (int nM = 4; nM >= 1 && !found; --nM) {
         if ((p.kdfold ? nM * kAccRing * kPG : 2 * p.groups * nM * p.N) > 512) continue;
         if (forced >= 1 && forced <= 4 && nM > forced) continue;
@@ -922,8 +919,8 @@ bool make_plan(const Spec* d, Plan& pl) {
         // single slot in flight per SM (0.8 TB/s), so every byte of shared memory left over goes to more slots in flight.
         int stages_fit = (int)(((size_t)kSmemLimit - kTail - bbytes) / p.slot_bytes);
         if (stages_fit > kMaxStages) stages_fit = kMaxStages;
-        const char* fs = getenv("MVS_TC_STAGES");              // test / tuning knob
-        if (fs && atoi(fs) >= min_stages && atoi(fs) <= stages_fit) stages_fit = atoi(fs);
+        const int fs = mvs_knob(MVS_KNOB_TC_STAGES, 0);        // test / tuning knob
+        if (fs >= min_stages && fs <= stages_fit) stages_fit = fs;
         pl.stages_chosen = stages_fit;
         pl.smem = (size_t)stages_fit * p.slot_bytes + bbytes + kTail;
         p.nwt = (p.Wt + kTW - 1) / kTW;
@@ -944,7 +941,7 @@ bool make_plan(const Spec* d, Plan& pl) {
     // power-of-two split (16 segments, 768 items) leaves the 6th round 19 % full.
     const int min_ld = p.kdfold ? 4 : (d->two_d ? 1 : 2);
     const int extra = (d->two_d ? 0 : (p.mode == MODE_S1 ? 2 : 1)) + 1;
-    const char* fseg = getenv("MVS_TC_NSEG");               // test / tuning knob
+    const int fseg = mvs_knob(MVS_KNOB_TC_NSEG, 0);          // test / tuning knob
     int best_nseg = 1;
     int64_t best_cost = -1;
     for (int nseg = 1; nseg <= max(1, p.Dt / min_ld); ++nseg) {
@@ -954,7 +951,7 @@ bool make_plan(const Spec* d, Plan& pl) {
         const int64_t cost = rounds * (ld + extra);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nseg = nseg; }
     }
-    if (fseg && atoi(fseg) >= 1 && atoi(fseg) <= p.Dt) best_nseg = atoi(fseg);
+    if (fseg >= 1 && fseg <= p.Dt) best_nseg = fseg;
     p.LD = (p.Dt + best_nseg - 1) / best_nseg; p.nseg = (p.Dt + p.LD - 1) / p.LD;
     return tiles * p.nseg < (1ll << 31);
 }

@@ -17,6 +17,16 @@ int mvs_set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+int g_mvs_knobs[MVS_KNOB_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+static const char* const kKnobNames[MVS_KNOB_COUNT] = {"warp_tma", "warp_dc", "warp_tma_minb", "warp_cpt", "warp_minb", "warp_dz",
+                                                      "tc_kdfold", "tc_planes", "tc_nm", "tc_stages", "tc_nseg"};
+extern "C" int mvs_set_knob(const char* name, int value) {
+    MVS_REQUIRE(name, MVS_E_ARG, "mvs_set_knob: null name");
+    for (int i = 0; i < MVS_KNOB_COUNT; ++i)
+        if (strcmp(name, kKnobNames[i]) == 0) { g_mvs_knobs[i] = value < 0 ? -1 : value; return MVS_OK; }
+    return mvs_set_error(MVS_E_ARG, "mvs_set_knob: unknown knob '%s'", name);
+}
+
 extern "C" int mvs_version(void) { return MVS_B200_VERSION; }
 extern "C" const char* mvs_last_error(void) { return g_err; }
 extern "C" int mvs_is_emulation(void) {

@@ -63,6 +63,12 @@ static inline int mvs_check_launch(const char* name) {
 #endif
 #define MVS_REQUIRE(cond, code, ...) do { if (!(cond)) return mvs_set_error((code), __VA_ARGS__); } while (0)
 
+// ------------------------------------------------------------------ test / tuning knobs (mvs_set_knob; never read from the environment)
+enum { MVS_KNOB_WARP_TMA, MVS_KNOB_WARP_DC, MVS_KNOB_WARP_TMA_MINB, MVS_KNOB_WARP_CPT, MVS_KNOB_WARP_MINB, MVS_KNOB_WARP_DZ,
+       MVS_KNOB_TC_KDFOLD, MVS_KNOB_TC_PLANES, MVS_KNOB_TC_NM, MVS_KNOB_TC_STAGES, MVS_KNOB_TC_NSEG, MVS_KNOB_COUNT };
+extern int g_mvs_knobs[MVS_KNOB_COUNT];   // -1 = unset: the built-in (measured best) default applies
+static inline int mvs_knob(int id, int dflt) { return g_mvs_knobs[id] < 0 ? dflt : g_mvs_knobs[id]; }
+
 static inline unsigned mvs_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------ 8-wide channel-block vectors

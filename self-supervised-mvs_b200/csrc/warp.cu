@@ -790,8 +790,7 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     for (int s = 0; s < MVS_MAX_SRC; ++s) sp.p[s] = s < nsrc ? srcs[s] : nullptr;
     const int CB = C / 8, HW = H * W;
 #ifndef MVS_CPU_EMU
-    const char* tma_env = getenv("MVS_WARP_TMA");          // test / tuning knob, read per call: 0 = gather every source from global memory
-    const int tma_knob = tma_env ? atoi(tma_env) : 1;
+    const int tma_knob = mvs_knob(MVS_KNOB_WARP_TMA, 1);    // test knob (mvs_set_knob): 0 = gather every source from global memory
     if (dtype_in == dtype_out && dtype_in != MVS_F32 && pad && !per_pixel && (CB == 2 || CB == 4) && tma_knob) {
         // 16-bit storage, zero-bordered maps, plane hypotheses shared by the pixels of an item: TMA-staged source windows
         const size_t smem = (size_t)nsrc * CB * kBH * kBW * 16;
@@ -809,8 +808,8 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_warp_var_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
             }
-            const char* dc_env = getenv("MVS_WARP_DC");      // tuning knob: planes per block (window size grows with it)
-            const int DC = (dc_env && atoi(dc_env) >= 4 && atoi(dc_env) <= 64) ? atoi(dc_env) : 16;
+            const int dc_knob = mvs_knob(MVS_KNOB_WARP_DC, 16);   // tuning knob: planes per block (window size grows with it)
+            const int DC = (dc_knob >= 4 && dc_knob <= 64) ? dc_knob : 16;
             const int tiles = (int)(mvs_cdiv(H, kTileH) * mvs_cdiv(W, kTileW));
             MVS_REQUIRE((int64_t)B * mvs_cdiv(D, DC) <= 65535, MVS_E_SHAPE, "mvs_warp_var_fwd: B*D/16 too large for the launch grid");
             const dim3 gridt((unsigned)tiles, (unsigned)(B * mvs_cdiv(D, DC)));
@@ -819,7 +818,7 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
 #define MVS_WT_LAUNCH1(T, NS, RS, MB) do { cudaFuncSetAttribute(warp_var_fwd_tma_kernel<T, NS, RS, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
                 warp_var_fwd_tma_kernel<T, NS, RS, MB><<<gridt, nthr, smem, (cudaStream_t)stream>>>(MVS_WT_ARGS(T)); } while (0)
 #define MVS_WT_LAUNCH(T, NS, MB) do { if (ref_sq_in_sum) MVS_WT_LAUNCH1(T, NS, true, MB); else MVS_WT_LAUNCH1(T, NS, false, MB); } while (0)
-            static const int tma_minb = [] { const char* e = getenv("MVS_WARP_TMA_MINB"); return e ? atoi(e) : 2; }();
+            const int tma_minb = mvs_knob(MVS_KNOB_WARP_TMA_MINB, 2);
 #define MVS_WT_BY_NS(T) do { if (nsrc <= 2) MVS_WT_LAUNCH(T, 2, 3); else if (nsrc <= 4) { if (tma_minb == 3) MVS_WT_LAUNCH(T, 4, 3); else MVS_WT_LAUNCH(T, 4, 2); } \
                              else if (nsrc <= 6) MVS_WT_LAUNCH(T, 6, 1); else MVS_WT_LAUNCH(T, 8, 1); } while (0)
             if (dtype_in == MVS_F16) MVS_WT_BY_NS(__half); else MVS_WT_BY_NS(__nv_bfloat16);
@@ -833,10 +832,10 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
     if (dtype_in == dtype_out && dtype_in != MVS_F32 && pad && CB % 2 == 0) {
         // 16-bit storage, zero-bordered maps: packed-math kernel, all channels of a pixel in one thread when C % 32 == 0
         MVS_REQUIRE((int64_t)(H + 3) * (W + 2) * 16 < (1ll << 31), MVS_E_SHAPE, "mvs_warp_var_fwd: maps too large");
-        static const int cpt_knob = [] { const char* e = getenv("MVS_WARP_CPT"); return e ? atoi(e) : 2; }();     // tuning knobs; measured at N=5, C=32, D=192, 128x160 x4 items:
+        const int cpt_knob = mvs_knob(MVS_KNOB_WARP_CPT, 2);     // tuning knobs; measured at N=5, C=32, D=192, 128x160 x4 items:
         // CPT 2 / 4 blocks per SM 0.76 ms, CPT 4 / 3 blocks 0.91 ms (fewer instructions but too few warps to hide the gathers)
-        static const int minb4 = [] { const char* e = getenv("MVS_WARP_MINB"); return e ? atoi(e) : 3; }();
-        static const int dz_knob = [] { const char* e = getenv("MVS_WARP_DZ"); return e ? atoi(e) : 1; }();     // measured: 0 -> 0.795, 1 -> 0.759, 2 -> 0.768, 3 -> 0.813 ms
+        const int minb4 = mvs_knob(MVS_KNOB_WARP_MINB, 3);
+        const int dz_knob = mvs_knob(MVS_KNOB_WARP_DZ, 1);     // measured: 0 -> 0.795, 1 -> 0.759, 2 -> 0.768, 3 -> 0.813 ms
         const int cpt = (CB % 4 == 0 && cpt_knob == 4) ? 4 : 2;
         int dzl = dz_knob < 0 ? 0 : (dz_knob > 3 ? 3 : dz_knob);
         while (dzl > 0 && (1 << dzl) > D) --dzl;
@@ -863,7 +862,7 @@ extern "C" int mvs_warp_var_fwd(const void* ref, const void* const* srcs, int ns
         // 16-bit storage, plain C8 maps: packed-math kernel, 2 channel blocks per thread, source-count bound in {2,4,6,8}
         const int dperf = depth_chunk(D, HW, B, CB / 2);
         const dim3 gridf(mvs_cdiv(HW, 128), (unsigned)(B * (CB / 2) * ((D + dperf - 1) / dperf)));
-        static const int mb4 = [] { const char* e = getenv("MVS_WARP_MINB"); return e ? atoi(e) : 4; }();   // tuning knob: 4 blocks/SM (122 registers, no spills) measured faster than 5 (96, spills)
+        const int mb4 = mvs_knob(MVS_KNOB_WARP_MINB, 4);   // tuning knob: 4 blocks/SM (122 registers, no spills) measured faster than 5 (96, spills)
 #define MVS_WV_LAUNCH(T, NS, MB) warp_var_fwd_fast_kernel<T, 2, NS, MB><<<gridf, 128, 0, (cudaStream_t)stream>>>( \
             (const T*)ref, sp, nsrc, rt, depth, per_pixel, (T*)var, B, CB, D, H, W, dperf, align_corners, ref_sq_in_sum)
 #define MVS_WV_BY_NS(T) do { if (nsrc <= 2) MVS_WV_LAUNCH(T, 2, 5); else if (nsrc <= 4) { if (mb4 == 4) MVS_WV_LAUNCH(T, 4, 4); else MVS_WV_LAUNCH(T, 4, 5); } \

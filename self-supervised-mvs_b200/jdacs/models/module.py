@@ -53,6 +53,10 @@ class ConvBnReLU3D(nn.Module):
         self.bn = nn.BatchNorm3d(out_channels)
         self._cache = regnet.PackCache()
 
+    def train(self, mode=True):
+        self._cache.clear()     # everything derived from the weights is re-packed on the next eval forward
+        return super().train(mode)
+
     def forward(self, x, skip=None, algo=0):
         plain = x.dim() == 5
         y = regnet.conv_bn_relu(regnet.as_c8(x, torch.float32), self.conv, self.bn, self.training, self._cache, skip, algo)

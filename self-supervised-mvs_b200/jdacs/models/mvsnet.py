@@ -38,13 +38,18 @@ class FeatureNet(nn.Module):
         x = self.conv4(self.conv3(self.conv2(x)))
         return self.feature(self.conv6(self.conv5(x)))
 
+    def train(self, mode=True):
+        self.__dict__.pop("_folded", None)     # weights are about to change (or have): drop everything derived from them
+        return super().train(mode)
+
     def forward_folded(self, x, dtype):
         """Eval-mode fast path (library code): BatchNorm folded into the convolution weights, `dtype` channels-last
         activations, so each layer is one cuDNN tensor-core convolution + ReLU.  Same arithmetic as forward() in eval
         mode up to the rounding of `dtype`."""
         key = (dtype, x.device)
         sig = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
-        hit = getattr(self, "_folded", {}).get(key)
+        keep = regnet.owned(self)      # DataParallel replicas recompute (their tensors come and go): regnet.owned
+        hit = getattr(self, "_folded", {}).get(key) if keep else None
         if hit is None or hit[0] != sig:
             layers = []
             for blk in (self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6):
@@ -54,7 +59,8 @@ class FeatureNet(nn.Module):
             layers.append((self.feature.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last),
                            self.feature.bias.detach().to(dtype), self.feature.stride, self.feature.padding, False))
             hit = (sig, layers)
-            self.__dict__.setdefault("_folded", {})[key] = hit
+            if keep:
+                self.__dict__.setdefault("_folded", {})[key] = hit
         y = x.to(dtype).contiguous(memory_format=torch.channels_last)
         fused = getattr(torch, "cudnn_convolution_relu", None) if y.is_cuda else None
         for w, b, stride, pad, relu in hit[1]:
@@ -74,7 +80,8 @@ class FeatureNet(nn.Module):
         dev = imgs.device
         sig = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
         key = ("tc", dtype, dev)
-        hit = self.__dict__.setdefault("_folded", {}).get(key)
+        keep = regnet.owned(self)
+        hit = self.__dict__.setdefault("_folded", {}).get(key) if keep else None
         if hit is None or hit[0] != sig:
             layers = []
             for blk in (self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6):
@@ -84,7 +91,8 @@ class FeatureNet(nn.Module):
             layers.append((ops.pack_conv2d_weight(self.feature.weight), self.feature.out_channels, 3, 1, None,
                            self.feature.bias.detach().float().contiguous(), False))
             hit = (sig, layers, {})
-            self._folded[key] = hit
+            if keep:
+                self._folded[key] = hit
         b, n = imgs.shape[0], imgs.shape[1]
         x = ops.pack_images_c8(imgs, dtype)
         for i, (g, cout, k, stride, scale, shift, relu) in enumerate(hit[1]):
@@ -119,6 +127,10 @@ class CostRegNet(nn.Module):
         self._cache = regnet.PackCache()
         self.algo = 0           # 0 auto, 1 SIMT fp32, 2 tcgen05 (mvs_conv3d_desc.algo)
         self.act_dtype = None   # storage dtype of activations in eval mode; None = dtype of the input volume
+
+    def train(self, mode=True):
+        self._cache.clear()
+        return super().train(mode)
 
     def forward(self, x):
         plain = x.dim() == 5
@@ -182,6 +194,7 @@ class MVSNet(nn.Module):
         self.align_corners = align_corners
         self.feature_autocast = True   # eval + 16-bit volume, feature_tc off: FeatureNet as folded 16-bit library convolutions
         self.feature_tc = True         # eval + 16-bit volume: FeatureNet on the repo's tcgen05 convolution kernel
+        self.keep_index = False        # also return "depth_index" (the truncated expected plane index, mvsnet.py:149-150)
 
     def forward(self, imgs, proj_matrices, depth_values):
         assert imgs.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
@@ -214,11 +227,13 @@ class MVSNet(nn.Module):
         self.cost_regularization.act_dtype = None if self.training else dt
         cost_reg = self.cost_regularization(variance)
         # softmax + regression + confidence, fused (:142-151)
-        depth, _, photometric_confidence, _ = ops.soft_argmin(cost_reg, depth_values)
-        if not self.refine:
-            return {"depth": depth, "photometric_confidence": photometric_confidence}
-        refined_depth = self.refine_network(imgs[:, 0], depth)
-        return {"depth": refined_depth, "photometric_confidence": photometric_confidence}
+        depth, index, photometric_confidence, _ = ops.soft_argmin(cost_reg, depth_values)
+        if self.refine:
+            depth = self.refine_network(imgs[:, 0], depth)
+        out = {"depth": depth, "photometric_confidence": photometric_confidence}
+        if self.keep_index:
+            out["depth_index"] = index
+        return out
 
 
 def mvsnet_loss(depth_est, depth_gt, mask):

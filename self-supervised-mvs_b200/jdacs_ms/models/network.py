@@ -44,14 +44,16 @@ class FeaturePyramid(nn.Module):
         dev = imgs.device
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
         key = ("tc", dtype, dev)
-        hit = self.__dict__.setdefault("_packed", {}).get(key)
+        keep = regnet.owned(self)      # DataParallel replicas recompute (their tensors come and go): regnet.owned
+        hit = self.__dict__.setdefault("_packed", {}).get(key) if keep else None
         if hit is None or hit[0] != sig:
             layers = []
             for name in self.LAYERS:
                 c = getattr(self, name)[0]
                 layers.append((ops.pack_conv2d_weight(c.weight), c.out_channels, c.bias.detach().float().contiguous()))
             hit = (sig, layers, {})
-            self._packed[key] = hit
+            if keep:
+                self._packed[key] = hit
         b, n = imgs.shape[0], imgs.shape[1]
         out = []
         cur = imgs
@@ -64,6 +66,10 @@ class FeaturePyramid(nn.Module):
                 x = ops.conv2d_raw(x, g, cout, 3, 1, None, bias, 0.1, out_padded=(i == len(hit[1]) - 1), tile_cache=hit[2])
             out.append(x.view(n, b, *x.shape[1:]))
         return out
+
+    def train(self, mode=True):
+        self.__dict__.pop("_packed", None)
+        return super().train(mode)
 
     def forward(self, img, scales=5):
         fp = [self._trunk(img)]
@@ -97,6 +103,10 @@ class CostRegNet(nn.Module):
         self.algo = 0
         self.act_dtype = None
 
+    def train(self, mode=True):
+        self._cache.clear()
+        return super().train(mode)
+
     def forward(self, x):
         tr = self.training
         x = regnet.as_c8(x, torch.float32 if tr else (self.act_dtype or torch.float32))
@@ -127,6 +137,7 @@ class CVPMVSNet(nn.Module):
         self.args = args
         self.volume_dtype = volume_dtype
         self.feature_tc = True      # eval + 16-bit volumes: FeaturePyramid on the repo's tcgen05 convolution kernel
+        self.keep_index = False     # also return "depth_index" of the finest level (network.py:187-188)
 
     def forward(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max):
         nsrc, nscale = self.args.nsrc, self.args.nscale
@@ -157,7 +168,7 @@ class CVPMVSNet(nn.Module):
         else:
             cost_volume = ops.warp_variance(ref_pyr[-1], [p[-1] for p in src_pyrs], rt, depth_hypos, dt, ALIGN_CORNERS, True)
         cost_reg = self.cost_reg_refine(cost_volume)
-        depth, _, conf, _ = ops.soft_argmin(cost_reg, depth_hypos)
+        depth, index, conf, _ = ops.soft_argmin(cost_reg, depth_hypos)
         depth_est_list.append(depth)
 
         # refinement up the pyramid (network.py:153-180)
@@ -172,11 +183,14 @@ class CVPMVSNet(nn.Module):
                 cost_volume = proj_cost(self.args, ref_pyr[level], src_pyrs, level, ref_in_ms[:, level],
                                         src_in_ms[:, :, level], ref_ex, src_ex, depth_hypos, dt, as_c8=True)
             cost_reg2 = self.cost_reg_refine(cost_volume)
-            depth, _, conf, _ = ops.soft_argmin(cost_reg2, depth_hypos)
+            depth, index, conf, _ = ops.soft_argmin(cost_reg2, depth_hypos)
             depth_est_list.append(depth)
 
         depth_est_list.reverse()  # finest first (network.py:195)
-        return {"depth_est_list": depth_est_list, "prob_confidence": conf}
+        out = {"depth_est_list": depth_est_list, "prob_confidence": conf}
+        if self.keep_index:
+            out["depth_index"] = index
+        return out
 
 
 def sL1_loss(depth_est, depth_gt, mask):

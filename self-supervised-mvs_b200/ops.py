@@ -43,6 +43,17 @@ def pack_c8(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
     return out
 
 
+def alloc_c8p(m: int, cb: int, h: int, w: int, dtype: torch.dtype, device, zero: bool) -> Tensor:
+    """Storage of zero-bordered C8P maps [m, cb, h+3, w+2, 8] FOLLOWED BY ONE ZERO VECTOR (include/mvs_b200.h): a sample beyond
+    the bottom-right corner puts its zero-weight 4th tap at row h+2, column w+2 -- the first vector of the next plane, i.e. one
+    vector past the buffer for the last plane.  The returned tensor is a view of the first m*cb*(h+3)*(w+2)*8 elements."""
+    n = m * cb * (h + 3) * (w + 2) * 8
+    flat = torch.zeros(n + 8, dtype=dtype, device=device) if zero else torch.empty(n + 8, dtype=dtype, device=device)
+    if not zero:
+        flat[n:].zero_()
+    return flat[:n].view(m, cb, h + 3, w + 2, 8)
+
+
 def pack_c8_padded(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
     """[M,C,H,W] (fp32 NCHW, or channels-last `dtype`) or C8 [M,C/8,H,W,8] `dtype` -> zero-bordered C8P [M,C/8,H+3,W+2,8] `dtype`:
     pixel (y, x) sits at row y+1, column x+1 (the layout the fused warp+variance kernel gathers from)."""
@@ -63,7 +74,7 @@ def pack_c8_padded(x: Tensor, dtype: torch.dtype = torch.float32) -> Tensor:
             x, layout = _f32c(x), 0
     else:
         raise ValueError("expected [M,C,H,W] or C8 [M,C/8,H,W,8], got %s" % (tuple(x.shape),))
-    out = torch.empty(m, c // 8, h + 3, w + 2, 8, dtype=dtype, device=x.device)
+    out = alloc_c8p(m, c // 8, h, w, dtype, x.device, zero=False)
     call("mvs_pack_c8_padded", x, ptr(x), ptr(out), m, c, h, w, layout, dtype_code(dtype))
     return out
 
@@ -296,7 +307,7 @@ def conv2d_raw(x: Tensor, g: Tensor, cout: int, ksize: int, stride: int, scale: 
     d = Conv2dDesc(m, cib * 8, cout, h, w, ho, wo, ksize, stride, dtype_code(x.dtype), 2 if leaky else int(bool(relu)), int(out_padded), 0,
                    float(relu) if leaky else 0.0)
     if out_padded:
-        y = torch.zeros(m, cout // 8, ho + 3, wo + 2, 8, dtype=x.dtype, device=x.device)
+        y = alloc_c8p(m, cout // 8, ho, wo, x.dtype, x.device, zero=True)
     else:
         y = torch.empty(cout // 8, m, ho, wo, 8, dtype=x.dtype, device=x.device)
     nws = _lib.lib().mvs_conv2d_workspace_bytes(C.byref(d))

@@ -19,12 +19,27 @@ from . import ops
 Tensor = torch.Tensor
 
 
+def owned(module: nn.Module) -> bool:
+    """True when every parameter of `module` is a leaf nn.Parameter, i.e. the module is the one the user holds.  The replicas
+    nn.DataParallel builds per forward (the reference's train.py:65) hold plain tensors instead -- fresh broadcast copies at
+    recycled addresses with `_version` 0, and they share the original's __dict__ (replicate() copies it shallowly) -- so nothing
+    derived from their weights may be cached: a later replica with NEW weights could otherwise hit a stale entry."""
+    return all(isinstance(p, nn.Parameter) for p in module._parameters.values() if p is not None) and \
+        all(owned(m) for m in module.children())
+
+
 class PackCache:
-    """Packed weights / folded BN affines of frozen (eval-mode) parameters, invalidated by in-place updates."""
+    """Packed weights / folded BN affines of frozen (eval-mode) parameters of the module that owns them.  Entries are keyed by
+    (id, data_ptr, _version, device): in-place updates (optimizer steps, load_state_dict) invalidate them; writes through `.data`
+    do not bump `_version` -- call clear() (or module.train(); module.eval()) after such an update."""
 
     def __init__(self) -> None:
         self._store: Dict[Tuple, Tuple] = {}
         self.tiles: Dict[Tuple, Tensor] = {}   # tcgen05 weight tap tiles, keyed by the packed weight (ops.conv3d_raw)
+
+    def clear(self) -> None:
+        self._store.clear()
+        self.tiles.clear()
 
     @staticmethod
     def _key(*tensors: Tensor) -> Tuple:
@@ -61,6 +76,10 @@ def conv_bn_relu(x: Tensor, conv: nn.Module, bn: nn.modules.batchnorm._BatchNorm
     if training:
         z = ops.conv3d(x, conv.weight, None, stride, transposed)
         return ops.bn_act_train(z, bn, skip, True)
+    if not (isinstance(conv.weight, nn.Parameter) and isinstance(bn.weight, nn.Parameter)):   # a DataParallel replica: see owned()
+        scale, shift = ops.fold_bn(bn)
+        return ops.conv3d_raw(x, ops.pack_conv3d_weight(conv.weight, transposed), cout, stride, transposed, scale, shift, skip,
+                              relu=True, algo=algo)
     scale, shift = cache.folded(bn)
     return ops.conv3d_raw(x, cache.packed(conv.weight, transposed), cout, stride, transposed, scale, shift, skip,
                           relu=True, algo=algo, tile_cache=cache.tiles)
@@ -71,6 +90,9 @@ def conv_bias(x: Tensor, conv: nn.Conv3d, training: bool, cache: PackCache, algo
     if training:
         return ops.conv3d(x, conv.weight, conv.bias, 1, False)
     bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+    if not isinstance(conv.weight, nn.Parameter):
+        return ops.conv3d_raw(x, ops.pack_conv3d_weight(conv.weight, False), conv.out_channels, 1, False, None, bias, None,
+                              relu=False, algo=algo)
     return ops.conv3d_raw(x, cache.packed(conv.weight, False), conv.out_channels, 1, False, None, bias, None, relu=False,
                           algo=algo, tile_cache=cache.tiles)
 

@@ -124,3 +124,17 @@ def plausible_depth(batch: int, hf: int, wf: int, seed: int = 0) -> torch.Tensor
     d = 600.0 + 120.0 * torch.sin(3.0 * xx + 0.5) * torch.cos(2.0 * yy) + 40.0 * xx
     d = d.unsqueeze(0).repeat(batch, 1, 1) + 2.0 * torch.randn(batch, hf, wf, generator=g)
     return d.contiguous()
+
+
+def randomise_bn(model: torch.nn.Module, seed: int = 5) -> None:
+    """Give every BatchNorm of `model` non-trivial affine parameters and running statistics (the fixtures of
+    oracle/gen_golden.py use the same recipe): with the default statistics (mean 0, var 1) and default-initialised
+    convolutions the regularised volume is almost flat along depth and the softmax is uniform (hazard H11)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+                m.weight.copy_(0.75 + 0.5 * torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))

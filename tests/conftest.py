@@ -89,6 +89,20 @@ def gpu():
     return Backend("cuda:0")
 
 
+@pytest.fixture
+def knob():
+    """Set test / tuning knobs of the bound library (mvs_set_knob); every knob touched is reset afterwards."""
+    import ssmvs_b200
+    touched = []
+
+    def setter(name, value):
+        touched.append(name)
+        ssmvs_b200._lib.set_knob(name, value)
+    yield setter
+    for name in touched:
+        ssmvs_b200._lib.set_knob(name, -1)
+
+
 def rel_err(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()

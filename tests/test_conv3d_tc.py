@@ -42,15 +42,15 @@ CASES += [
 @pytest.mark.parametrize("dtype,force_nm,kdfold", [(torch.float16, 0, 1), (torch.bfloat16, 0, 1), (torch.float16, 4, 1), (torch.float16, 2, 1),
                                                    (torch.float16, 0, 0), (torch.float16, 4, 0)])
 @pytest.mark.parametrize("cin,cout,stride,tr,shape", CASES)
-def test_tc_matches_simt_and_aten(gpu, monkeypatch, cin, cout, stride, tr, shape, dtype, force_nm, kdfold):
+def test_tc_matches_simt_and_aten(gpu, knob, cin, cout, stride, tr, shape, dtype, force_nm, kdfold):
     from ssmvs_b200 import ops
     if not kdfold and not (stride == 1 and cout <= 8):
         pytest.skip("MVS_TC_KDFOLD only changes stride-1 layers with <= 8 output channels")
-    monkeypatch.setenv("MVS_TC_KDFOLD", str(kdfold))       # library test knob: fold the kd taps into N as well (default on)
+    knob("tc_kdfold", kdfold)       # library test knob: fold the kd taps into N as well (default on)
     if force_nm:
-        monkeypatch.setenv("MVS_TC_NM", str(force_nm))     # library test knob: M-tiles per CTA (default: by volume size)
+        knob("tc_nm", force_nm)     # library test knob: M-tiles per CTA (default: by volume size)
     else:
-        monkeypatch.delenv("MVS_TC_NM", raising=False)
+        knob("tc_nm", -1)
     torch.manual_seed(cin * 100 + cout + stride)
     b, d, h, w = shape
     dev = gpu.device

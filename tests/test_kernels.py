@@ -173,7 +173,7 @@ def test_warp_variance_16bit_padded(gpu, oracle, dtype, tol, channels, nsrc, ref
 @pytest.mark.gpu
 @pytest.mark.parametrize("baseline", [1.0, 4.0, 25.0])
 @pytest.mark.parametrize("shape", [(32, 4, 64, 96, 40), (16, 2, 37, 53, 9)])
-def test_warp_variance_tma_staging_is_transparent(gpu, monkeypatch, shape, baseline):
+def test_warp_variance_tma_staging_is_transparent(gpu, knob, shape, baseline):
     """TMA-staged source windows vs the same kernel arithmetic gathering from global memory: bit-identical volumes, whether
     every window fits (baseline 1), some do (4) or none does (25: the per-source fallback inside the staged kernel)."""
     ops = _ops()
@@ -190,9 +190,9 @@ def test_warp_variance_tma_staging_is_transparent(gpu, monkeypatch, shape, basel
     maps = ops.pack_c8_padded(gpu.to(inp["features"].flatten(0, 1)), torch.float16)
     maps = maps.view(nsrc + 1, 2, *maps.shape[1:])
     dv = gpu.to(inp["depth_values"])
-    monkeypatch.setenv("MVS_WARP_TMA", "1")
+    knob("warp_tma", 1)
     a = ops.warp_variance_maps(maps, rt, dv, torch.float16)
-    monkeypatch.setenv("MVS_WARP_TMA", "0")
+    knob("warp_tma", 0)
     b = ops.warp_variance_maps(maps, rt, dv, torch.float16)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
@@ -217,6 +217,43 @@ def test_warp_variance_16bit_padded_degenerate(gpu):
     r = feats[0].half().float()
     for d in (0, 2, 3):
         assert torch.allclose(v[:, :, d], r * r / 4, rtol=2e-3, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tma", [1, 0])
+def test_warp_variance_bottom_right_overshoot_reads_only_the_slack_vector(gpu, knob, tma):
+    """A source that projects beyond the bottom-right corner clamps to (H+1, W+1): its zero-weight 4th tap is the vector right
+    after the last plane.  The C8P contract gives the buffer exactly one zero vector of slack; everything behind it is poisoned
+    with NaN here, so a read one vector further (or a missing slack) turns the volume into NaN."""
+    ops = _ops()
+    torch.manual_seed(4)
+    c, h, w, nd = 16, 10, 14, 8
+    feats = torch.randn(2, 1, c, h, w)
+    P = torch.eye(4).reshape(1, 1, 4, 4).repeat(1, 2, 1, 1)
+    P[0, 1, 0, 3] = 1e5   # huge +x, +y translation: every sample lands far beyond the bottom-right corner
+    P[0, 1, 1, 3] = 1e5
+    depth = (10.0 + torch.arange(nd, dtype=torch.float32)).unsqueeze(0)
+    rt = ops.compose_proj(gpu.to(P))
+    good = ops.pack_c8_padded(gpu.to(feats.flatten(0, 1)), torch.float16)
+    n = good.numel()
+    big = torch.full((n + 8 + 4096,), float("nan"), dtype=torch.float16, device=gpu.device)
+    big[:n] = good.flatten()
+    big[n:n + 8] = 0          # the one slack vector the header asks for
+    maps = big[:n].view(2, 1, *good.shape[1:])
+    knob("warp_tma", tma)
+    v = ops.unpack_c8(ops.warp_variance_maps(maps, rt, gpu.to(depth), torch.float16)).cpu()
+    assert torch.isfinite(v).all()
+    r = feats[0].half().float()
+    assert torch.allclose(v[:, :, 0], r * r / 4, rtol=2e-3, atol=1e-4)     # variance of (ref, 0)
+    # per-pixel hypotheses always take the gather kernel
+    dpp = depth.view(1, nd, 1, 1).expand(1, nd, h, w).contiguous()
+    v2 = ops.unpack_c8(ops.warp_variance_maps(maps, rt, gpu.to(dpp), torch.float16)).cpu()
+    assert torch.isfinite(v2).all() and torch.allclose(v2[:, :, 0], r * r / 4, rtol=2e-3, atol=1e-4)
+    # and the allocation helper really provides that slack
+    st = good.untyped_storage()
+    assert st.nbytes() >= (good.storage_offset() + n + 8) * 2
+    tail = torch.empty(0, dtype=torch.float16, device=gpu.device).set_(st, good.storage_offset() + n, (8,))
+    assert torch.count_nonzero(tail) == 0
 
 
 def test_soft_argmin(be, oracle, golden):

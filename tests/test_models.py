@@ -101,3 +101,46 @@ def test_unsup_loss(be, golden):
     with pytest.raises(RuntimeError):                          # hazard H5: top-3 needs >= 3 source views
         g = golden("jdacs_unsup_loss")
         UnSupLoss()(be.to(g["imgs"][:, :3]), be.to(g["cams"][:, :3]), be.to(g["depth"]))
+
+
+def _fake_replica(module):
+    """What nn.parallel.replicate() hands a DataParallel worker under no_grad: a shallow copy of every module (shared __dict__
+    entries such as the pack caches!) whose parameters are plain tensor copies, not nn.Parameters."""
+    memo = {}
+    for name, m in module.named_modules():
+        r = m._replicate_for_data_parallel()
+        memo[m] = r
+    for m, r in memo.items():
+        for k, child in m._modules.items():
+            r._modules[k] = memo[child] if child is not None else None
+        for k, p in m._parameters.items():
+            r._parameters[k] = None if p is None else p.detach().clone()
+        for k, b in m._buffers.items():
+            r._buffers[k] = None if b is None else b.detach().clone()
+    return memo[module]
+
+
+def test_replicas_never_populate_or_hit_the_pack_caches(emu, golden):
+    """DataParallel replicas share the original's cache objects and hold fresh tensors with recycled ids / addresses /
+    _version 0, so an entry cached for one replica could be served to a later replica with different weights."""
+    from ssmvs_b200 import regnet
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    g = golden("jdacs_mvsnet")
+    model = MVSNet(refine=False)
+    model.load_state_dict(state_dict_of(g), strict=False)
+    model.eval()
+    args = [emu.to(g[k]) for k in ("imgs", "proj_matrices", "depth_values")]
+    with torch.no_grad():
+        rep = _fake_replica(model)
+        assert regnet.owned(model) and not regnet.owned(rep) and rep.cost_regularization._cache is model.cost_regularization._cache
+        a = rep(*args)["depth"]
+        assert not model.cost_regularization._cache._store and not model.cost_regularization.conv0._cache._store
+        assert rel_err(a, g["depth"]) < 1e-4
+        # "an epoch later": new weights, a new replica -- must see the new weights
+        model.cost_regularization.prob.weight.mul_(0.5)
+        b = _fake_replica(model)(*args)["depth"]
+        want = model(*args)["depth"]
+        assert torch.equal(b, want) and not torch.equal(a, b)
+        assert model.cost_regularization._cache._store            # the owner itself does cache ...
+        model.train()
+        assert not model.cost_regularization._cache._store        # ... and train() drops everything derived from the weights

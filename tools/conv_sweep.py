@@ -25,9 +25,9 @@ def timeit(fn, reps=5):
 
 def run(cin, cout, stride, tr, shape, nm=0):
     if nm:
-        os.environ["MVS_TC_NM"] = str(nm)
+        ssmvs_b200._lib.set_knob("tc_nm", nm)
     else:
-        os.environ.pop("MVS_TC_NM", None)
+        ssmvs_b200._lib.set_knob("tc_nm", -1)
     b, d, h, w = shape
     x8 = ops.pack_c8(torch.randn(b, cin, d, h, w, device=dev), torch.float16)
     wt = 0.1 * (torch.randn(cin, cout, 3, 3, 3, device=dev) if tr else torch.randn(cout, cin, 3, 3, 3, device=dev))
