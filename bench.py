@@ -68,10 +68,12 @@ def load_oracle():
 
 def make_model(dtype):
     from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200 import synth
     torch.manual_seed(0)
     model = MVSNet(refine=False, volume_dtype=dtype)
-    with torch.no_grad():
-        model.cost_regularization.prob.weight.mul_(64.0)  # peaky softmax (hazard H11); same work either way
+    synth.randomise_bn(model, 5)                          # non-trivial BN statistics and a scaled last layer: a non-uniform
+    with torch.no_grad():                                 # softmax (hazard H11); the work is the same either way, and the
+        model.cost_regularization.prob.weight.mul_(64.0)  # parity leg (parity_check) calibrates and asserts the peakiness itself
     return model.eval()
 
 
@@ -213,6 +215,36 @@ def gpu_library_timer(dev, steps: int = 3):
     return [a.elapsed_time(b) * 1e-3 for a, b in ev]
 
 
+def parity_check(dev, dtype, name):
+    """The product path at the benchmarked precision against the fp32 oracle run on this GPU (checker only, outside every timed
+    region), at the workload's full size, on a probability volume asserted to be peaky (tests/parity_util.py, hazard H11)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_util as pu
+    try:
+        model, inp, want, cond = pu.peaky_mvsnet(dev, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=0, target_peak=0.3)
+        assert cond["peak"] >= 0.3 and cond["depth_std"] >= 10.0, cond
+        r = pu.depth_parity(pu.product_mvsnet(model, inp, dtype), want)
+        out = {"against": "oracle/planesweep.py mvsnet_forward in fp32 on this GPU (TF32 off), 1 item of the workload", "dtype": name,
+               "conditions": cond, "depth_rel_max": r["depth_rel_max"], "depth_rel_p999": r["depth_rel_p999"],
+               "depth_rel_median": r["depth_rel_median"], "frac_pixels_within_1e-3": r["frac_within_1e-3"],
+               "index_mismatch": r["index_mismatch"], "index_mismatch_near_integer": r["index_mismatch_near_integer"],
+               "index_off_by_more_than_1": r["index_off_by_more_than_1"], "pixels": r["pixels"],
+               "conf_abs_max": r["conf_abs_max"], "conf_abs_p999": r["conf_abs_p999"]}
+        if dtype != torch.float32:
+            ideal = pu.depth_parity(pu.ideal_storage_mvsnet(model, inp, dtype), want)
+            out["storage_floor"] = {"what": "the oracle's fp32 arithmetic with every stored tensor rounded once to %s" % name,
+                                    "depth_rel_max": ideal["depth_rel_max"], "depth_rel_p999": ideal["depth_rel_p999"],
+                                    "index_mismatch": ideal["index_mismatch"]}
+        tf = pu.depth_parity(pu.oracle_mvsnet(model, inp, tf32=True)[0], want)
+        out["oracle_with_torch_default_tf32"] = {"depth_rel_max": tf["depth_rel_max"], "depth_rel_p999": tf["depth_rel_p999"],
+                                                 "index_mismatch": tf["index_mismatch"]}
+        return out
+    except Exception as exc:
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+    finally:
+        torch.cuda.empty_cache()
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -239,6 +271,10 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU; measured 1 / 2 / 4 / 8 items: 4.4 / 5.3 / 6.3 / 6.4 G samples/s)")
     ap.add_argument("--lanes", type=int, default=1, help="item groups captured on separate streams inside the CUDA graph (GraphedForward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the end-to-end parity check against the fp32 oracle (rank 0, 1 GPU only)")
+    ap.add_argument("--img-dtype", choices=["same", "fp32"], default="same",
+                    help="storage of the images handed to MVSNet.forward: 'same' = the volume dtype (16-bit images give bit-identical "
+                         "results to fp32 images on the 16-bit path, whose first layer rounds its input anyway, at half the upload)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -262,6 +298,8 @@ def main():
     model = make_model(dtype).to(dev)
     PB = args.batch
     host = synth.mvsnet_inputs(PB, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=rank)
+    if args.img_dtype == "same" and dtype != torch.float32:
+        host["imgs"] = host["imgs"].to(dtype)
     pinned = {k: host[k].pin_memory() for k in ("imgs", "proj_matrices", "depth_values")}
     res = {k: v.to(dev) for k, v in pinned.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -426,6 +464,8 @@ def main():
                         "how": "StreamedForward.run: pinned host batch -> H2D (copy stream, one step ahead, straight into the static inputs of one of two captured graphs) -> graph replay -> D2H of depth + confidence, every step; one event pair around the K steps, max over ranks"},
                 "roofline": dominant, "roofline_warp_var": roof_wv, "roofline_conv0": roof_conv0, "roofline_reg3d": roof_reg,
                 "stage_ms": stages}
+        if world == 1 and not args.no_parity:
+            line["parity"] = parity_check(dev, dtype, args.dtype)
         if world == 1 and not args.no_cpu_baseline:
             times, threads = cpu_forward_timer(3, 1)
             line["cpu_baseline"] = {"value": SAMPLES_PER_ITEM * len(times) / sum(times), "unit": "depth-samples/s", "cores": threads,

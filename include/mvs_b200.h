@@ -146,8 +146,10 @@ typedef struct {
 int64_t mvs_conv2d_workspace_bytes(const mvs_conv2d_desc* d);
 int mvs_conv2d_fwd(const mvs_conv2d_desc* d, const void* x, const float* g, const float* scale, const float* shift, void* y,
                    void* ws, void* stream);
-/* fp32 images [B][N][3][H][W] -> C8 stack [1][M = N*B][H][W][8] in `dtype`, image index m = v * B + b, channels 3..7 zero. */
-int mvs_pack_images_c8(const float* imgs, void* dst, int B, int N, int H, int W, int dtype, void* stream);
+/* images [B][N][3][H][W] stored as `src_dtype` (fp32, or fp16 / bf16 as a host pipeline may upload them: the first layer rounds
+ * its input to the storage type anyway, so 16-bit images of the volume dtype give bit-identical results at half the H2D bytes)
+ * -> C8 stack [1][M = N*B][H][W][8] in `dtype`, image index m = v * B + b, channels 3..7 zero. */
+int mvs_pack_images_c8(const void* imgs, int src_dtype, void* dst, int B, int N, int H, int W, int dtype, void* stream);
 
 /* batch-norm helpers for training mode (statistics over B*D*H*W per channel), C8 fp32 volumes.
  * sums = [2][C] (sum, sum of squares), zero-initialised by the caller.  jdacs/models/module.py:39-42. */

@@ -123,12 +123,13 @@ def homo_warping_ms(src_fea: Tensor, ref_in: Tensor, src_in: Tensor, ref_ex: Ten
 # a4: variance cost volume
 # --------------------------------------------------------------------------------------------
 def variance_volume(ref_fea: Tensor, src_feas: Sequence[Tensor], ref_proj: Tensor, src_projs: Sequence[Tensor],
-                    depth: Tensor, ref_sq_in_sum: bool = False, align_corners: bool = False) -> Tensor:
+                    depth: Tensor, ref_sq_in_sum: bool = False, align_corners: bool = False, inplace: bool = False) -> Tensor:
     """var = S2/N - (S1/N)^2 over the reference volume and the warped sources.
 
     jdacs/models/mvsnet.py:120-136.  ref_sq_in_sum=True reproduces the CVP aliasing
     (hazard H2, jdacs-ms/models/network.py:114-116, modules.py:216-217): `pow_` squares the
-    tensor that `volume_sum` aliases, so S1 starts from ref^2 instead of ref."""
+    tensor that `volume_sum` aliases, so S1 starts from ref^2 instead of ref.
+    inplace=True is the reference's eval-mode branch (mvsnet.py:130-136): the same values, accumulated in place (no autograd)."""
     nd = depth.shape[1]
     n = len(src_feas) + 1
     ref_vol = ref_fea.unsqueeze(2).repeat(1, 1, nd, 1, 1)
@@ -136,8 +137,14 @@ def variance_volume(ref_fea: Tensor, src_feas: Sequence[Tensor], ref_proj: Tenso
     s1 = s2.clone() if ref_sq_in_sum else ref_vol
     for fea, proj in zip(src_feas, src_projs):
         wv = homo_warping(fea, proj, ref_proj, depth, align_corners)
-        s1 = s1 + wv
-        s2 = s2 + wv ** 2
+        if inplace:
+            s1 += wv
+            s2 += wv.pow_(2)
+        else:
+            s1 = s1 + wv
+            s2 = s2 + wv ** 2
+    if inplace:
+        return s2.div_(n).sub_(s1.div_(n).pow_(2))
     return s2 / n - (s1 / n) ** 2
 
 
@@ -256,7 +263,7 @@ def mvsnet_forward(imgs: Tensor, proj_matrices: Tensor, depth_values: Tensor, P:
     fp = _sub(P, "feature.")
     feats = [feature_net(imgs[:, v], fp, training) for v in range(views)]
     var = variance_volume(feats[0], feats[1:], proj_matrices[:, 0], [proj_matrices[:, v] for v in range(1, views)],
-                          depth_values, False, align_corners)
+                          depth_values, False, align_corners, inplace=not training and not torch.is_grad_enabled())
     reg = cost_reg_mvsnet(var, _sub(P, "cost_regularization."), training).squeeze(1)
     prob, depth = soft_argmin(reg, depth_values)
     with torch.no_grad():

@@ -53,7 +53,7 @@ _SIGS = {
     "mvs_conv3d_bwd_weight": ([C.POINTER(Conv3dDesc), _P, _P, _P, _P], _I),
     "mvs_conv2d_workspace_bytes": ([C.POINTER(Conv2dDesc)], _L),
     "mvs_conv2d_fwd": ([C.POINTER(Conv2dDesc), _P, _P, _P, _P, _P, _P, _P], _I),
-    "mvs_pack_images_c8": ([_P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "mvs_pack_images_c8": ([_P, _I, _P, _I, _I, _I, _I, _I, _P], _I),
     "mvs_bn_stats": ([_P, _P, _I, _I, _L, _P], _I),
     "mvs_bn_act_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P], _I),
     "mvs_bn_act_bwd_reduce": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _P], _I),

@@ -149,28 +149,35 @@ extern "C" int mvs_pack_c8_padded(const void* src, void* dst, int M, int C, int 
     return MVS_CHECK_LAUNCH("mvs_pack_c8_padded");
 }
 
-// fp32 images [B][N][3][H][W] -> C8 image stack [M = N*B][H][W][8] (m = v * B + b), channels 3..7 zero: the input of the
-// tcgen05 feature extractor.  One thread per pixel: three coalesced plane reads, one 16-byte store.
-template <typename T>
-__global__ void pack_images_c8_kernel(const float* __restrict__ imgs, T* __restrict__ dst, int B, int N, int64_t S, int64_t total) {
+// images [B][N][3][H][W] (fp32, or already 16-bit as a host pipeline uploads them) -> C8 image stack [M = N*B][H][W][8]
+// (m = v * B + b), channels 3..7 zero: the input of the tcgen05 feature extractor.  One thread per pixel: three coalesced
+// plane reads, one 16-byte store.
+template <typename TS> __device__ __forceinline__ float img_load(const TS* p) { return (float)__ldg(p); }
+#ifndef MVS_CPU_EMU
+template <> __device__ __forceinline__ float img_load<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float img_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+#endif
+template <typename TS, typename T>
+__global__ void pack_images_c8_kernel(const TS* __restrict__ imgs, T* __restrict__ dst, int B, int N, int64_t S, int64_t total) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // m * S + s
     if (i >= total) return;
     const int64_t s = i % S;
     const int m = (int)(i / S);
     const int v = m / B, b = m % B;
-    const float* p = imgs + (((int64_t)b * N + v) * 3) * S + s;
+    const TS* p = imgs + (((int64_t)b * N + v) * 3) * S + s;
     float o[8];
-    o[0] = __ldg(p); o[1] = __ldg(p + S); o[2] = __ldg(p + 2 * S);
+    o[0] = img_load<TS>(p); o[1] = img_load<TS>(p + S); o[2] = img_load<TS>(p + 2 * S);
 #pragma unroll
     for (int k = 3; k < 8; ++k) o[k] = 0.f;
     V8<T>::store(dst + i * 8, o);
 }
 
-extern "C" int mvs_pack_images_c8(const float* imgs, void* dst, int B, int N, int H, int W, int dtype, void* stream) {
+extern "C" int mvs_pack_images_c8(const void* imgs, int src_dtype, void* dst, int B, int N, int H, int W, int dtype, void* stream) {
     MVS_REQUIRE(imgs && dst, MVS_E_ARG, "mvs_pack_images_c8: null pointer");
     MVS_REQUIRE(B > 0 && N > 0 && H > 0 && W > 0, MVS_E_SHAPE, "mvs_pack_images_c8: bad dims");
     const int64_t S = (int64_t)H * W, total = (int64_t)B * N * S;
-    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(pack_images_c8_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, imgs, (T*)dst, B, N, S, total));
+    MVS_DISPATCH_DTYPE(src_dtype, TS, MVS_DISPATCH_DTYPE(dtype, T,
+        MVS_LAUNCH((pack_images_c8_kernel<TS, T>), dim3(mvs_cdiv(total, 256)), dim3(256), stream, (const TS*)imgs, (T*)dst, B, N, S, total)));
     return MVS_CHECK_LAUNCH("mvs_pack_images_c8");
 }
 

@@ -203,12 +203,15 @@ class MVSNet(nn.Module):
         # each view is its own call, because BatchNorm2d statistics are per call in the reference (:115).
         dt = torch.float32 if self.training else self.volume_dtype
         rt = ops.compose_proj(proj_matrices)
+        fast = (not self.training) and dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0
+        if imgs.dtype != torch.float32 and not (fast and imgs.dtype == dt):
+            imgs = imgs.float()     # 16-bit images (a host pipeline may upload them so) are only consumed as such by the 16-bit fast path
         if self.training:
             features = [self.feature(imgs[:, v]) for v in range(n)]
             # step 2. plane sweep: warp + variance, fused (:120-136)
             variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
         else:
-            if dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0:
+            if fast:
                 # the feature extractor on the tcgen05 convolution kernel, emitting the gather layout directly
                 maps = self.feature.forward_maps(imgs, dt)
             else:
@@ -229,7 +232,7 @@ class MVSNet(nn.Module):
         # softmax + regression + confidence, fused (:142-151)
         depth, index, photometric_confidence, _ = ops.soft_argmin(cost_reg, depth_values)
         if self.refine:
-            depth = self.refine_network(imgs[:, 0], depth)
+            depth = self.refine_network(imgs[:, 0].float(), depth)
         out = {"depth": depth, "photometric_confidence": photometric_confidence}
         if self.keep_index:
             out["depth_index"] = index

@@ -142,6 +142,7 @@ class CVPMVSNet(nn.Module):
     def forward(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max):
         nsrc, nscale = self.args.nsrc, self.args.nscale
         depth_est_list = []
+        ref_img, src_imgs = ref_img.float(), src_imgs.float()    # 16-bit uploads are widened here: the image pyramid is built in fp32
         dt = torch.float32 if self.training else self.volume_dtype
         self.cost_reg_refine.act_dtype = None if self.training else dt
 

@@ -275,13 +275,13 @@ def conv3d_raw(x: Tensor, g: Tensor, cout: int, stride: int = 1, transposed: boo
 
 # ------------------------------------------------------------------------------------------------ 2-D feature layers (tcgen05)
 def pack_images_c8(imgs: Tensor, dtype: torch.dtype) -> Tensor:
-    """fp32 images [B,N,3,H,W] -> C8 image stack [1, N*B, H, W, 8] (`dtype`; image m = v*B + b; channels 3..7 zero)."""
-    x = _f32c(imgs)
+    """images [B,N,3,H,W] (fp32 / fp16 / bf16) -> C8 image stack [1, N*B, H, W, 8] (`dtype`; image m = v*B + b; channels 3..7 zero)."""
+    x = imgs.detach().contiguous() if imgs.dtype in (torch.float16, torch.bfloat16) else _f32c(imgs)
     b, n, c, h, w = x.shape
     if c != 3:
         raise ValueError("expected 3-channel images, got %d channels" % c)
     out = torch.empty(1, n * b, h, w, 8, dtype=dtype, device=x.device)
-    call("mvs_pack_images_c8", x, ptr(x), ptr(out), b, n, h, w, dtype_code(dtype))
+    call("mvs_pack_images_c8", x, ptr(x), dtype_code(x.dtype), ptr(out), b, n, h, w, dtype_code(dtype))
     return out
 
 

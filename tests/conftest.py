@@ -64,24 +64,31 @@ class Backend:
         return t.detach().clone().to(self.device) if isinstance(t, torch.Tensor) else t
 
 
-@pytest.fixture(scope="session")
+_EMU_PATH = []
+
+
+@pytest.fixture
 def emu():
-    """Bind the host-emulation build of the kernel sources (CPU tensors)."""
+    """Bind the host-emulation build of the kernel sources (CPU tensors).  Re-bound per test: other tests bind the product library."""
     import ssmvs_b200
-    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
-    from build_emu import build_emu
-    ssmvs_b200._lib.bind(build_emu())
+    if not _EMU_PATH:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        from build_emu import build_emu
+        _EMU_PATH.append(build_emu())
+    if ssmvs_b200._lib._lib is None or not ssmvs_b200._lib._emulation:
+        ssmvs_b200._lib.bind(_EMU_PATH[0])
     assert ssmvs_b200._lib.is_emulation()
     return Backend("cpu")
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture
 def gpu():
     """Bind libmvs_b200.so (CUDA tensors)."""
     import ssmvs_b200
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    ssmvs_b200._lib.bind()
+    if ssmvs_b200._lib._lib is None or ssmvs_b200._lib._emulation:
+        ssmvs_b200._lib.bind()
     assert not ssmvs_b200._lib.is_emulation()
     # parity tests compare fp32 with fp32: keep the library (cuDNN / cuBLAS) parts of the models off TF32
     torch.backends.cudnn.allow_tf32 = False

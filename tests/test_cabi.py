@@ -86,7 +86,7 @@ def test_new_entry_points_validate_before_touching_the_device():
     assert lib.mvs_pack_c8_padded(None, None, 1, 8, 4, 4, 0, 0, None) == -1
     assert lib.mvs_pack_c8_padded(1, 1, 1, 7, 4, 4, 0, 0, None) == -2 and b"multiple of 8" in lib.mvs_last_error()
     assert lib.mvs_pack_c8_padded(1, 1, 1, 8, 4, 4, 5, 0, None) == -1 and b"src_layout" in lib.mvs_last_error()
-    assert lib.mvs_pack_images_c8(None, None, 1, 1, 4, 4, 1, None) == -1
+    assert lib.mvs_pack_images_c8(None, 0, None, 1, 1, 4, 4, 1, None) == -1
     # unsupported 2-D layer shapes are reported, not silently computed some other way
     bad = Conv2dDesc(2, 8, 8, 16, 16, 16, 16, 7, 1, 1, 1, 0, 0, 0.0)
     assert lib.mvs_conv2d_workspace_bytes(ctypes.byref(bad)) == 0
