@@ -36,17 +36,20 @@ def load_oracle():
 
 
 class fp32_exact:
-    """Library convolutions / matmuls in true fp32 (torch's default lets cuDNN use TF32)."""
+    """Run the oracle on `dev` (its helper tensors are created on torch's default device) with library convolutions / matmuls in
+    true fp32 (torch's default lets cuDNN use TF32; tf32=True keeps that default)."""
 
-    def __init__(self, tf32: bool = False):
-        self.tf32 = tf32
+    def __init__(self, dev, tf32: bool = False):
+        self.tf32, self.dev = tf32, torch.device(dev)
 
     def __enter__(self):
         self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32 = self.tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
+        self.dev.__enter__()
 
     def __exit__(self, *a):
+        self.dev.__exit__(*a)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
@@ -100,7 +103,7 @@ def peaky_mvsnet(dev, views: int, height: int, width: int, ndepth: int, seed: in
     model = model.to(dev).eval()
     model.keep_index = True
     inp = {k: v.to(dev) for k, v in synth.mvsnet_inputs(batch, views, height, width, ndepth, seed=seed).items()}
-    with torch.no_grad(), fp32_exact():
+    with torch.no_grad(), fp32_exact(dev):
         st = {}
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], sd, False, False, st)
@@ -118,7 +121,7 @@ def oracle_mvsnet(model, inp, tf32: bool = False):
     oracle = load_oracle()
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     st = {}
-    with torch.no_grad(), fp32_exact(tf32):
+    with torch.no_grad(), fp32_exact(inp["imgs"].device, tf32):
         out = oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], sd, False, False, st)
         nd = st["prob"].shape[1]
         ramp = torch.arange(nd, dtype=torch.float32, device=st["prob"].device).view(1, nd, 1, 1)
@@ -161,7 +164,7 @@ def ideal_storage_mvsnet(model, inp, dtype) -> Dict[str, torch.Tensor]:
         sc, sh = affine(R, name + ".1.")
         return F.relu(F.conv_transpose3d(x, q(R[name + ".0.weight"]), None, 2, 1, 1) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
 
-    with torch.no_grad(), fp32_exact():
+    with torch.no_grad(), fp32_exact(inp["imgs"].device):
         imgs, proj, dv = inp["imgs"], inp["proj_matrices"], inp["depth_values"]
         feats = []
         for v in range(imgs.shape[1]):
@@ -194,7 +197,7 @@ def peaky_cvp(dev, nsrc: int, nscale: int, height: int, width: int, seed: int = 
     model = model.to(dev).eval()
     model.keep_index = True
     inp = {k: v.to(dev) for k, v in synth.cvp_inputs(1, nsrc, height, width, seed=seed).items()}
-    with torch.no_grad(), fp32_exact():
+    with torch.no_grad(), fp32_exact(dev):
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         st = {}
         oracle.cvp_forward(inp, sd, nscale, False, False, st)
@@ -210,7 +213,7 @@ def oracle_cvp(model, inp, nscale: int, tf32: bool = False):
     oracle = load_oracle()
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     st = {}
-    with torch.no_grad(), fp32_exact(tf32):
+    with torch.no_grad(), fp32_exact(inp["ref_img"].device, tf32):
         out = oracle.cvp_forward(inp, sd, nscale, False, False, st)
         coarse = out["depth_est_list"][-1]
         cond = {"peak": F.softmax(st["cost_reg0"], 1).max(1)[0].mean().item(), "depth_std": coarse.std().item(),
