@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVS_B200_VERSION 100 /* major*100 + minor */
+#define MVS_B200_VERSION 101 /* major*100 + minor */
 
 enum { MVS_F32 = 0, MVS_F16 = 1, MVS_BF16 = 2 };
 enum { MVS_OK = 0, MVS_E_ARG = -1, MVS_E_SHAPE = -2, MVS_E_LAUNCH = -3, MVS_E_UNSUPPORTED = -4 };
@@ -166,6 +166,36 @@ int mvs_bn_act_bwd_reduce(const float* x, const float* grad_y, const float* mean
 int mvs_bn_act_bwd_apply(const float* x, const float* grad_y, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* red, float* grad_x, int B, int C,
                          int64_t S, int relu, void* stream);
+
+/* ---- training with 16-bit activations (fp32 master weights, fp32 / fp64 accumulation): csrc/train.cu ------------------------------
+ * The forward convolution and the gradient w.r.t. the input are mvs_conv3d_fwd on the tcgen05 kernel (the latter with the same torch
+ * weight packed under the opposite `transposed` flag); the passes below are what BatchNorm3d + ReLU (+ skip) and the weight gradient
+ * add.  z / y / grad_* volumes are C8 in `dtype` (any of MVS_F32 / F16 / BF16).  Reference: the autograd of ConvBnReLU3D and
+ * ConvTranspose3d + BatchNorm3d + ReLU, jdacs/models/module.py:35-42, mvsnet.py:37-74, jdacs-ms/models/network.py:44-74. */
+/* sums = [2][C] doubles (sum, sum of squares over B*S), zero-initialised by the caller */
+int mvs_bn_stats_t(const void* z, int dtype, double* sums, int B, int C, int64_t S, void* stream);
+/* batch statistics -> a = gamma * invstd, b = beta - mean * a, mean, invstd ([C] fp32 each); running_mean / running_var (may be
+ * NULL) are updated like nn.BatchNorm3d.train(): momentum, unbiased variance.  count = B*S. */
+int mvs_bn_finalize(const double* sums, const float* gamma, const float* beta, float eps, float momentum, double count, float* a,
+                    float* b, float* mean, float* invstd, float* running_mean, float* running_var, int C, void* stream);
+/* y = [relu](z * a + b) + skip      (skip may be NULL) */
+int mvs_bn_act_fwd_t(const void* z, const float* a, const float* b, const void* skip, void* y, int dtype, int B, int C, int64_t S,
+                     int relu, void* stream);
+/* red = [2][C] doubles, zero-initialised: red[0] = sum g (= grad beta), red[1] = sum g * xhat (= grad gamma), g = grad_y [z a + b > 0] */
+int mvs_bn_act_bwd_reduce_t(const void* z, const void* grad_y, const float* a, const float* b, const float* mean, const float* invstd,
+                            double* red, int dtype, int B, int C, int64_t S, int relu, void* stream);
+/* grad_z = a (g - red[0]/M - xhat red[1]/M), M = B*S; frozen = 1 (statistics not taken from the batch): grad_z = a g.
+ * grad_gamma / grad_beta ([C] fp32, may be NULL) receive red[1] / red[0]. */
+int mvs_bn_act_bwd_apply_t(const void* z, const void* grad_y, const float* a, const float* b, const float* mean, const float* invstd,
+                           const double* red, void* grad_z, float* grad_gamma, float* grad_beta, int dtype, int B, int C, int64_t S,
+                           int relu, int frozen, void* stream);
+/* plain fp32 [n] -> C8 block [n][8] in `dtype`, value in channel 0 (lifts the gradient of the single-channel `prob` output) */
+int mvs_lift_c1(const float* src, void* dst, int dtype, int64_t n, void* stream);
+/* Weight gradient on tensor cores (warp-level mma.sync m16n8k16, fp32 accumulation; why not tcgen05: see csrc/train.cu).
+ * x and grad_z: C8 volumes in d->dtype_in (fp16 / bf16), Cin and Cout multiples of 8 (<= 64); grad_w: torch layout [Cout][Cin][27]
+ * or, transposed, [Cin][Cout][27], fp32, zero-initialised by the caller, with cout_real <= d->Cout output channels (1 for a lifted
+ * single-channel gradient). */
+int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real, void* stream);
 
 /* ---- a7/a8: softmax + soft-argmin + photometric confidence ------------------------------------------------------ */
 /* cost [B][D][H][W] fp32; depth [B][D] or [B][D][H][W]; outputs (any may be NULL): depth_out [B][H][W] fp32,

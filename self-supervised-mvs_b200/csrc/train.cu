@@ -1,0 +1,490 @@
+// train.cu — the training half of the regularisation U-Net with 16-bit activations (fp32 master weights, fp32 accumulation):
+//
+//   forward   z = conv(x)            tcgen05 kernel of conv3d_tc.cu, no affine (scale/shift NULL)
+//             sums = stats(z)        mvs_bn_stats_t      per-channel sum / sum of squares, fp64 accumulation across blocks
+//             a, b, mean, invstd     mvs_bn_finalize     batch statistics -> per-channel affine, running-stat update
+//             y = relu(z a + b) + s  mvs_bn_act_fwd_t
+//   backward  red = reduce(z, gy)    mvs_bn_act_bwd_reduce_t   sum g, sum g xhat  (g = gy [z a + b > 0])
+//             gz, ggamma, gbeta      mvs_bn_act_bwd_apply_t
+//             gx = conv^T(gz)        tcgen05 kernel again with the adjoint tap program (the same torch weight packed under the
+//                                    opposite `transposed` flag), no entry point of its own
+//             gw = x (*) gz          mvs_conv3d_wgrad_mma      this file: warp-level tensor-core MMAs (mma.sync m16n8k16)
+//
+// Why the weight gradient is NOT a tcgen05 kernel: gw[tap][ci][co] = sum_voxels x[v + tap][ci] gz[v][co] is a GEMM whose M x N is
+// at most 64 x 64 (per tap) and whose K is the voxel count.  One tcgen05.mma covers K = 16 and costs >= ~32 cycles of operand
+// fetch whatever M x N is (tools/umma_bench.cu), so at M x N = 32 x 8 (conv0, 68 % of the flops) it would run at ~120 MAC/clk per
+// SM, ten times below the forward kernel; four independently issuing warp schedulers doing m16n8k16 MMAs on shifted views of one
+// shared-memory tile are the right tool for tiny-MN / huge-K products.
+// Reference: the autograd of ConvBnReLU3D / ConvTranspose3d + BatchNorm3d + ReLU, jdacs/models/module.py:35-42, mvsnet.py:37-74,
+// jdacs-ms/models/network.py:44-74 (PyTorch derives these gradients; nothing is written out in the reference).
+#include "mvs_rt.h"
+
+// ------------------------------------------------------------------------------------------------ batch-norm passes, any storage type
+// C8 volumes [B][C/8][S][8]; blockIdx.y = b * CB + cb; threads stride over s.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_t_kernel(const T* __restrict__ z, double* __restrict__ sums, int C, int64_t S) {
+    const int CB = C / 8;
+    const int cb = blockIdx.y % CB;
+    const int64_t base = (int64_t)blockIdx.y * S;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+        V8<T>::load(z + (base + s) * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s1[k] += v[k]; s2[k] += v[k] * v[k]; }
+    }
+    // a thread sums <= ~16 values and a warp 32 threads in fp32; everything above that is accumulated in fp64, so the variance
+    // S2/M - (S1/M)^2 is formed from sums that carry ~1e-7 relative error each (cancellation at |mean| >> std)
+#ifndef MVS_CPU_EMU
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o); s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o); }
+    if ((threadIdx.x & 31) != 0) return;
+#endif
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(sums + cb * 8 + k, (double)s1[k]); atomicAdd(sums + C + cb * 8 + k, (double)s2[k]); }
+}
+
+// sums -> a = gamma * invstd, b = beta - mean * a, mean, invstd (fp32), and the running statistics exactly as nn.BatchNorm3d
+// updates them in training mode (momentum, unbiased variance).  One thread per channel.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, double count, float* __restrict__ a, float* __restrict__ b,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float av = gamma[c] * is;
+    a[c] = av; b[c] = beta[c] - (float)m * av; mean[c] = (float)m; invstd[c] = is;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (count / (count > 1.0 ? count - 1.0 : 1.0)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_t_kernel(const T* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b, const T* __restrict__ skip,
+                    T* __restrict__ y, int C, int64_t S, int64_t total, int relu) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cb = (int)((i / S) % (C / 8));
+    float v[8];
+    V8<T>::load(z + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float o = v[k] * __ldg(a + cb * 8 + k) + __ldg(b + cb * 8 + k);
+        if (relu) o = fmaxf(o, 0.f);
+        v[k] = o;
+    }
+    if (skip) {
+        float sv[8];
+        V8<T>::load(skip + i * 8, sv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += sv[k];
+    }
+    V8<T>::store(y + i * 8, v);
+}
+
+// g = gy [z a + b > 0];  red[0][c] += g (= grad beta), red[1][c] += g * xhat (= grad gamma), xhat = (z - mean) invstd
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_t_kernel(const T* __restrict__ z, const T* __restrict__ gy, const float* __restrict__ a, const float* __restrict__ b,
+                           const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ red, int C,
+                           int64_t S, int relu) {
+    const int CB = C / 8;
+    const int cb = blockIdx.y % CB;
+    const int64_t base = (int64_t)blockIdx.y * S;
+    float av[8], bv[8], m[8], is[8], r0[8], r1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cb * 8 + k;
+        av[k] = __ldg(a + c); bv[k] = __ldg(b + c); m[k] = __ldg(mean + c); is[k] = __ldg(invstd + c);
+        r0[k] = 0.f; r1[k] = 0.f;
+    }
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        float v[8], g[8];
+        V8<T>::load(z + (base + s) * 8, v);
+        V8<T>::load(gy + (base + s) * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gg = (relu && !(v[k] * av[k] + bv[k] > 0.f)) ? 0.f : g[k];
+            r0[k] += gg; r1[k] += gg * ((v[k] - m[k]) * is[k]);
+        }
+    }
+#ifndef MVS_CPU_EMU
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { r0[k] += __shfl_xor_sync(0xffffffffu, r0[k], o); r1[k] += __shfl_xor_sync(0xffffffffu, r1[k], o); }
+    if ((threadIdx.x & 31) != 0) return;
+#endif
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(red + cb * 8 + k, (double)r0[k]); atomicAdd(red + C + cb * 8 + k, (double)r1[k]); }
+}
+
+// batch statistics: gz = a (g - red0/M - xhat red1/M);  frozen statistics (eval-mode fine-tuning): gz = a g.
+// Block 0 also hands out grad_gamma = red1, grad_beta = red0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_t_kernel(const T* __restrict__ z, const T* __restrict__ gy, const float* __restrict__ a, const float* __restrict__ b,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ red,
+                          T* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta, int C, int64_t S, int64_t total,
+                          double inv_m, int relu, int frozen) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && (int)threadIdx.x < C) {
+        if (ggamma) ggamma[threadIdx.x] = (float)red[C + threadIdx.x];
+        if (gbeta) gbeta[threadIdx.x] = (float)red[threadIdx.x];
+    }
+    if (i >= total) return;
+    const int cb = (int)((i / S) % (C / 8));
+    float v[8], g[8];
+    V8<T>::load(z + i * 8, v);
+    V8<T>::load(gy + i * 8, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cb * 8 + k;
+        const float av = __ldg(a + c);
+        const float gg = (relu && !(v[k] * av + __ldg(b + c) > 0.f)) ? 0.f : g[k];
+        if (frozen) { v[k] = av * gg; continue; }
+        const float xh = (v[k] - __ldg(mean + c)) * __ldg(invstd + c);
+        v[k] = av * (gg - (float)(red[c] * inv_m) - xh * (float)(red[C + c] * inv_m));
+    }
+    V8<T>::store(gz + i * 8, v);
+}
+
+// plain fp32 [n] -> C8 block [n][8] with the value in channel 0 (the gradient of the single-channel `prob` output)
+template <typename T>
+__global__ void lift_c1_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[8] = {__ldg(src + i), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    V8<T>::store(dst + i * 8, v);
+}
+
+static int check_bn_t(const char* who, int B, int C, int64_t S) {
+    MVS_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && C <= 256 && S > 0, MVS_E_SHAPE, "%s: bad dims (C must be a multiple of 8, <= 256)", who);
+    MVS_REQUIRE((int64_t)B * (C / 8) <= 65535, MVS_E_SHAPE, "%s: B*C/8 too large for the launch grid", who);
+    return MVS_OK;
+}
+
+extern "C" int mvs_bn_stats_t(const void* z, int dtype, double* sums, int B, int C, int64_t S, void* stream) {
+    MVS_REQUIRE(z && sums, MVS_E_ARG, "mvs_bn_stats_t: null pointer");
+    int rc = check_bn_t("mvs_bn_stats_t", B, C, S);
+    if (rc) return rc;
+    unsigned bx = mvs_cdiv(S, 256 * 16);
+    if (bx > 2048) bx = 2048;
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(bn_stats_t_kernel<T>, dim3(bx, (unsigned)(B * (C / 8))), dim3(256), stream, (const T*)z, sums, C, S));
+    return MVS_CHECK_LAUNCH("mvs_bn_stats_t");
+}
+
+extern "C" int mvs_bn_finalize(const double* sums, const float* gamma, const float* beta, float eps, float momentum, double count,
+                               float* a, float* b, float* mean, float* invstd, float* running_mean, float* running_var, int C,
+                               void* stream) {
+    MVS_REQUIRE(sums && gamma && beta && a && b && mean && invstd, MVS_E_ARG, "mvs_bn_finalize: null pointer");
+    MVS_REQUIRE(C > 0 && count >= 1.0, MVS_E_SHAPE, "mvs_bn_finalize: bad dims");
+    MVS_LAUNCH(bn_finalize_kernel, dim3(mvs_cdiv(C, 64)), dim3(64), stream, sums, gamma, beta, eps, momentum, count, a, b, mean, invstd,
+               running_mean, running_var, C);
+    return MVS_CHECK_LAUNCH("mvs_bn_finalize");
+}
+
+extern "C" int mvs_bn_act_fwd_t(const void* z, const float* a, const float* b, const void* skip, void* y, int dtype, int B, int C,
+                                int64_t S, int relu, void* stream) {
+    MVS_REQUIRE(z && a && b && y, MVS_E_ARG, "mvs_bn_act_fwd_t: null pointer");
+    int rc = check_bn_t("mvs_bn_act_fwd_t", B, C, S);
+    if (rc) return rc;
+    const int64_t total = (int64_t)B * (C / 8) * S;
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(bn_act_fwd_t_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, (const T*)z, a, b,
+                                            (const T*)skip, (T*)y, C, S, total, relu));
+    return MVS_CHECK_LAUNCH("mvs_bn_act_fwd_t");
+}
+
+extern "C" int mvs_bn_act_bwd_reduce_t(const void* z, const void* grad_y, const float* a, const float* b, const float* mean,
+                                       const float* invstd, double* red, int dtype, int B, int C, int64_t S, int relu, void* stream) {
+    MVS_REQUIRE(z && grad_y && a && b && mean && invstd && red, MVS_E_ARG, "mvs_bn_act_bwd_reduce_t: null pointer");
+    int rc = check_bn_t("mvs_bn_act_bwd_reduce_t", B, C, S);
+    if (rc) return rc;
+    unsigned bx = mvs_cdiv(S, 256 * 16);
+    if (bx > 2048) bx = 2048;
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(bn_act_bwd_reduce_t_kernel<T>, dim3(bx, (unsigned)(B * (C / 8))), dim3(256), stream, (const T*)z,
+                                            (const T*)grad_y, a, b, mean, invstd, red, C, S, relu));
+    return MVS_CHECK_LAUNCH("mvs_bn_act_bwd_reduce_t");
+}
+
+extern "C" int mvs_bn_act_bwd_apply_t(const void* z, const void* grad_y, const float* a, const float* b, const float* mean,
+                                      const float* invstd, const double* red, void* grad_z, float* grad_gamma, float* grad_beta,
+                                      int dtype, int B, int C, int64_t S, int relu, int frozen, void* stream) {
+    MVS_REQUIRE(z && grad_y && a && b && mean && invstd && red && grad_z, MVS_E_ARG, "mvs_bn_act_bwd_apply_t: null pointer");
+    int rc = check_bn_t("mvs_bn_act_bwd_apply_t", B, C, S);
+    if (rc) return rc;
+    const int64_t total = (int64_t)B * (C / 8) * S;
+    const double inv_m = 1.0 / ((double)B * (double)S);
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(bn_act_bwd_apply_t_kernel<T>, dim3(mvs_cdiv(total, 256)), dim3(256), stream, (const T*)z,
+                                            (const T*)grad_y, a, b, mean, invstd, red, (T*)grad_z, grad_gamma, grad_beta, C, S, total,
+                                            inv_m, relu, frozen));
+    return MVS_CHECK_LAUNCH("mvs_bn_act_bwd_apply_t");
+}
+
+extern "C" int mvs_lift_c1(const float* src, void* dst, int dtype, int64_t n, void* stream) {
+    MVS_REQUIRE(src && dst, MVS_E_ARG, "mvs_lift_c1: null pointer");
+    MVS_REQUIRE(n > 0, MVS_E_SHAPE, "mvs_lift_c1: empty tensor");
+    MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(lift_c1_kernel<T>, dim3(mvs_cdiv(n, 256)), dim3(256), stream, src, (T*)dst, n));
+    return MVS_CHECK_LAUNCH("mvs_lift_c1");
+}
+
+#ifndef MVS_CPU_EMU
+// ------------------------------------------------------------------------------------------------ weight gradient on tensor cores
+// grad[pc][qc][tap] = sum_b sum_p P[b][p][pc] Q[b][p * stride - 1 + k][qc]            (the formulation of conv3d_wgrad_kernel)
+//   Conv3d          : P = gz (output grid, Cout), Q = x  (input grid, Cin)   -> grad_w [Cout][Cin][27]
+//   ConvTranspose3d : P = x  (input grid, Cin),   Q = gz (output grid, Cout) -> grad_w [Cin][Cout][27]
+// As MMAs:  D[m][n] += A[m][k] B[k][n] with k = 16 consecutive positions of a P tile, m = 16 channels of one tensor, n = 8 channels
+// of the other, one accumulator tile per filter tap.  Both tensors are staged per step as [channel block][position][8] (16-byte
+// rows, the C8 layout itself), so either can be the M side: ldmatrix.trans turns 8 position rows x 8 channels into the fragment
+// of the channel-major operand, and the row ADDRESSES carry the tap shift and the stride (Q row = (hh s + kh) TWq + (ww s + kw)).
+// A CTA owns one tap group (all 27 taps, the 9 taps of one kd, or the 3 taps of one (kd, kh): whatever keeps the accumulators in
+// registers) and walks P tiles of 8 x 32 positions; its 8 warps split the (tap, m-tile) units and each loops over all 16 k-steps.
+constexpr int kWgTH = 8, kWgTW = 32, kWgWarps = 8;
+
+struct WgParams {
+    const void* P; const void* Q; float* grad;
+    int B, PCB, QCB, PCreal, QCreal;       // channel blocks of P / Q; real channel counts (padding blocks are not written)
+    int Dp, Hp, Wp, Dq, Hq, Wq, stride;
+    int a_is_p;                            // M side: 1 = P, 0 = Q
+    int MT, NB;                            // m-tiles (16 channels) of the M side, n-blocks (8 channels) of the N side
+    int tpc, ngroups;                      // taps per CTA (27 / 9 / 3) and tap groups (1 / 3 / 9)
+    int nht, nwt, ntiles;                  // P tiles per plane and in total (B * Dp * nht * nwt)
+    int THq, TWq;                          // staged Q tile (with halo)
+    int q_rows;                            // THq * TWq
+};
+
+__device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t (&r)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+template <typename T> __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]);
+template <> __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <> __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// UPW = (tap, m-tile) units per warp, NB = n-blocks: UPW * NB * 4 accumulator registers per thread.
+template <typename T, int UPW, int NB>
+__global__ void __launch_bounds__(kWgWarps * 32, 2)
+conv3d_wgrad_mma_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ __align__(128) uint8_t wg_smem[];
+    uint8_t* sP = wg_smem;                                              // [PCB][TH * TW][8]
+    uint8_t* sQ = wg_smem + (size_t)p.PCB * kWgTH * kWgTW * 16;         // [QCB][THq * TWq][8]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.y;                                       // tap group
+    const int nkd = p.tpc == 27 ? 3 : 1, nkh = p.tpc >= 9 ? 3 : 1;
+    const int kd0 = p.tpc == 27 ? 0 : (p.tpc == 9 ? group : group / 3), kh0 = p.tpc >= 9 ? 0 : group % 3;
+    const int units = p.tpc * p.MT;                                     // unit u = tap_local * MT + mt, tap_local = (kdi * nkh + khi) * 3 + kw
+
+    float acc[UPW][NB][4];
+#pragma unroll
+    for (int j = 0; j < UPW; ++j)
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][n][e] = 0.f;
+
+    const uint32_t sP32 = wg_smem_u32(sP), sQ32 = wg_smem_u32(sQ);
+    const uint32_t p_blk = kWgTH * kWgTW * 16u, q_blk = (uint32_t)p.q_rows * 16u;      // bytes per channel block
+    const int lj = lane >> 3, li = lane & 7;          // ldmatrix: this lane supplies row li of matrix lj
+    const bool a_is_p = p.a_is_p != 0;
+    const int MCB = a_is_p ? p.PCB : p.QCB, NCB = a_is_p ? p.QCB : p.PCB;              // channel blocks of the M / N side
+    // Units of this warp: u = warp + 8 j, tap_local = u / MT, m-tile = u % MT = warp % MT for every j (MT divides 8).
+    const int mt = warp % p.MT;
+    const bool half_m = MCB * 8 < (mt + 1) * 16;      // an 8-channel M side: rows 8..15 of the tile do not exist
+    // Lane-constant parts of the row addresses.  P rows: position q = hh * TW + ww.  Q rows: (hh s + kh) TWq + ww s + kw.
+    //   A matrices (x4): j = 0: (block 2 mt, k 0-7), 1: (2 mt + 1, k 0-7), 2: (2 mt, k 8-15), 3: (2 mt + 1, k 8-15)
+    //   B matrices (x4): j = 0: (block n, k 0-7), 1: (n, k 8-15), 2: (n + 1, k 0-7), 3: (n + 1, k 8-15)
+    const int a_cb = min(2 * mt + (lj & 1), MCB - 1), a_k = (lj >> 1) * 8 + li;
+    const int b_dn = lj >> 1, b_k = (lj & 1) * 8 + li;
+    uint32_t unit_shift[UPW];                         // byte offset of the unit's tap inside the Q tile: (kh TWq + kw) * 16
+    int unit_kd[UPW];
+#pragma unroll
+    for (int j = 0; j < UPW; ++j) {
+        const int u = warp + kWgWarps * j, tl = u / p.MT;
+        const int kw = tl % 3, khi = (tl / 3) % nkh;
+        unit_kd[j] = u < units ? tl / (3 * nkh) : -1;
+        unit_shift[j] = (uint32_t)((kh0 + khi) * p.TWq + kw) * 16u;
+    }
+
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        int tt = t;
+        const int wt = tt % p.nwt; tt /= p.nwt;
+        const int ht = tt % p.nht; tt /= p.nht;
+        const int dp = tt % p.Dp;
+        const int b = tt / p.Dp;
+        const int h0 = ht * kWgTH, w0 = wt * kWgTW;
+        bool p_staged = false;
+        for (int kdi = 0; kdi < nkd; ++kdi) {
+            const int qd = dp * p.stride - 1 + kd0 + kdi;
+            if (qd < 0 || qd >= p.Dq) continue;                         // block-uniform: this tap plane lies in the zero padding
+            __syncthreads();                                            // everyone has finished reading the previous tiles
+            if (!p_staged) {                                            // the P tile (zeros outside the volume), once per tile
+                const int nP = p.PCB * kWgTH * kWgTW;
+                for (int i = threadIdx.x; i < nP; i += blockDim.x) {
+                    const int pcb = i / (kWgTH * kWgTW), r = i - pcb * (kWgTH * kWgTW);
+                    const int hh = r / kWgTW, ww = r - hh * kWgTW;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (h0 + hh < p.Hp && w0 + ww < p.Wp)
+                        v = __ldg(reinterpret_cast<const uint4*>(p.P) + ((((int64_t)b * p.PCB + pcb) * p.Dp + dp) * p.Hp + h0 + hh) * p.Wp + w0 + ww);
+                    *reinterpret_cast<uint4*>(sP + (size_t)i * 16) = v;
+                }
+                p_staged = true;
+            }
+            {                                                           // plane qd of the Q tile with its halo
+                const int nQ = p.QCB * p.q_rows;
+                const int gh0 = h0 * p.stride - 1, gw0 = w0 * p.stride - 1;
+                for (int i = threadIdx.x; i < nQ; i += blockDim.x) {
+                    const int qcb = i / p.q_rows, r = i - qcb * p.q_rows;
+                    const int qh = r / p.TWq, qw = r - qh * p.TWq;
+                    const int gh = gh0 + qh, gw = gw0 + qw;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (gh >= 0 && gh < p.Hq && gw >= 0 && gw < p.Wq)
+                        v = __ldg(reinterpret_cast<const uint4*>(p.Q) + ((((int64_t)b * p.QCB + qcb) * p.Dq + qd) * p.Hq + gh) * p.Wq + gw);
+                    *reinterpret_cast<uint4*>(sQ + (size_t)i * 16) = v;
+                }
+            }
+            __syncthreads();
+            // ---- MMAs of this kd phase: 16 k-steps of 16 positions; the unshifted (P) operand is fetched once per k-step
+            for (int ks = 0; ks < kWgTH * kWgTW / 16; ++ks) {
+                const int hh = ks / (kWgTW / 16), wwb = (ks % (kWgTW / 16)) * 16;
+                const uint32_t p_row = (uint32_t)(hh * kWgTW + wwb) * 16u;                            // + k * 16
+                const uint32_t q_row = (uint32_t)(hh * p.stride * p.TWq + wwb * p.stride) * 16u;      // + k * stride * 16 + unit_shift
+                if (a_is_p) {
+                    uint32_t afrag[4];
+                    ldmatrix_x4_trans(sP32 + (uint32_t)a_cb * p_blk + p_row + (uint32_t)a_k * 16u, afrag);
+                    if (half_m) { afrag[1] = 0u; afrag[3] = 0u; }
+#pragma unroll
+                    for (int j = 0; j < UPW; ++j) {
+                        if (unit_kd[j] != kdi) continue;
+                        const uint32_t qa = sQ32 + q_row + unit_shift[j] + (uint32_t)(b_k * p.stride) * 16u;
+#pragma unroll
+                        for (int n = 0; n < NB; n += 2) {
+                            uint32_t bfrag[4];
+                            ldmatrix_x4_trans(qa + (uint32_t)min(n + b_dn, NCB - 1) * q_blk, bfrag);
+                            const uint32_t b0[2] = {bfrag[0], bfrag[1]}, b1[2] = {bfrag[2], bfrag[3]};
+                            mma_16816<T>(acc[j][n], afrag, b0);
+                            if (n + 1 < NB) mma_16816<T>(acc[j][n + 1 < NB ? n + 1 : n], afrag, b1);
+                        }
+                    }
+                } else {
+                    uint32_t bfr[NB][2];
+#pragma unroll
+                    for (int n = 0; n < NB; n += 2) {
+                        uint32_t bfrag[4];
+                        ldmatrix_x4_trans(sP32 + (uint32_t)min(n + b_dn, NCB - 1) * p_blk + p_row + (uint32_t)b_k * 16u, bfrag);
+                        bfr[n][0] = bfrag[0]; bfr[n][1] = bfrag[1];
+                        if (n + 1 < NB) { bfr[n + 1 < NB ? n + 1 : n][0] = bfrag[2]; bfr[n + 1 < NB ? n + 1 : n][1] = bfrag[3]; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < UPW; ++j) {
+                        if (unit_kd[j] != kdi) continue;
+                        uint32_t afrag[4];
+                        ldmatrix_x4_trans(sQ32 + (uint32_t)a_cb * q_blk + q_row + unit_shift[j] + (uint32_t)(a_k * p.stride) * 16u, afrag);
+                        if (half_m) { afrag[1] = 0u; afrag[3] = 0u; }
+#pragma unroll
+                        for (int n = 0; n < NB; ++n) mma_16816<T>(acc[j][n], afrag, bfr[n]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- write-out: C fragment (m = lane / 4 (+ 8), n = 2 (lane % 4) + {0, 1}) -> grad[pc][qc][tap], torch layout
+    const int QC = p.QCreal, PC = p.PCreal;
+#pragma unroll
+    for (int j = 0; j < UPW; ++j) {
+        const int u = warp + kWgWarps * j;
+        if (u >= units) continue;
+        const int tl = u / p.MT;
+        const int kw = tl % 3, khi = (tl / 3) % nkh, kdu = tl / (3 * nkh);
+        const int tap = ((kd0 + kdu) * 3 + (kh0 + khi)) * 3 + kw;
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = mt * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0), nn = n * 8 + 2 * (lane & 3) + (e & 1);
+                const int pc = p.a_is_p ? m : nn, qc = p.a_is_p ? nn : m;
+                if (pc < PC && qc < QC && acc[j][n][e] != 0.f) atomicAdd(p.grad + ((int64_t)pc * QC + qc) * 27 + tap, acc[j][n][e]);
+            }
+    }
+}
+
+extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real,
+                                    void* stream) {
+    MVS_REQUIRE(d && x && grad_z && grad_w, MVS_E_ARG, "mvs_conv3d_wgrad_mma: null pointer");
+    MVS_REQUIRE(d->dtype_in == MVS_F16 || d->dtype_in == MVS_BF16, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: 16-bit storage only (fp32 takes mvs_conv3d_bwd_weight)");
+    MVS_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->Cin <= 64 && d->Cout <= 64, MVS_E_SHAPE,
+                "mvs_conv3d_wgrad_mma: Cin=%d / Cout=%d must be multiples of 8, <= 64 (lift a single-channel gradient with mvs_lift_c1)", d->Cin, d->Cout);
+    MVS_REQUIRE(d->stride == 1 || d->stride == 2, MVS_E_SHAPE, "mvs_conv3d_wgrad_mma: stride must be 1 or 2");
+    MVS_REQUIRE(cout_real >= 1 && cout_real <= d->Cout, MVS_E_ARG, "mvs_conv3d_wgrad_mma: bad cout_real");
+    WgParams p;
+    const bool tr = d->transposed != 0;
+    p.P = tr ? x : grad_z; p.Q = tr ? grad_z : x; p.grad = grad_w;
+    p.B = d->B;
+    const int PC = tr ? d->Cin : d->Cout, QC = tr ? d->Cout : d->Cin;
+    p.PCB = PC / 8; p.QCB = QC / 8;
+    p.PCreal = tr ? d->Cin : cout_real; p.QCreal = tr ? cout_real : d->Cin;
+    p.Dp = tr ? d->Din : d->Dout; p.Hp = tr ? d->Hin : d->Hout; p.Wp = tr ? d->Win : d->Wout;
+    p.Dq = tr ? d->Dout : d->Din; p.Hq = tr ? d->Hout : d->Hin; p.Wq = tr ? d->Wout : d->Win;
+    p.stride = d->stride;
+    // M side: a tensor whose channel count is a multiple of 16 (the wider one if both are); else P with its upper half empty
+    if (PC % 16 == 0 && (QC % 16 != 0 || PC >= QC)) p.a_is_p = 1;
+    else if (QC % 16 == 0) p.a_is_p = 0;
+    else p.a_is_p = 1;
+    const int MC = p.a_is_p ? PC : QC, NC = p.a_is_p ? QC : PC;
+    p.MT = (MC + 15) / 16; p.NB = NC / 8;
+    MVS_REQUIRE(p.MT == 1 || p.MT == 2 || p.MT == 4, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: %d channels on the M side (16, 32 or 64 supported)", MC);
+    // taps per CTA: the largest group whose accumulators fit (UPW * NB <= 16 -> <= 64 registers per thread)
+    const int tpcs[3] = {27, 9, 3};
+    int upw = 0;
+    p.tpc = 0;
+    for (int i = 0; i < 3 && !p.tpc; ++i) {
+        const int u = (tpcs[i] * p.MT + kWgWarps - 1) / kWgWarps;
+        if (u * p.NB <= 16) { p.tpc = tpcs[i]; upw = u; }
+    }
+    MVS_REQUIRE(p.tpc, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: no tap grouping fits the registers for %d x %d channels", MC, NC);
+    p.ngroups = 27 / p.tpc;
+    p.nht = (p.Hp + kWgTH - 1) / kWgTH; p.nwt = (p.Wp + kWgTW - 1) / kWgTW;
+    p.ntiles = p.B * p.Dp * p.nht * p.nwt;
+    p.THq = kWgTH * p.stride + 2; p.TWq = kWgTW * p.stride + 2;
+    p.q_rows = p.THq * p.TWq;
+    const size_t smem = ((size_t)p.PCB * kWgTH * kWgTW + (size_t)p.QCB * p.q_rows) * 16;
+    MVS_REQUIRE(smem <= 113 * 1024, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tiles of %d + %d channels at stride %d need %zu bytes of shared memory", PC, QC, p.stride, smem);
+    int gx = (2 * 148 * 2 + p.ngroups - 1) / p.ngroups;
+    if (gx > p.ntiles) gx = p.ntiles;
+    const dim3 grid((unsigned)gx, (unsigned)p.ngroups);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_WG_LAUNCH(T, U, N) do { cudaFuncSetAttribute(conv3d_wgrad_mma_kernel<T, U, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                                    conv3d_wgrad_mma_kernel<T, U, N><<<grid, kWgWarps * 32, smem, st>>>(p); } while (0)
+#define MVS_WG_BY_SHAPE(T) do { \
+        if (p.NB == 1) { if (upw <= 4) MVS_WG_LAUNCH(T, 4, 1); else MVS_WG_LAUNCH(T, 7, 1); } \
+        else if (p.NB == 2) { if (upw <= 4) MVS_WG_LAUNCH(T, 4, 2); else MVS_WG_LAUNCH(T, 7, 2); } \
+        else if (p.NB == 4) { if (upw <= 2) MVS_WG_LAUNCH(T, 2, 4); else MVS_WG_LAUNCH(T, 4, 4); } \
+        else if (p.NB == 8) MVS_WG_LAUNCH(T, 2, 8); \
+        else return mvs_set_error(MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: %d n-blocks", p.NB); } while (0)
+    if (d->dtype_in == MVS_F16) MVS_WG_BY_SHAPE(__half); else MVS_WG_BY_SHAPE(__nv_bfloat16);
+#undef MVS_WG_BY_SHAPE
+#undef MVS_WG_LAUNCH
+    return MVS_CHECK_LAUNCH("mvs_conv3d_wgrad_mma");
+}
+#else
+extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc*, const void*, const void*, float*, int, void*) {
+    return mvs_set_error(MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tensor-core kernels do not exist in the emulation build");
+}
+#endif

@@ -746,6 +746,157 @@ warp_var_fwd_tma_kernel(const __grid_constant__ WvMaps maps, const T* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fused backward, 16-bit storage
+// Training path (zero-bordered C8P maps, 16-bit volumes).  Same gradient as warp_var_bwd_kernel; what differs is the scatter:
+//   * a thread owns (pixel, 8 channels) and walks the planes of its chunk.  Consecutive planes sample the SAME 2x2 source cell
+//     for several steps (the sweep moves a fraction of a pixel per plane), so the four tap contributions are accumulated in
+//     registers while the cell is unchanged and flushed with 8 vector reductions (red.global.add.v4.f32) when it changes:
+//     ~3x fewer reductions than per plane, and 4x fewer instructions than scalar atomics (32 of them per voxel and source in
+//     warp_var_bwd_kernel).  Shared-memory privatisation was rejected: fp32 atomicAdd on shared memory is a CAS loop on sm_100
+//     (ATOMS.CAST.SPIN, 2 cycles per lane), slower than REDG to L2 (1.3 cycles per lane for 4 floats).
+//   * 64 accumulator registers hold two sources, so sources are processed in groups of two, each group re-gathering all sources
+//     for S1 (the maps are L1 / L2 resident); taps are blended in fp32 with exact weights.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename T, int NS, bool REFSQ>
+__global__ void __launch_bounds__(128, 2)
+warp_var_bwd16_kernel(const T* __restrict__ gvar, const T* __restrict__ ref, SrcPtrs srcs, int nsrc, const float* __restrict__ rt,
+                      const float* __restrict__ depth, int per_pixel, float* __restrict__ gref, GradPtrs gsrcs, int B, int CB, int D,
+                      int H, int W, int dper, int align_corners) {
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int nchunk = (D + dper - 1) / dper;
+    int y = blockIdx.y;
+    const int dc = y % nchunk; y /= nchunk;
+    const int cb = y % CB;
+    const int b = y / CB;
+    const int py = p / W, px = p - py * W;
+    const int pitch = W + 2;
+    const uint32_t row_b = (uint32_t)pitch * 16u, plane_b = (uint32_t)(H + 3) * row_b;
+    const int64_t map_b = ((int64_t)b * CB + cb) * plane_b;
+    const int64_t grad_off = ((int64_t)b * CB + cb) * HW * 8;
+
+    float r[8];
+    V8<T>::load(reinterpret_cast<const T*>(reinterpret_cast<const char*>(ref) + map_b + (uint32_t)((py + 1) * pitch + px + 1) * 16u), r);
+    const float sx = align_corners ? 1.f : (float)W / (float)(W - 1), sy = align_corners ? 1.f : (float)H / (float)(H - 1);
+    const float oxy = (align_corners ? 0.f : -0.5f) + 1.f;
+    float rx[NS], ry[NS], rz[NS], tx[NS], ty[NS], tz[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if (s < nsrc) {
+            const float* m = rt + ((int64_t)s * B + b) * 12;
+            float ray[3];
+            pixel_ray(m, (float)px, (float)py, ray);
+            rx[s] = ray[0] * sx; ry[s] = ray[1] * sy; rz[s] = ray[2];
+            tx[s] = __ldg(m + 9) * sx; ty[s] = __ldg(m + 10) * sy; tz[s] = __ldg(m + 11);
+        }
+    const float xmax = (float)(W + 1), ymax = (float)(H + 1);
+    const float inv_n = 1.f / (float)(nsrc + 1);
+    float gr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gr[k] = 0.f;
+    const int d_begin = dc * dper, d_end = min(D, d_begin + dper);
+
+    for (int g0 = 0; g0 < nsrc; g0 += 2) {
+        int cell[2] = {-1, -1};                  // padded-map index (yi * pitch + xi) of the cell the accumulators belong to
+        float acc[2][4][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[q][t][k] = 0.f;
+        auto flush = [&](int q) {
+            if (cell[q] < 0) return;
+            float* gs = gsrcs.p[g0 + q] + grad_off;
+            const int yi = cell[q] / pitch, xi = cell[q] - yi * pitch;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int yy = yi + (t >> 1) - 1, xx = xi + (t & 1) - 1;       // pixel of the un-bordered gradient map
+                if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) {
+                    float* o = gs + (int64_t)(yy * W + xx) * 8;
+                    red_add_v4(o, acc[q][t][0], acc[q][t][1], acc[q][t][2], acc[q][t][3]);
+                    red_add_v4(o + 4, acc[q][t][4], acc[q][t][5], acc[q][t][6], acc[q][t][7]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[q][t][k] = 0.f;
+            }
+        };
+        const bool on0 = gsrcs.p[g0] != nullptr, on1 = g0 + 1 < nsrc && gsrcs.p[g0 + 1] != nullptr;
+        for (int d = d_begin; d < d_end; ++d) {
+            const float dv = per_pixel ? __ldg(depth + ((int64_t)b * D + d) * HW + p) : __ldg(depth + (int64_t)b * D + d);
+            float g[8];
+            V8<T>::load(gvar + ((((int64_t)b * CB + cb) * D + d) * HW + p) * 8, g);
+            float s1[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s1[k] = REFSQ ? r[k] * r[k] : r[k];
+            float ws[2][8], wt[2][4];
+            int cid[2] = {-1, -1};
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                if (s < nsrc) {
+                    const float pz = fmaf(rz[s], dv, tz[s]);
+                    float iz;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(pz));
+                    const float ix = fminf(fmaxf(fmaf(fmaf(rx[s], dv, tx[s]), iz, oxy), 0.f), xmax);
+                    const float iy = fminf(fmaxf(fmaf(fmaf(ry[s], dv, ty[s]), iz, oxy), 0.f), ymax);
+                    const float fxm = floorf(ix), fym = floorf(iy);
+                    const int xi = (int)fxm, yi = (int)fym;
+                    const float wx = ix - fxm, wy = iy - fym;
+                    const float w11 = wx * wy, w10 = wx - w11, w01 = wy - w11, w00 = (1.f - wx) - w01;
+                    const char* base = reinterpret_cast<const char*>(srcs.p[s]) + map_b + (uint32_t)(yi * pitch + xi) * 16u;
+                    float a0[8], a1[8], a2[8], a3[8], v[8];
+                    V8<T>::load(reinterpret_cast<const T*>(base), a0);
+                    V8<T>::load(reinterpret_cast<const T*>(base + 16), a1);
+                    V8<T>::load(reinterpret_cast<const T*>(base + row_b), a2);
+                    V8<T>::load(reinterpret_cast<const T*>(base + row_b + 16), a3);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { v[k] = fmaf(a3[k], w11, fmaf(a2[k], w01, fmaf(a1[k], w10, a0[k] * w00))); s1[k] += v[k]; }
+                    if (s == g0 || s == g0 + 1) {
+                        const int q = s - g0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ws[q][k] = v[k];
+                        wt[q][0] = w00; wt[q][1] = w10; wt[q][2] = w01; wt[q][3] = w11;
+                        cid[q] = yi * pitch + xi;
+                    }
+                }
+            }
+            float m2[8];      // 2 S1 / N^2
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m2[k] = 2.f * s1[k] * inv_n * inv_n;
+            if (g0 == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float dr = REFSQ ? (2.f * r[k] * inv_n - m2[k] * 2.f * r[k]) : (2.f * r[k] * inv_n - m2[k]);
+                    gr[k] += g[k] * dr;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q == 0 ? on0 : on1) {
+                    if (cid[q] != cell[q]) { flush(q); cell[q] = cid[q]; }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float c = g[k] * (2.f * ws[q][k] * inv_n - m2[k]);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) acc[q][t][k] = fmaf(wt[q][t], c, acc[q][t][k]);
+                    }
+                }
+            }
+        }
+        if (on0) flush(0);
+        if (on1) flush(1);
+    }
+    if (gref != nullptr) {
+        float* o = gref + grad_off + (int64_t)p * 8;
+        red_add_v4(o, gr[0], gr[1], gr[2], gr[3]);
+        red_add_v4(o + 4, gr[4], gr[5], gr[6], gr[7]);
+    }
+}
+
 typedef CUresult (*WvEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -894,6 +1045,22 @@ extern "C" int mvs_warp_var_bwd(const void* grad_var, const void* ref, const voi
     const int CB = C / 8, HW = H * W;
     const int dper = depth_chunk(D, HW, B, CB);
     const dim3 grid(mvs_cdiv(HW, 128), (unsigned)(B * CB * ((D + dper - 1) / dper)));
+#ifndef MVS_CPU_EMU
+    if (dtype_in == dtype_out && dtype_in != MVS_F32 && pad) {
+        // the training path: 16-bit storage, zero-bordered maps -> register-merged vector reductions
+        MVS_REQUIRE((int64_t)(H + 3) * (W + 2) * 16 < (1ll << 31), MVS_E_SHAPE, "mvs_warp_var_bwd: maps too large");
+#define MVS_WB_ARGS(T) (const T*)grad_var, (const T*)ref, sp, nsrc, rt, depth, per_pixel, grad_ref, gp, B, CB, D, H, W, dper, align_corners
+#define MVS_WB_LAUNCH(T, NS) do { if (ref_sq_in_sum) warp_var_bwd16_kernel<T, NS, true><<<grid, 128, 0, (cudaStream_t)stream>>>(MVS_WB_ARGS(T)); \
+                                  else warp_var_bwd16_kernel<T, NS, false><<<grid, 128, 0, (cudaStream_t)stream>>>(MVS_WB_ARGS(T)); } while (0)
+#define MVS_WB_BY_NS(T) do { if (nsrc <= 2) MVS_WB_LAUNCH(T, 2); else if (nsrc <= 4) MVS_WB_LAUNCH(T, 4); else if (nsrc <= 6) MVS_WB_LAUNCH(T, 6); \
+                             else MVS_WB_LAUNCH(T, 8); } while (0)
+        if (dtype_in == MVS_F16) MVS_WB_BY_NS(__half); else MVS_WB_BY_NS(__nv_bfloat16);
+#undef MVS_WB_BY_NS
+#undef MVS_WB_LAUNCH
+#undef MVS_WB_ARGS
+        return MVS_CHECK_LAUNCH("mvs_warp_var_bwd");
+    }
+#endif
     MVS_DISPATCH_DTYPE(dtype_in, TI, MVS_DISPATCH_DTYPE(dtype_out, TO,
         MVS_LAUNCH((warp_var_bwd_kernel<TI, TO>), grid, dim3(128), stream, (const TO*)grad_var, (const TI*)ref, sp, nsrc, rt,
                    depth, per_pixel, grad_ref, gp, B, CB, D, H, W, dper, align_corners, ref_sq_in_sum, pad)));

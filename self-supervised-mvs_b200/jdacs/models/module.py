@@ -57,9 +57,9 @@ class ConvBnReLU3D(nn.Module):
         self._cache.clear()     # everything derived from the weights is re-packed on the next eval forward
         return super().train(mode)
 
-    def forward(self, x, skip=None, algo=0):
+    def forward(self, x, skip=None, algo=0, frozen_grad=False):
         plain = x.dim() == 5
-        y = regnet.conv_bn_relu(regnet.as_c8(x, torch.float32), self.conv, self.bn, self.training, self._cache, skip, algo)
+        y = regnet.conv_bn_relu(regnet.as_c8(x, torch.float32), self.conv, self.bn, self.training, self._cache, skip, algo, frozen_grad)
         return regnet.unpack_c8_grad(y) if plain else y
 
 

@@ -10,6 +10,8 @@ What runs where:
 """
 from __future__ import annotations
 
+import warnings
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -132,25 +134,27 @@ class CostRegNet(nn.Module):
         self._cache.clear()
         return super().train(mode)
 
-    def forward(self, x):
+    def forward(self, x, frozen_grad=False):
+        """frozen_grad: eval-mode BatchNorm (running statistics) but differentiable -- fine-tuning under module.eval()."""
         plain = x.dim() == 5
         tr = self.training
-        x = regnet.as_c8(x, torch.float32 if tr else (self.act_dtype or torch.float32))
+        fg = frozen_grad and not tr
+        x = regnet.as_c8(x, torch.float32 if (tr or fg) else (self.act_dtype or torch.float32))
         for n in (x.shape[2], x.shape[3], x.shape[4]):
             if n % 8:
                 raise ValueError("CostRegNet needs D, H, W divisible by 8 (got %s), as the reference does" % (tuple(x.shape[2:5]),))
-        if not tr and self.act_dtype is not None and x.dtype != self.act_dtype:
+        if not tr and not fg and self.act_dtype is not None and x.dtype != self.act_dtype:
             raise ValueError("variance volume is %s but CostRegNet.act_dtype is %s" % (x.dtype, self.act_dtype))
         a = self.algo
-        conv0 = self.conv0(x, None, a)
-        conv2 = self.conv2(self.conv1(conv0, None, a), None, a)
-        conv4 = self.conv4(self.conv3(conv2, None, a), None, a)
-        y = self.conv6(self.conv5(conv4, None, a), None, a)
+        conv0 = self.conv0(x, None, a, fg)
+        conv2 = self.conv2(self.conv1(conv0, None, a, fg), None, a, fg)
+        conv4 = self.conv4(self.conv3(conv2, None, a, fg), None, a, fg)
+        y = self.conv6(self.conv5(conv4, None, a, fg), None, a, fg)
         c = self._cache
-        y = regnet.conv_bn_relu(y, self.conv7[0], self.conv7[1], tr, c, conv4, a)    # conv4 + relu(bn(convT(x)))
-        y = regnet.conv_bn_relu(y, self.conv9[0], self.conv9[1], tr, c, conv2, a)
-        y = regnet.conv_bn_relu(y, self.conv11[0], self.conv11[1], tr, c, conv0, a)
-        out = regnet.conv_bias(y, self.prob, tr, c, a)                                # [B,D,H,W] fp32
+        y = regnet.conv_bn_relu(y, self.conv7[0], self.conv7[1], tr, c, conv4, a, fg)    # conv4 + relu(bn(convT(x)))
+        y = regnet.conv_bn_relu(y, self.conv9[0], self.conv9[1], tr, c, conv2, a, fg)
+        y = regnet.conv_bn_relu(y, self.conv11[0], self.conv11[1], tr, c, conv0, a, fg)
+        out = regnet.conv_bias(y, self.prob, tr, c, a, fg)                                # [B,D,H,W] fp32
         return out.unsqueeze(1) if plain else out
 
 
@@ -178,12 +182,18 @@ class MVSNet(nn.Module):
     forward(imgs [B,N,3,H,W], proj_matrices [B,N,4,4], depth_values [B,D])
         -> {"depth": [B,H/4,W/4], "photometric_confidence": [B,H/4,W/4]}
 
-    Extra, optional knobs (defaults reproduce the reference as it runs on torch >= 1.3):
-      volume_dtype   storage of the cost volume / activations in eval mode (fp32 | fp16 | bf16); training is fp32
+    Extra, optional knobs:
+      volume_dtype   storage of feature maps / cost volume / U-Net activations in eval mode.  None (default) = fp16 on a CUDA device
+                     (every stage on the tcgen05 / TMA kernels; depth within the 16-bit storage floor of the fp32 reference, see
+                     profiles/r02_parity.json), fp32 on the host-emulation build.  torch.float32 = the reference's arithmetic
+                     (fp32 SIMT kernels, 1e-5 relative on depth).
+      train_dtype    the same for training mode.  None (default) = bf16 activations on a CUDA device with fp32 master weights,
+                     fp32 accumulation and fp64 BatchNorm statistics (tensor-core forward / dgrad / wgrad); torch.float32 = fp32.
       align_corners  True = the geometry the authors intended on torch 1.1 (hazard H1)
+    Gradients under module.eval() (fine-tuning with frozen BatchNorm statistics) are supported with 16-bit train_dtype.
     """
 
-    def __init__(self, refine=True, volume_dtype=torch.float32, align_corners=ALIGN_CORNERS):
+    def __init__(self, refine=True, volume_dtype=None, align_corners=ALIGN_CORNERS, train_dtype=None):
         super().__init__()
         self.refine = refine
         self.feature = FeatureNet()
@@ -191,6 +201,7 @@ class MVSNet(nn.Module):
         if self.refine:
             self.refine_network = RefineNet()
         self.volume_dtype = volume_dtype
+        self.train_dtype = train_dtype
         self.align_corners = align_corners
         self.feature_autocast = True   # eval + 16-bit volume, feature_tc off: FeatureNet as folded 16-bit library convolutions
         self.feature_tc = True         # eval + 16-bit volume: FeatureNet on the repo's tcgen05 convolution kernel
@@ -201,12 +212,25 @@ class MVSNet(nn.Module):
         b, n = imgs.shape[0], imgs.shape[1]
         # step 1. feature extraction (library code).  In eval mode all views share one batched call; in training
         # each view is its own call, because BatchNorm2d statistics are per call in the reference (:115).
-        dt = torch.float32 if self.training else self.volume_dtype
+        auto16 = imgs.is_cuda
+        tdt = self.train_dtype if self.train_dtype is not None else (torch.bfloat16 if auto16 else torch.float32)
+        # differentiable pass: training mode, or eval mode with gradients requested (fine-tuning with frozen BatchNorm statistics,
+        # which the reference supports; wrap inference in torch.no_grad() -- as the reference's scripts do -- to get the fused path)
+        wants_grad = (not self.training) and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if wants_grad and tdt == torch.float32:
+            wants_grad = False
+            if not getattr(self, "_warned_eval_grad", False):
+                self._warned_eval_grad = True
+                warnings.warn("MVSNet.eval() with fp32 train_dtype runs the fused inference kernels: no gradient flows through the cost "
+                              "volume / CostRegNet.  Use train() or a 16-bit train_dtype for eval-mode fine-tuning.")
+        diff = self.training or wants_grad
+        dt = tdt if diff else (self.volume_dtype if self.volume_dtype is not None else (torch.float16 if auto16 else torch.float32))
         rt = ops.compose_proj(proj_matrices)
-        fast = (not self.training) and dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0
+        fast = (not diff) and dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0
         if imgs.dtype != torch.float32 and not (fast and imgs.dtype == dt):
             imgs = imgs.float()     # 16-bit images (a host pipeline may upload them so) are only consumed as such by the 16-bit fast path
-        if self.training:
+        if diff:
+            # each view is its own call in training mode: BatchNorm2d statistics are per call in the reference (:115)
             features = [self.feature(imgs[:, v]) for v in range(n)]
             # step 2. plane sweep: warp + variance, fused (:120-136)
             variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
@@ -227,8 +251,8 @@ class MVSNet(nn.Module):
             # step 2. the fused plane sweep
             variance = ops.warp_variance_maps(maps, rt, depth_values, dt, self.align_corners, False)
         # step 3. regularisation (:139-141)
-        self.cost_regularization.act_dtype = None if self.training else dt
-        cost_reg = self.cost_regularization(variance)
+        self.cost_regularization.act_dtype = None if diff else dt
+        cost_reg = self.cost_regularization(variance, frozen_grad=diff and not self.training)
         # softmax + regression + confidence, fused (:142-151)
         depth, index, photometric_confidence, _ = ops.soft_argmin(cost_reg, depth_values)
         if self.refine:

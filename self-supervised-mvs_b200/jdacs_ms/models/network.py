@@ -107,19 +107,20 @@ class CostRegNet(nn.Module):
         self._cache.clear()
         return super().train(mode)
 
-    def forward(self, x):
+    def forward(self, x, frozen_grad=False):
         tr = self.training
-        x = regnet.as_c8(x, torch.float32 if tr else (self.act_dtype or torch.float32))
+        fg = frozen_grad and not tr
+        x = regnet.as_c8(x, torch.float32 if (tr or fg) else (self.act_dtype or torch.float32))
         for n in (x.shape[2], x.shape[3], x.shape[4]):
             if n % 2:
                 raise ValueError("CVP CostRegNet needs even D, H, W (got %s), as the reference does" % (tuple(x.shape[2:5]),))
         a, c = self.algo, self._cache
-        conv0 = self.conv0a(self.conv0(x, None, a), None, a)
-        conv2 = self.conv2a(self.conv2(self.conv1(conv0, None, a), None, a), None, a)
-        conv4 = self.conv4a(self.conv4(self.conv3(conv2, None, a), None, a), None, a)
-        conv5 = regnet.conv_bn_relu(conv4, self.conv5[0], self.conv5[1], tr, c, conv2, a)
-        conv6 = regnet.conv_bn_relu(conv5, self.conv6[0], self.conv6[1], tr, c, conv0, a)
-        return regnet.conv_bias(conv6, self.prob0, tr, c, a)
+        conv0 = self.conv0a(self.conv0(x, None, a, fg), None, a, fg)
+        conv2 = self.conv2a(self.conv2(self.conv1(conv0, None, a, fg), None, a, fg), None, a, fg)
+        conv4 = self.conv4a(self.conv4(self.conv3(conv2, None, a, fg), None, a, fg), None, a, fg)
+        conv5 = regnet.conv_bn_relu(conv4, self.conv5[0], self.conv5[1], tr, c, conv2, a, fg)
+        conv6 = regnet.conv_bn_relu(conv5, self.conv6[0], self.conv6[1], tr, c, conv0, a, fg)
+        return regnet.conv_bias(conv6, self.prob0, tr, c, a, fg)
 
 
 class CVPMVSNet(nn.Module):
@@ -128,14 +129,17 @@ class CVPMVSNet(nn.Module):
     forward(ref_img [B,3,H,W], src_imgs [B,nsrc,3,H,W], ref_in [B,3,3], src_in [B,nsrc,3,3], ref_ex [B,4,4],
             src_ex [B,nsrc,4,4], depth_min [B], depth_max [B])
         -> {"depth_est_list": [finest ... coarsest], "prob_confidence": [B,H,W]}
-    args needs .nsrc, .nscale, .mode like the reference's argparse namespace."""
+    args needs .nsrc, .nscale, .mode like the reference's argparse namespace.
+    volume_dtype / train_dtype: storage of maps, volumes and activations in eval / training mode; None (default) = fp16 / bf16 on a
+    CUDA device (tensor-core kernels), fp32 on the host-emulation build; torch.float32 = the reference's arithmetic (see MVSNet)."""
 
-    def __init__(self, args, volume_dtype=torch.float32):
+    def __init__(self, args, volume_dtype=None, train_dtype=None):
         super().__init__()
         self.featurePyramid = FeaturePyramid()
         self.cost_reg_refine = CostRegNet()
         self.args = args
         self.volume_dtype = volume_dtype
+        self.train_dtype = train_dtype
         self.feature_tc = True      # eval + 16-bit volumes: FeaturePyramid on the repo's tcgen05 convolution kernel
         self.keep_index = False     # also return "depth_index" of the finest level (network.py:187-188)
 
@@ -143,10 +147,15 @@ class CVPMVSNet(nn.Module):
         nsrc, nscale = self.args.nsrc, self.args.nscale
         depth_est_list = []
         ref_img, src_imgs = ref_img.float(), src_imgs.float()    # 16-bit uploads are widened here: the image pyramid is built in fp32
-        dt = torch.float32 if self.training else self.volume_dtype
-        self.cost_reg_refine.act_dtype = None if self.training else dt
+        auto16 = ref_img.is_cuda
+        tdt = self.train_dtype if self.train_dtype is not None else (torch.bfloat16 if auto16 else torch.float32)
+        # differentiable pass: training mode, or eval mode with gradients requested and a 16-bit train_dtype (frozen BatchNorm)
+        diff = self.training or (torch.is_grad_enabled() and tdt != torch.float32 and any(p.requires_grad for p in self.parameters()))
+        fg = diff and not self.training
+        dt = tdt if diff else (self.volume_dtype if self.volume_dtype is not None else (torch.float16 if auto16 else torch.float32))
+        self.cost_reg_refine.act_dtype = None if diff else dt
 
-        fast = (not self.training) and dt != torch.float32 and ref_img.is_cuda and self.feature_tc
+        fast = (not diff) and dt != torch.float32 and ref_img.is_cuda and self.feature_tc
         if fast:
             # eval, 16-bit volumes: the pyramid on the tcgen05 kernel, every level already in the sweep's gather layout
             imgs = torch.cat((ref_img.unsqueeze(1), src_imgs[:, :nsrc]), 1)
@@ -168,7 +177,7 @@ class CVPMVSNet(nn.Module):
             cost_volume = ops.warp_variance_maps(maps[-1], rt, depth_hypos, dt, ALIGN_CORNERS, True)
         else:
             cost_volume = ops.warp_variance(ref_pyr[-1], [p[-1] for p in src_pyrs], rt, depth_hypos, dt, ALIGN_CORNERS, True)
-        cost_reg = self.cost_reg_refine(cost_volume)
+        cost_reg = self.cost_reg_refine(cost_volume, frozen_grad=fg)
         depth, index, conf, _ = ops.soft_argmin(cost_reg, depth_hypos)
         depth_est_list.append(depth)
 
@@ -183,7 +192,7 @@ class CVPMVSNet(nn.Module):
             else:
                 cost_volume = proj_cost(self.args, ref_pyr[level], src_pyrs, level, ref_in_ms[:, level],
                                         src_in_ms[:, :, level], ref_ex, src_ex, depth_hypos, dt, as_c8=True)
-            cost_reg2 = self.cost_reg_refine(cost_volume)
+            cost_reg2 = self.cost_reg_refine(cost_volume, frozen_grad=fg)
             depth, index, conf, _ = ops.soft_argmin(cost_reg2, depth_hypos)
             depth_est_list.append(depth)
 

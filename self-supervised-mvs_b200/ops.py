@@ -444,6 +444,124 @@ def bn_act_train(z: Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, skip: Opt
     return y
 
 
+# ------------------------------------------------------------------------------------------------ training on tensor cores (16-bit activations)
+def _adjoint_conv(g: Tensor, weight: Tensor, cin: int, stride: int, transposed: bool) -> Tensor:
+    """gradient w.r.t. the input of a (transposed) convolution = the convolution of `g` with the same torch weight packed under the
+    opposite flag (ATen's definition of conv_transpose), on the tcgen05 kernel: stride-2 Conv3d <-> stride-2 ConvTranspose3d."""
+    g_adj = pack_conv3d_weight(weight, not transposed)
+    return conv3d_raw(g, g_adj, cin, stride, not transposed, algo=0)
+
+
+def _wgrad_mma(x: Tensor, gz: Tensor, weight: Tensor, cout: int, stride: int, transposed: bool, cout_real: int) -> Tensor:
+    d = _desc(x, cout, stride, transposed, x.dtype, False, 0)
+    gw = torch.zeros_like(weight, dtype=torch.float32)
+    call("mvs_conv3d_wgrad_mma", x, C.byref(d), ptr(x), ptr(gz), ptr(gw), cout_real)
+    return gw
+
+
+class _ConvBnActTC(torch.autograd.Function):
+    """y = relu(bn(conv(x))) + skip for C8 volumes stored in fp16 / bf16: convolution and input gradient on the tcgen05 kernel,
+    weight gradient on warp-level tensor-core MMAs, BatchNorm statistics in fp64 (csrc/train.cu).  `frozen` uses the running
+    statistics (fine-tuning under module.eval()), otherwise batch statistics are taken and the running ones updated."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor, skip: Optional[Tensor], running_mean: Optional[Tensor],
+                running_var: Optional[Tensor], stride: int, transposed: bool, eps: float, momentum: float, frozen: bool) -> Tensor:
+        x = x.contiguous()
+        dt = x.dtype
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        z = conv3d_raw(x, pack_conv3d_weight(weight, transposed), cout, stride, transposed, algo=0)
+        b, cb = z.shape[0], z.shape[1]
+        s = z[0, 0].numel() // 8
+        dev = z.device
+        gamma_c, beta_c = _f32c(gamma), _f32c(beta)
+        stats = torch.empty(4, cout, dtype=torch.float32, device=dev)       # a, b, mean, invstd
+        if frozen:
+            inv = torch.rsqrt(running_var.detach().float() + eps)
+            stats[0] = gamma_c * inv
+            stats[1] = beta_c - running_mean.detach().float() * stats[0]
+            stats[2] = running_mean.detach().float()
+            stats[3] = inv
+        else:
+            sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+            call("mvs_bn_stats_t", z, ptr(z), dtype_code(dt), ptr(sums), b, cout, s)
+            call("mvs_bn_finalize", z, ptr(sums), ptr(gamma_c), ptr(beta_c), float(eps), float(momentum), float(b * s), ptr(stats[0]), ptr(stats[1]),
+                 ptr(stats[2]), ptr(stats[3]), ptr(running_mean), ptr(running_var), cout)
+        y = torch.empty_like(z)
+        skip_c = None if skip is None else skip.contiguous()
+        call("mvs_bn_act_fwd_t", z, ptr(z), ptr(stats[0]), ptr(stats[1]), ptr(skip_c), ptr(y), dtype_code(dt), b, cout, s, 1)
+        ctx.save_for_backward(x, weight, z, stats)
+        ctx.meta = (stride, transposed, cout, skip is not None, frozen)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x, weight, z, stats = ctx.saved_tensors
+        stride, transposed, cout, has_skip, frozen = ctx.meta
+        dt = z.dtype
+        gy = gy.detach().to(dt).contiguous()
+        b = z.shape[0]
+        s = z[0, 0].numel() // 8
+        red = torch.zeros(2, cout, dtype=torch.float64, device=z.device)
+        call("mvs_bn_act_bwd_reduce_t", z, ptr(z), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]), ptr(red), dtype_code(dt),
+             b, cout, s, 1)
+        gz = torch.empty_like(z)
+        gpar = torch.empty(2, cout, dtype=torch.float32, device=z.device)
+        call("mvs_bn_act_bwd_apply_t", z, ptr(z), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]), ptr(red), ptr(gz),
+             ptr(gpar[0]), ptr(gpar[1]), dtype_code(dt), b, cout, s, 1, int(frozen))
+        w32 = _f32c(weight)
+        gx = _adjoint_conv(gz, w32, x.shape[1] * 8, stride, transposed) if ctx.needs_input_grad[0] else None
+        gw = _wgrad_mma(x, gz, w32, cout, stride, transposed, cout) if ctx.needs_input_grad[1] else None
+        return (gx, gw, gpar[0] if ctx.needs_input_grad[2] else None, gpar[1] if ctx.needs_input_grad[3] else None,
+                gy if has_skip else None, None, None, None, None, None, None, None)
+
+
+def conv_bn_act_tc(x: Tensor, conv: torch.nn.Module, bn: torch.nn.modules.batchnorm._BatchNorm, skip: Optional[Tensor], frozen: bool) -> Tensor:
+    transposed = isinstance(conv, torch.nn.ConvTranspose3d)
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    track = bn.track_running_stats and bn.running_mean is not None
+    y = _ConvBnActTC.apply(x, conv.weight, bn.weight, bn.bias, skip, bn.running_mean if track else None, bn.running_var if track else None,
+                           conv.stride[0], transposed, bn.eps, mom, frozen)
+    if track and not frozen and bn.num_batches_tracked is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+    return y
+
+
+class _ConvBiasTC(torch.autograd.Function):
+    """The single-channel `prob` convolution (stride 1, bias): 16-bit C8 volume -> plain fp32 [B,D,H,W], differentiable."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+        x = x.contiguous()
+        y = conv3d_raw(x, pack_conv3d_weight(weight, False), 1, 1, False, shift=None if bias is None else _f32c(bias), algo=0)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x, weight = ctx.saved_tensors
+        gy = _f32c(gy)
+        b, d, h, w = gy.shape
+        g8 = torch.empty(b, 1, d, h, w, 8, dtype=x.dtype, device=x.device)     # the gradient lifted to one C8 block (channel 0)
+        call("mvs_lift_c1", gy, ptr(gy), ptr(g8), dtype_code(x.dtype), gy.numel())
+        w8 = torch.zeros(8, weight.shape[1], 3, 3, 3, dtype=torch.float32, device=weight.device)
+        w8[:1] = weight.detach().float()
+        gx = _adjoint_conv(g8, w8, x.shape[1] * 8, 1, False) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            d8 = _desc(x, 8, 1, False, x.dtype, False, 0)
+            gw = torch.zeros_like(weight, dtype=torch.float32)
+            call("mvs_conv3d_wgrad_mma", x, C.byref(d8), ptr(x), ptr(g8), ptr(gw), 1)
+        gb = gy.sum().reshape(1) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
+def conv_bias_tc(x: Tensor, conv: torch.nn.Conv3d) -> Tensor:
+    return _ConvBiasTC.apply(x, conv.weight, conv.bias)
+
+
 def fold_bn(bn: torch.nn.modules.batchnorm._BatchNorm) -> Tuple[Tensor, Tensor]:
     """Eval-mode BN as a per-channel affine: scale = gamma / sqrt(running_var + eps), shift = beta - mean * scale."""
     scale = (bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)).contiguous()

@@ -68,11 +68,18 @@ class PackCache:
 
 
 def conv_bn_relu(x: Tensor, conv: nn.Module, bn: nn.modules.batchnorm._BatchNorm, training: bool, cache: PackCache,
-                 skip: Optional[Tensor] = None, algo: int = 0) -> Tensor:
-    """relu(bn(conv(x))) + skip for nn.Conv3d or nn.ConvTranspose3d holders (3x3x3, pad 1, stride 1|2)."""
+                 skip: Optional[Tensor] = None, algo: int = 0, frozen_grad: bool = False) -> Tensor:
+    """relu(bn(conv(x))) + skip for nn.Conv3d or nn.ConvTranspose3d holders (3x3x3, pad 1, stride 1|2).
+    training: batch statistics, differentiable.  frozen_grad: eval-mode statistics but differentiable (fine-tuning under
+    module.eval(), which the reference supports); 16-bit volumes only.  Otherwise: the fused inference kernel, no autograd graph."""
     transposed = isinstance(conv, nn.ConvTranspose3d)
     stride = conv.stride[0]
     cout = conv.out_channels
+    if (training or frozen_grad) and x.dtype != torch.float32:
+        return ops.conv_bn_act_tc(x, conv, bn, skip, frozen=not training)      # tensor-core training path (csrc/train.cu)
+    if frozen_grad:
+        raise RuntimeError("gradients through an eval-mode CostRegNet need 16-bit volumes (train_dtype=torch.bfloat16); "
+                           "the fp32 path is differentiable in train() mode only")
     if training:
         z = ops.conv3d(x, conv.weight, None, stride, transposed)
         return ops.bn_act_train(z, bn, skip, True)
@@ -85,8 +92,10 @@ def conv_bn_relu(x: Tensor, conv: nn.Module, bn: nn.modules.batchnorm._BatchNorm
                           relu=True, algo=algo, tile_cache=cache.tiles)
 
 
-def conv_bias(x: Tensor, conv: nn.Conv3d, training: bool, cache: PackCache, algo: int = 0) -> Tensor:
+def conv_bias(x: Tensor, conv: nn.Conv3d, training: bool, cache: PackCache, algo: int = 0, frozen_grad: bool = False) -> Tensor:
     """The final single-channel `prob` convolution: plain fp32 [B,D,H,W] out."""
+    if (training or frozen_grad) and x.dtype != torch.float32:
+        return ops.conv_bias_tc(x, conv)
     if training:
         return ops.conv3d(x, conv.weight, conv.bias, 1, False)
     bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None

@@ -398,3 +398,44 @@ def test_depth_hypotheses(be, golden):
     g = golden("ms_warp")
     h = ops.depth_hypo_refine(*[be.to(t) for t in (g["depth_up"], g["ref_in"], g["src_in"][:, 0], g["ref_ex"], g["src_ex"][:, 0])])
     assert rel_err(h, g["refine_hypos"]) < 1e-6
+
+
+def test_bn_passes_of_the_training_path(be):
+    """mvs_bn_stats_t / _finalize / _act_fwd_t / _act_bwd_reduce_t / _act_bwd_apply_t (fp64 statistics, any storage type; here fp32
+    on both backends) against nn.BatchNorm3d + ReLU + skip autograd, including the running-statistics update."""
+    ops = _ops()
+    from ssmvs_b200._lib import call, ptr, dtype_code
+    torch.manual_seed(3)
+    b, c, s = 2, 16, (3, 5, 7)
+    z = (torch.randn(b, c, *s) * 2.0 + 5.0).requires_grad_(True)          # |mean| >> std: the cancellation case
+    skip = torch.randn(b, c, *s)
+    bn = torch.nn.BatchNorm3d(c)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.5)
+    gamma, beta = be.to(bn.weight.detach()), be.to(bn.bias.detach())
+    rm, rv = be.to(bn.running_mean), be.to(bn.running_var)
+    y_ref = torch.relu(bn(z)) + skip
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    z8, sk8, gy8 = ops.pack_c8(be.to(z)), ops.pack_c8(be.to(skip)), ops.pack_c8(be.to(gy))
+    n = s[0] * s[1] * s[2]
+    sums = torch.zeros(2, c, dtype=torch.float64, device=z8.device)
+    call("mvs_bn_stats_t", z8, ptr(z8), dtype_code(torch.float32), ptr(sums), b, c, n)
+    st = torch.empty(4, c, device=z8.device)
+    call("mvs_bn_finalize", z8, ptr(sums), ptr(gamma), ptr(beta), 1e-5, 0.1, float(b * n), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), ptr(rm), ptr(rv), c)
+    y8 = torch.empty_like(z8)
+    call("mvs_bn_act_fwd_t", z8, ptr(z8), ptr(st[0]), ptr(st[1]), ptr(sk8), ptr(y8), dtype_code(torch.float32), b, c, n, 1)
+    assert rel_err(ops.unpack_c8(y8), y_ref) < 1e-5
+    assert rel_err(rm, bn.running_mean) < 1e-6 and rel_err(rv, bn.running_var) < 1e-5
+    red = torch.zeros(2, c, dtype=torch.float64, device=z8.device)
+    call("mvs_bn_act_bwd_reduce_t", z8, ptr(z8), ptr(gy8), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), ptr(red), dtype_code(torch.float32), b, c, n, 1)
+    gz8 = torch.empty_like(z8)
+    gp = torch.empty(2, c, device=z8.device)
+    call("mvs_bn_act_bwd_apply_t", z8, ptr(z8), ptr(gy8), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), ptr(red), ptr(gz8), ptr(gp[0]), ptr(gp[1]),
+         dtype_code(torch.float32), b, c, n, 1, 0)
+    assert rel_err(ops.unpack_c8(gz8), z.grad) < 2e-4
+    assert rel_err(gp[0], bn.weight.grad) < 1e-4 and rel_err(gp[1], bn.bias.grad) < 1e-5
+    lifted = torch.empty(6, 8, device=z8.device)
+    src = be.to(torch.arange(6.0))
+    call("mvs_lift_c1", src, ptr(src), ptr(lifted), dtype_code(torch.float32), 6)
+    assert torch.equal(lifted[:, 0].cpu(), torch.arange(6.0)) and torch.count_nonzero(lifted[:, 1:]) == 0

@@ -15,7 +15,7 @@ def be(request):
 def test_mvsnet_eval_and_train(be, golden):
     from ssmvs_b200.jdacs.models.mvsnet import MVSNet
     g = golden("jdacs_mvsnet")
-    model = MVSNet(refine=False)
+    model = MVSNet(refine=False, volume_dtype=torch.float32, train_dtype=torch.float32)     # the reference's arithmetic
     res = model.load_state_dict(state_dict_of(g), strict=False)
     assert not res.unexpected_keys and all("num_batches_tracked" in k for k in res.missing_keys)
     model = model.to(be.device).eval()
@@ -68,7 +68,7 @@ def test_state_dict_keys_match_reference(golden):
 def test_cvpmvsnet(be, golden):
     from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
     g = golden("ms_cvp")
-    model = CVPMVSNet(SimpleNamespace(nsrc=2, nscale=2, mode="test"))
+    model = CVPMVSNet(SimpleNamespace(nsrc=2, nscale=2, mode="test"), volume_dtype=torch.float32, train_dtype=torch.float32)
     model.load_state_dict(state_dict_of(g), strict=False)
     model = model.to(be.device).eval()
     args = [be.to(g[k]) for k in ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")]

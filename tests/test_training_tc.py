@@ -1,0 +1,166 @@
+"""The training half of the path on tensor cores (csrc/train.cu, warp_var_bwd16_kernel): 16-bit activations, fp32 master
+weights, tcgen05 forward / input gradient, warp-level MMA weight gradient, fp64 BatchNorm statistics, register-merged scatter
+of the plane-sweep gradient.  Checked against PyTorch autograd in fp32 on the same (16-bit-rounded) inputs and against the
+gradients the unmodified reference produced (tests/golden)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err, state_dict_of
+
+pytestmark = pytest.mark.gpu
+
+
+def nerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+LAYERS = [  # cin, cout, stride, transposed, (d, h, w) of the input, skip
+    (32, 8, 1, False, (8, 16, 40), False), (8, 16, 2, False, (8, 16, 40), False), (16, 16, 1, False, (6, 10, 36), False),
+    (16, 32, 2, False, (8, 16, 24), False), (32, 32, 1, False, (4, 10, 20), False), (32, 64, 2, False, (8, 8, 16), False),
+    (64, 64, 1, False, (3, 6, 10), False), (64, 32, 2, True, (3, 6, 10), True), (32, 16, 2, True, (4, 6, 12), True),
+    (16, 8, 2, True, (4, 8, 20), True), (32, 64, 1, False, (4, 8, 12), False), (64, 32, 1, True, (4, 8, 12), True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,stride,tr,shape,skip", LAYERS)
+def test_conv_bn_relu_layer_forward_and_gradients(gpu, dtype, cin, cout, stride, tr, shape, skip):
+    """One ConvBnReLU3D / ConvTranspose3d+BN+ReLU(+skip) layer in training mode: output, running statistics and the gradients
+    w.r.t. input, weight, gamma, beta and skip against ATen autograd in fp32 on the same rounded inputs."""
+    from ssmvs_b200 import ops
+    torch.manual_seed(cin * 131 + cout * 7 + stride)
+    dev = gpu.device
+    d, h, w = shape
+    conv = (torch.nn.ConvTranspose3d(cin, cout, 3, stride=stride, padding=1, output_padding=stride - 1, bias=False) if tr
+            else torch.nn.Conv3d(cin, cout, 3, stride=stride, padding=1, bias=False)).to(dev)
+    bn = torch.nn.BatchNorm3d(cout).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+        conv.weight.copy_(conv.weight.to(dtype).float())        # weights the 16-bit kernels can represent exactly
+    x32 = torch.randn(2, cin, d, h, w, device=dev).to(dtype).float()
+    x8 = ops.pack_c8(x32, dtype).requires_grad_(True)
+    xr = x32.clone().requires_grad_(True)
+    # reference: ATen, fp32 (TF32 off through the gpu fixture)
+    bn_ref = torch.nn.BatchNorm3d(cout).to(dev)
+    bn_ref.load_state_dict(bn.state_dict())
+    zr = F.conv_transpose3d(xr, conv.weight, None, stride, 1, stride - 1) if tr else F.conv3d(xr, conv.weight, None, stride, 1)
+    yr = F.relu(bn_ref(zr))
+    sk32 = None
+    if skip:
+        sk32 = torch.randn_like(yr).to(dtype).float()
+        yr = yr + sk32
+    gout = torch.randn_like(yr).to(dtype).float()
+    w_ref = conv.weight.detach().clone().requires_grad_(True)
+    # (re-run with a leaf weight so that its gradient is kept apart from the module's)
+    zr = F.conv_transpose3d(xr, w_ref, None, stride, 1, stride - 1) if tr else F.conv3d(xr, w_ref, None, stride, 1)
+    bn_ref2 = torch.nn.BatchNorm3d(cout).to(dev)
+    bn_ref2.load_state_dict(bn.state_dict())
+    yr = F.relu(bn_ref2(zr)) + (sk32 if skip else 0)
+    yr.backward(gout)
+    # product
+    sk8 = ops.pack_c8(sk32, dtype).requires_grad_(True) if skip else None
+    y8 = ops.conv_bn_act_tc(x8, conv, bn, sk8, frozen=False)
+    y8.backward(ops.pack_c8(gout, dtype))
+    tol = 3e-2 if dtype == torch.bfloat16 else 6e-3
+    assert nerr(ops.unpack_c8(y8), yr) < tol
+    assert nerr(bn.running_mean, bn_ref2.running_mean) < 1e-3 and nerr(bn.running_var, bn_ref2.running_var) < 1e-2
+    assert int(bn.num_batches_tracked) == 1
+    assert nerr(ops.unpack_c8(x8.grad), xr.grad) < 2 * tol
+    assert nerr(conv.weight.grad, w_ref.grad) < 2 * tol
+    assert nerr(bn.weight.grad, bn_ref2.weight.grad) < 2 * tol and nerr(bn.bias.grad, bn_ref2.bias.grad) < 2 * tol
+    if skip:
+        assert nerr(ops.unpack_c8(sk8.grad), gout) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,stride,tr,shape", [(32, 8, 1, False, (8, 16, 40)), (8, 16, 2, False, (6, 12, 70)), (64, 64, 1, False, (3, 9, 33)),
+                                                      (64, 32, 2, True, (3, 5, 9)), (16, 8, 2, True, (4, 8, 20)), (32, 32, 1, False, (5, 7, 11)),
+                                                      (16, 32, 2, False, (4, 18, 66)), (8, 8, 1, False, (4, 9, 35)), (64, 32, 1, True, (2, 8, 12))])
+def test_wgrad_mma_matches_the_fp32_simt_weight_gradient(gpu, dtype, cin, cout, stride, tr, shape):
+    """mvs_conv3d_wgrad_mma (ldmatrix + mma.sync over shifted views of one staged tile) against mvs_conv3d_bwd_weight on the same
+    16-bit-representable data: both accumulate in fp32, so only the summation order differs.  Ragged tiles, both strides, both
+    operand orders (which tensor is the M side), every tap-group size."""
+    from ssmvs_b200 import ops
+    from ssmvs_b200._lib import call, ptr
+    import ctypes as C
+    torch.manual_seed(5)
+    dev = gpu.device
+    d, h, w = shape
+    x32 = torch.randn(2, cin, d, h, w, device=dev).to(dtype).float()
+    wt = torch.zeros(cin, cout, 3, 3, 3, device=dev) if tr else torch.zeros(cout, cin, 3, 3, 3, device=dev)
+    do, ho, wo = (2 * d, 2 * h, 2 * w) if (tr and stride == 2) else ((d // 2, h // 2, w // 2) if stride == 2 else (d, h, w))
+    gz32 = torch.randn(2, cout, do, ho, wo, device=dev).to(dtype).float()
+    x8f, gzf = ops.pack_c8(x32), ops.pack_c8(gz32)
+    want = torch.zeros_like(wt)
+    desc = ops._desc(x8f, cout, stride, tr, torch.float32, False, 1)
+    call("mvs_conv3d_bwd_weight", x8f, C.byref(desc), ptr(x8f), ptr(gzf), ptr(want))
+    got = ops._wgrad_mma(ops.pack_c8(x32, dtype), ops.pack_c8(gz32, dtype), wt, cout, stride, tr, cout)
+    assert rel_err(got, want) < 2e-4, rel_err(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("channels,nsrc,ref_sq,per_pixel", [(32, 4, False, False), (16, 3, True, True), (8, 1, False, False), (32, 6, False, False)])
+def test_sweep_backward_16bit_matches_fp32_scatter(gpu, dtype, channels, nsrc, ref_sq, per_pixel):
+    """warp_var_bwd16_kernel (run-length merged vector reductions) against the fp32 scalar-atomic kernel on the same rounded
+    feature maps and the same upstream gradient."""
+    from ssmvs_b200 import ops, synth
+    inp = synth.feature_inputs(2, nsrc + 1, channels, 19, 45, 20, seed=9)
+    f = [t.to(dtype).float().to(gpu.device) for t in inp["features"]]
+    depth = inp["depth_values"].to(gpu.device)
+    if per_pixel:
+        depth = depth.view(2, -1, 1, 1) + 2.0 * torch.randn(2, depth.shape[1], 19, 45, device=gpu.device)
+    rt = ops.compose_proj(inp["proj_matrices"].to(gpu.device))
+    gup = torch.randn(2, channels // 8, 20, 19, 45, 8, device=gpu.device).to(dtype)
+    grads = {}
+    for name, dt in (("ref", torch.float32), ("got", dtype)):
+        fl = [t.clone().requires_grad_(True) for t in f]
+        v = ops.warp_variance(fl[0], fl[1:], rt, depth, dt, False, ref_sq)
+        v.backward(gup.to(dt))
+        grads[name] = [t.grad for t in fl]
+    for a, b in zip(grads["got"], grads["ref"]):
+        assert nerr(a, b) < (2e-2 if dtype == torch.bfloat16 else 3e-3)
+
+
+def test_mvsnet_bf16_training_gradients_against_the_reference(gpu, golden):
+    """Whole MVSNet in train() mode with the default (bf16, tensor-core) training path against the depth map and the parameter
+    gradients the unmodified reference produced in fp32 (tests/golden/jdacs_mvsnet.npz)."""
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    g = golden("jdacs_mvsnet")
+    model = MVSNet(refine=False)
+    model.load_state_dict(state_dict_of(g), strict=False)
+    model = model.to(gpu.device).train()
+    args = [gpu.to(g[k]) for k in ("imgs", "proj_matrices", "depth_values")]
+    out = model(*args)
+    assert nerr(out["depth"], g["train_depth"]) < 5e-3
+    (out["depth"] * gpu.to(g["loss_weight"])).sum().backward()
+    params = dict(model.named_parameters())
+    worst = {}
+    for k, v in g.items():
+        if k.startswith("grad."):
+            worst[k] = nerr(params[k[5:]].grad, v)
+    bad = {k: e for k, e in worst.items() if not e < 0.15}
+    assert not bad, bad
+    assert sorted(worst.values())[len(worst) // 2] < 5e-2, worst      # median over the parameter tensors
+
+
+def test_eval_mode_fine_tuning_uses_frozen_statistics(gpu):
+    """module.eval() with gradients enabled (the reference allows fine-tuning with frozen BatchNorm): the 16-bit path is
+    differentiable, uses the running statistics and leaves them untouched."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False)
+    synth.randomise_bn(model, 5)
+    model = model.to(gpu.device).eval()
+    inp = gpu.to(synth.mvsnet_inputs(1, 3, 64, 96, 16, seed=1))
+    before = model.cost_regularization.conv0.bn.running_mean.clone()
+    out = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])
+    out["depth"].sum().backward()
+    assert torch.equal(before, model.cost_regularization.conv0.bn.running_mean)
+    g = model.cost_regularization.conv0.conv.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+    with torch.no_grad():
+        ref = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])["depth"]     # fused inference path, fp16
+    assert nerr(out["depth"], ref) < 2e-2
