@@ -261,14 +261,255 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+# ================================================================================================ secondary workloads
+def _timed_steps(fn, steps, warmup, dev, flush, parallel):
+    """W warm-up steps, then K steps bracketed per step by CUDA events on the launching stream (L2 flushed between steps, outside
+    the event pairs), barrier + synchronize on both sides; -> (sum of step ms, max over ranks)."""
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    parallel.barrier()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        fn()
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    parallel.barrier()
+    return parallel.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev)
+
+
+def _event_ms(fn, dev, flush, reps=3):
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def cpu_train_timer(ndepth=48):
+    """The reference's CPU path for one train_sample-equivalent (forward in train mode + UnSupLoss + backward + Adam) through the
+    oracle port, on a bounded sample: 1 item, full image size, `ndepth` planes."""
+    from ssmvs_b200 import synth
+    oracle = load_oracle()
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    torch.manual_seed(0)
+    model = MVSNet(refine=False)
+    params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in model.state_dict().items()}
+    leaves = [v for v in params.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    inp = synth.mvsnet_inputs(1, VIEWS, HEIGHT, WIDTH, ndepth, seed=0)
+    threads = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    out = oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], params, True)
+    loss = oracle.unsup_loss(inp["imgs"], inp["cams"], out["depth"])
+    loss = loss[0] if isinstance(loss, (tuple, list)) else (loss["total"] if isinstance(loss, dict) else loss)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return time.perf_counter() - t0, threads, ndepth
+
+
+def run_train(args):
+    """BASELINE configs[3]: one JDACS training batch = train_sample + train_sample_aug (two forward / backward / Adam steps,
+    jdacs/train.py:189-291) with the photometric loss, N = 5 views (the reference's top-3 view selection needs >= 3 sources,
+    SURVEY hazard H5), 512x640, D = 192; the batch is sharded over the ranks and the gradients take one NCCL all-reduce per
+    optimiser step."""
+    import ssmvs_b200
+    from ssmvs_b200 import ops, parallel, synth
+    from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200.trainer import TrainStep
+    rank, world, local = parallel.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ssmvs_b200._lib.bind()
+    tdt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.train_dtype]
+    PB = args.batch if args.batch_given else 2
+    torch.manual_seed(0)
+    model = MVSNet(refine=False, train_dtype=tdt).to(dev)
+    step = TrainStep(model, UnSupLoss())
+    host = synth.mvsnet_inputs(PB, VIEWS, HEIGHT, WIDTH, NDEPTH, seed=rank)
+    host["imgs_aug"] = host["imgs"] + 0.05 * torch.randn(host["imgs"].shape, generator=torch.Generator().manual_seed(100 + rank))
+    keys = ("imgs", "imgs_aug", "cams", "proj_matrices", "depth_values")
+    pinned = {k: host[k].pin_memory() for k in keys}
+    res = {k: v.to(dev) for k, v in pinned.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.empty(2).pin_memory()
+
+    def step_resident():
+        return step(res["imgs"], res["imgs_aug"], res["cams"], res["proj_matrices"], res["depth_values"])
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        o = step(d["imgs"], d["imgs_aug"], d["cams"], d["proj_matrices"], d["depth_values"])
+        loss_host.copy_(torch.stack((o["loss"], o["augment_loss"])), non_blocking=True)
+
+    l0 = ssmvs_b200._lib.launches
+    with ClockSampler(local) as clk:
+        ms_total = _timed_steps(step_resident, args.steps, args.warmup, dev, flush, parallel)
+        launches = ssmvs_b200._lib.launches - l0
+        ms_e2e = _timed_steps(step_e2e, args.steps, 1, dev, flush, parallel)
+    clocks = clk.summary()
+    losses = step_resident()
+    assert torch.isfinite(losses["loss"]) and torch.isfinite(losses["augment_loss"]), losses
+
+    # ---- where the time goes: phases of the first pass, and the two dominant kernels alone
+    mk = lambda: torch.cuda.Event(enable_timing=True)
+    e = [mk() for _ in range(5)]
+    step.grads.zero()
+    flush.zero_(); e[0].record()
+    depth = model(res["imgs"], res["proj_matrices"], res["depth_values"])["depth"]
+    e[1].record()
+    loss = step.criterion(res["imgs"], res["cams"], depth)
+    e[2].record()
+    loss.backward()
+    e[3].record()
+    step.opt.step()
+    e[4].record()
+    torch.cuda.synchronize(dev)
+    stages = {k: e[i].elapsed_time(e[i + 1]) for i, k in enumerate(("forward", "loss", "backward", "allreduce+adam"))}
+    peaks = load_peaks()
+    rooflines = {}
+    if tdt != torch.float32:
+        elem = 2
+        var = torch.randn(PB, CHANNELS // 8, NDEPTH, HF, WF, 8, device=dev).to(tdt)
+        gz = torch.randn(PB, 1, NDEPTH, HF, WF, 8, device=dev).to(tdt)
+        w0 = torch.zeros(8, CHANNELS, 3, 3, 3, device=dev)
+        t_wg = _event_ms(lambda: ops._wgrad_mma(var, gz, w0, 8, 1, False, 8), dev, flush)
+        tf = PB * CONV0_FLOPS / (t_wg * 1e-3) / 1e12
+        rooflines["roofline_wgrad_conv0"] = {"kernel": "conv3d_wgrad_mma_kernel (conv0: 32 x 8 x 27 taps over D x H x W, mma.sync m16n8k16)", "bound": "tensor",
+                                             "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None,
+                                             "ms": t_wg, "peak_source": peaks["source"], "algorithmic_flops": PB * CONV0_FLOPS,
+                                             "hbm": {"achieved": PB * CONV0_BYTES(elem) / (t_wg * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                     "frac": PB * CONV0_BYTES(elem) / (t_wg * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+        feats = [torch.randn(PB, CHANNELS, HF, WF, device=dev).requires_grad_(True) for _ in range(VIEWS)]
+        rt = ops.compose_proj(res["proj_matrices"])
+        v = ops.warp_variance(feats[0], feats[1:], rt, res["depth_values"], tdt)
+        gv = torch.randn_like(v)
+        t_wb = _event_ms(lambda: torch.autograd.grad(v, feats, gv, retain_graph=True), dev, flush)
+        bwd_bytes = PB * (elem * CHANNELS * SAMPLES_PER_ITEM + VIEWS * CHANNELS * HF * WF * (elem + 4))
+        gbs = bwd_bytes / (t_wb * 1e-3) / 1e9
+        rooflines["roofline_sweep_bwd"] = {"kernel": "warp_var_bwd16_kernel (+ unpack of the 5 gradient maps)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                                           "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms": t_wb, "peak_source": peaks["source"],
+                                           "algorithmic_bytes": bwd_bytes}
+    dominant = max(rooflines.values(), key=lambda r: r["ms"]) if rooflines else None
+
+    if rank == 0:
+        items = world * args.steps * PB
+        line = {"metric": "depth-samples/sec through one JDACS training batch (train_sample + train_sample_aug: 2 x forward/backward/Adam), N=5, D=192, 512x640",
+                "value": items * SAMPLES_PER_ITEM / (ms_total * 1e-3), "unit": "depth-samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_item": ms_total / args.steps / PB, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "%s activations, f32 master weights / accumulation, f64 BatchNorm statistics" % args.train_dtype,
+                "data": "synthetic",
+                "config": {"workload": "JDACS training batch, photometric loss (BASELINE.json configs[3]; N=5 per SURVEY H5; co-segmentation term out of scope, H10)",
+                           "global_batch": world * PB, "per_gpu_batch": PB,
+                           "parallelism": "dp%d: batch sharded, one flat-bucket NCCL all-reduce (%.2f MB fp32) per optimiser step, 2 per batch" % (world, step.grads.flat.numel() * 4 / 1e6),
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)", "launch": "python (no graph)"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": items * SAMPLES_PER_ITEM / (ms_e2e * 1e-3), "unit": "depth-samples/s",
+                        "h2d_bytes_per_step": world * sum(v.numel() * v.element_size() for v in pinned.values()),
+                        "d2h_bytes_per_step": world * loss_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                        "how": "every step copies imgs, imgs_aug, cams, proj_matrices, depth_values from pinned host memory and reads both losses back"},
+                "roofline": dominant, "stage_ms_first_pass": stages, "losses": {k: float(v) for k, v in losses.items()}}
+        line.update(rooflines)
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sec, threads, nd = cpu_train_timer()
+                line["cpu_baseline"] = {"value": nd * HF * WF / sec, "unit": "depth-samples/s", "cores": threads, "kind": "port",
+                                        "sample": "one train_sample-equivalent (forward in train mode + UnSupLoss + backward + Adam) of 1 item at 512x640 with %d of the 192 planes, oracle port on the host cores; the GPU step does two such passes per batch" % nd}
+            except Exception as exc:
+                line["cpu_baseline"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+        print(json.dumps(line))
+    parallel.barrier()
+
+
+CVP_NSRC, CVP_NSCALE = 4, 3
+CVP_SAMPLES = 48 * 128 * 160 + 8 * 256 * 320 + 8 * 512 * 640
+CVP_FLOPS = 132192 * CVP_SAMPLES + 2 * 121536 * 512 * 640 * (1 + CVP_NSRC) * (1 + 0.25 + 0.0625)   # 3 regularisations + feature pyramid
+
+
+def run_cvp(args):
+    """BASELINE configs[2]: CVP-MVSNet, 3 pyramid levels, 1 + 4 views of 512x640, bf16 volumes, eval."""
+    from types import SimpleNamespace
+    import ssmvs_b200
+    from ssmvs_b200 import parallel, synth
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    rank, world, local = parallel.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ssmvs_b200._lib.bind()
+    dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype if args.dtype_given else "bf16"]
+    PB = args.batch if args.batch_given else 4
+    torch.manual_seed(0)
+    model = CVPMVSNet(SimpleNamespace(nsrc=CVP_NSRC, nscale=CVP_NSCALE, mode="test"), volume_dtype=dtype)
+    synth.randomise_bn(model, 5)
+    model = model.to(dev).eval()
+    keys = ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")
+    host = synth.cvp_inputs(PB, CVP_NSRC, HEIGHT, WIDTH, seed=rank)
+    pinned = {k: host[k].pin_memory() for k in keys}
+    res = {k: v.to(dev) for k, v in pinned.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out_host = {"depth": torch.empty(PB, HEIGHT, WIDTH).pin_memory(), "conf": torch.empty(PB, HEIGHT, WIDTH).pin_memory()}
+
+    def fwd(d):
+        with torch.no_grad():
+            return model(*[d[k] for k in keys])
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        o = fwd(d)
+        out_host["depth"].copy_(o["depth_est_list"][0], non_blocking=True)
+        out_host["conf"].copy_(o["prob_confidence"], non_blocking=True)
+
+    l0 = ssmvs_b200._lib.launches
+    with ClockSampler(local) as clk:
+        ms_total = _timed_steps(lambda: fwd(res), args.steps, args.warmup, dev, flush, parallel)
+        launches = ssmvs_b200._lib.launches - l0
+        ms_e2e = _timed_steps(step_e2e, args.steps, 1, dev, flush, parallel)
+    clocks = clk.summary()
+    peaks = load_peaks()
+    if rank == 0:
+        items = world * args.steps * PB
+        tf = items * CVP_FLOPS / (ms_total * 1e-3) / 1e12 / world
+        line = {"metric": "depth-samples/sec (CVP-MVSNet, 3 levels, nsrc=4, 512x640)", "value": items * CVP_SAMPLES / (ms_total * 1e-3), "unit": "depth-samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_item": ms_total / args.steps / PB,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {torch.float16: "f16", torch.bfloat16: "bf16", torch.float32: "f32"}[dtype] + " storage, f32 accumulate", "data": "synthetic",
+                "config": {"workload": "CVP-MVSNet forward, 3 pyramid levels, 1 + 4 views of 512x640 (BASELINE.json configs[2])", "global_batch": world * PB,
+                           "per_gpu_batch": PB, "parallelism": "dp%d (items sharded, no collective)" % world,
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)", "launch": "python (no graph)"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": items * CVP_SAMPLES / (ms_e2e * 1e-3), "unit": "depth-samples/s",
+                        "h2d_bytes_per_step": world * sum(v.numel() * v.element_size() for v in pinned.values()),
+                        "d2h_bytes_per_step": world * sum(v.numel() * 4 for v in out_host.values()), "ms_per_step": ms_e2e / args.steps},
+                "roofline": {"kernel": "whole forward: feature pyramid + 3 x CostRegNet on conv3d_tc_kernel (86 % of the step), sweeps, soft-argmin", "bound": "tensor",
+                             "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                             "peak_source": peaks["source"], "algorithmic_flops": PB * CVP_FLOPS}}
+        print(json.dumps(line))
+    parallel.barrier()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16")
-    ap.add_argument("--batch", type=int, default=8, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU; measured 1 / 2 / 4 / 8 items: 4.4 / 5.3 / 6.3 / 6.4 G samples/s)")
+    ap.add_argument("--workload", choices=["mvsnet", "cvp", "train"], default="mvsnet",
+                    help="mvsnet = the headline metric (BASELINE configs[1]); cvp = configs[2]; train = configs[3] (one JDACS training batch)")
+    ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default=None, help="storage dtype of the inference workloads (default fp16; cvp: bf16)")
+    ap.add_argument("--train-dtype", choices=["fp16", "bf16", "fp32"], default="bf16")
+    ap.add_argument("--batch", type=int, default=None, help="items per GPU per step (independent MVS problems; the reference ran 1 per 11 GB GPU; measured 1 / 2 / 4 / 8 items: 4.4 / 5.3 / 6.3 / 6.4 G samples/s)")
     ap.add_argument("--lanes", type=int, default=1, help="item groups captured on separate streams inside the CUDA graph (GraphedForward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the end-to-end parity check against the fp32 oracle (rank 0, 1 GPU only)")
@@ -279,6 +520,9 @@ def main():
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.dtype_given, args.batch_given = args.dtype is not None, args.batch is not None
+    args.dtype = args.dtype or "fp16"
+    args.batch = args.batch if args.batch is not None else 8
 
     import ssmvs_b200
     from ssmvs_b200 import ops, parallel, synth
@@ -286,6 +530,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
         return
+    if args.workload == "train":
+        return run_train(args)
+    if args.workload == "cvp":
+        return run_cvp(args)
 
     rank, world, local = parallel.init_from_env("nccl")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the plane-sweep path has no CPU fallback)"

@@ -65,7 +65,9 @@ def test_conv_bn_relu_layer_forward_and_gradients(gpu, dtype, cin, cout, stride,
     y8.backward(ops.pack_c8(gout, dtype))
     tol = 3e-2 if dtype == torch.bfloat16 else 6e-3
     assert nerr(ops.unpack_c8(y8), yr) < tol
-    assert nerr(bn.running_mean, bn_ref2.running_mean) < 1e-3 and nerr(bn.running_var, bn_ref2.running_var) < 1e-2
+    # the statistics are those of the STORED (16-bit) convolution output: compare on the scale of its standard deviation
+    sd = bn_ref2.running_var.sqrt().max().item()
+    assert (bn.running_mean - bn_ref2.running_mean).abs().max().item() < 2e-3 * sd and nerr(bn.running_var, bn_ref2.running_var) < 1e-2
     assert int(bn.num_batches_tracked) == 1
     assert nerr(ops.unpack_c8(x8.grad), xr.grad) < 2 * tol
     assert nerr(conv.weight.grad, w_ref.grad) < 2 * tol
