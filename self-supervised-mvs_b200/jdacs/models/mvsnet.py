@@ -230,8 +230,14 @@ class MVSNet(nn.Module):
         if imgs.dtype != torch.float32 and not (fast and imgs.dtype == dt):
             imgs = imgs.float()     # 16-bit images (a host pipeline may upload them so) are only consumed as such by the 16-bit fast path
         if diff:
-            # each view is its own call in training mode: BatchNorm2d statistics are per call in the reference (:115)
-            features = [self.feature(imgs[:, v]) for v in range(n)]
+            # each view is its own call in training mode: BatchNorm2d statistics are per call in the reference (:115).
+            # With 16-bit activations the (library) feature extractor runs under autocast on channels-last tensors -- cuDNN's
+            # tensor-core convolutions and NHWC BatchNorm kernels instead of its fp32 NCHW ones (10 ms -> ~3 ms per item at 512x640)
+            if dt != torch.float32 and imgs.is_cuda and self.feature_autocast:
+                with torch.autocast("cuda", dtype=dt):
+                    features = [self.feature(imgs[:, v].contiguous(memory_format=torch.channels_last)) for v in range(n)]
+            else:
+                features = [self.feature(imgs[:, v]) for v in range(n)]
             # step 2. plane sweep: warp + variance, fused (:120-136)
             variance = ops.warp_variance(features[0], features[1:], rt, depth_values, dt, self.align_corners, False)
         else:
