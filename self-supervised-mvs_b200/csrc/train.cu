@@ -238,36 +238,39 @@ extern "C" int mvs_lift_c1(const float* src, void* dst, int dtype, int64_t n, vo
 }
 
 #ifndef MVS_CPU_EMU
+#include <cuda.h>
+#include <string.h>
 // ------------------------------------------------------------------------------------------------ weight gradient on tensor cores
 // grad[pc][qc][tap] = sum_b sum_p P[b][p][pc] Q[b][p * stride - 1 + k][qc]            (the formulation of conv3d_wgrad_kernel)
 //   Conv3d          : P = gz (output grid, Cout), Q = x  (input grid, Cin)   -> grad_w [Cout][Cin][27]
 //   ConvTranspose3d : P = x  (input grid, Cin),   Q = gz (output grid, Cout) -> grad_w [Cin][Cout][27]
 // As MMAs:  D[m][n] += A[m][k] B[k][n] with k = 16 consecutive positions of a P tile, m = 16 channels of one tensor, n = 8 channels
-// of the other, one accumulator tile per filter tap.  Both tensors are staged per step as [channel block][position][8] (16-byte
-// rows, the C8 layout itself), so either can be the M side: ldmatrix.trans turns 8 position rows x 8 channels into the fragment
-// of the channel-major operand, and the row ADDRESSES carry the tap shift and the stride (Q row = (hh s + kh) TWq + (ww s + kw)).
-// A CTA owns one tap group (all 27 taps, the 9 taps of one kd, or the 3 taps of one (kd, kh): whatever keeps the accumulators in
-// registers) and walks P tiles of 8 x 32 positions; its 8 warps split the (tap, m-tile) units and each loops over all 16 k-steps.
-constexpr int kWgTH = 8, kWgTW = 32, kWgWarps = 8;
+// of the other, one accumulator tile per filter tap.  Both tensors are staged per tile by TMA (zero fill outside the volume = the
+// convolution's padding and the ragged tile edges) as [channel block][position][8] -- 16-byte rows, the C8 layout itself -- so
+// either can be the M side: ldmatrix.trans turns 8 position rows x 8 channels into the fragment of the channel-major operand, and
+// the row ADDRESSES carry the tap shift and the stride (Q row = (hh s + kh) TWq + (ww s + kw)).
+// A CTA owns the 9 (kh, kw) taps of one kd (or, when 16 x MT x NB accumulators would not fit the registers, the 3 kw taps of one
+// (kd, kh)) and walks P tiles of TH x 32 positions.  WARP w OWNS TAP w (times a slice of the m-tiles): every warp has the same
+// work, the shifted operand is fetched once per k-step and warp, and nothing but ldmatrix + mma is left in the inner loop
+// (first version: 58 instructions per MMA from index arithmetic and a per-unit dispatch; ncu: tensor pipe 22 %).
+constexpr int kWgTW = 32;
 
 struct WgParams {
-    const void* P; const void* Q; float* grad;
-    int B, PCB, QCB, PCreal, QCreal;       // channel blocks of P / Q; real channel counts (padding blocks are not written)
-    int Dp, Hp, Wp, Dq, Hq, Wq, stride;
+    float* grad;
+    int PCB, QCB, PCreal, QCreal;          // channel blocks of P / Q; real channel counts (padding blocks are not written)
+    int Dp, Dq, stride;
     int a_is_p;                            // M side: 1 = P, 0 = Q
-    int MT, NB;                            // m-tiles (16 channels) of the M side, n-blocks (8 channels) of the N side
-    int tpc, ngroups;                      // taps per CTA (27 / 9 / 3) and tap groups (1 / 3 / 9)
-    int nht, nwt, ntiles;                  // P tiles per plane and in total (B * Dp * nht * nwt)
-    int THq, TWq;                          // staged Q tile (with halo)
-    int q_rows;                            // THq * TWq
+    int MT;                                // m-tiles (16 channels) of the M side
+    int tpc, msplit;                       // taps per CTA (9 / 3); warps = tpc * msplit, each owning MT / msplit m-tiles of one tap
+    int TH, nht, nwt, ntiles, B;           // P tile rows; tiles per plane; tiles in total (B * Dp * nht * nwt)
+    int THq, TWq, q_rows;                  // staged Q tile (with halo)
+    uint32_t p_bytes, q_bytes;             // bytes one TMA brings
 };
+struct WgMaps { CUtensorMap p, q; };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t (&r)[2]) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 template <typename T> __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]);
 template <> __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -279,150 +282,151 @@ template <> __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// UPW = (tap, m-tile) units per warp, NB = n-blocks: UPW * NB * 4 accumulator registers per thread.
-template <typename T, int UPW, int NB>
-__global__ void __launch_bounds__(kWgWarps * 32, 2)
-conv3d_wgrad_mma_kernel(const __grid_constant__ WgParams p) {
+// MTW = m-tiles per warp, NB = n-blocks: MTW * NB * 4 accumulator registers per thread.
+template <typename T, int MTW, int NB>
+__global__ void __launch_bounds__(288, (MTW * NB >= 16) ? 1 : 2)
+conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams p) {
     extern __shared__ __align__(128) uint8_t wg_smem[];
+    __shared__ uint64_t bar;
     uint8_t* sP = wg_smem;                                              // [PCB][TH * TW][8]
-    uint8_t* sQ = wg_smem + (size_t)p.PCB * kWgTH * kWgTW * 16;         // [QCB][THq * TWq][8]
+    uint8_t* sQ = wg_smem + p.p_bytes;                                  // [QCB][THq * TWq][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = blockIdx.y;                                       // tap group
-    const int nkd = p.tpc == 27 ? 3 : 1, nkh = p.tpc >= 9 ? 3 : 1;
-    const int kd0 = p.tpc == 27 ? 0 : (p.tpc == 9 ? group : group / 3), kh0 = p.tpc >= 9 ? 0 : group % 3;
-    const int units = p.tpc * p.MT;                                     // unit u = tap_local * MT + mt, tap_local = (kdi * nkh + khi) * 3 + kw
+    const int group = blockIdx.y;                                       // tap group: kd (tpc = 9) or kd * 3 + kh (tpc = 3)
+    const int kd = p.tpc == 9 ? group : group / 3;
+    const int tapl = warp % p.tpc, mslice = warp / p.tpc;               // this warp's tap inside the group, and its slice of the m-tiles
+    const int kh = p.tpc == 9 ? tapl / 3 : group % 3, kw = tapl % 3;
+    const int mt0 = mslice * MTW;
 
-    float acc[UPW][NB][4];
+    float acc[MTW][NB][4];
 #pragma unroll
-    for (int j = 0; j < UPW; ++j)
+    for (int j = 0; j < MTW; ++j)
 #pragma unroll
         for (int n = 0; n < NB; ++n)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[j][n][e] = 0.f;
 
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wg_smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.p) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q) : "memory");
+    }
+    __syncthreads();
+
     const uint32_t sP32 = wg_smem_u32(sP), sQ32 = wg_smem_u32(sQ);
-    const uint32_t p_blk = kWgTH * kWgTW * 16u, q_blk = (uint32_t)p.q_rows * 16u;      // bytes per channel block
+    const uint32_t p_blk = (uint32_t)(p.TH * kWgTW) * 16u, q_blk = (uint32_t)p.q_rows * 16u;      // bytes per channel block
     const int lj = lane >> 3, li = lane & 7;          // ldmatrix: this lane supplies row li of matrix lj
     const bool a_is_p = p.a_is_p != 0;
     const int MCB = a_is_p ? p.PCB : p.QCB, NCB = a_is_p ? p.QCB : p.PCB;              // channel blocks of the M / N side
-    // Units of this warp: u = warp + 8 j, tap_local = u / MT, m-tile = u % MT = warp % MT for every j (MT divides 8).
-    const int mt = warp % p.MT;
-    const bool half_m = MCB * 8 < (mt + 1) * 16;      // an 8-channel M side: rows 8..15 of the tile do not exist
     // Lane-constant parts of the row addresses.  P rows: position q = hh * TW + ww.  Q rows: (hh s + kh) TWq + ww s + kw.
     //   A matrices (x4): j = 0: (block 2 mt, k 0-7), 1: (2 mt + 1, k 0-7), 2: (2 mt, k 8-15), 3: (2 mt + 1, k 8-15)
     //   B matrices (x4): j = 0: (block n, k 0-7), 1: (n, k 8-15), 2: (n + 1, k 0-7), 3: (n + 1, k 8-15)
-    const int a_cb = min(2 * mt + (lj & 1), MCB - 1), a_k = (lj >> 1) * 8 + li;
-    const int b_dn = lj >> 1, b_k = (lj & 1) * 8 + li;
-    uint32_t unit_shift[UPW];                         // byte offset of the unit's tap inside the Q tile: (kh TWq + kw) * 16
-    int unit_kd[UPW];
+    const uint32_t tap_shift = (uint32_t)(kh * p.TWq + kw) * 16u;
+    uint32_t a_lane[MTW], b_lane[(NB + 1) / 2];
+    bool half_m[MTW];
 #pragma unroll
-    for (int j = 0; j < UPW; ++j) {
-        const int u = warp + kWgWarps * j, tl = u / p.MT;
-        const int kw = tl % 3, khi = (tl / 3) % nkh;
-        unit_kd[j] = u < units ? tl / (3 * nkh) : -1;
-        unit_shift[j] = (uint32_t)((kh0 + khi) * p.TWq + kw) * 16u;
+    for (int j = 0; j < MTW; ++j) {
+        const int cbk = min(2 * (mt0 + j) + (lj & 1), MCB - 1), kk = (lj >> 1) * 8 + li;
+        a_lane[j] = a_is_p ? sP32 + (uint32_t)cbk * p_blk + (uint32_t)kk * 16u
+                           : sQ32 + (uint32_t)cbk * q_blk + tap_shift + (uint32_t)(kk * p.stride) * 16u;
+        half_m[j] = MCB * 8 < (mt0 + j + 1) * 16;     // an 8-channel M side: rows 8..15 of the tile do not exist
     }
+#pragma unroll
+    for (int n = 0; n < NB; n += 2) {
+        const int nbc = min(n + (lj >> 1), NCB - 1), kk = (lj & 1) * 8 + li;
+        b_lane[n / 2] = a_is_p ? sQ32 + (uint32_t)nbc * q_blk + tap_shift + (uint32_t)(kk * p.stride) * 16u
+                               : sP32 + (uint32_t)nbc * p_blk + (uint32_t)kk * 16u;
+    }
+    const uint32_t p_row_h = kWgTW * 16u, q_row_h = (uint32_t)(p.stride * p.TWq) * 16u;          // bytes per tile row hh
+    const uint32_t p_k16 = 16u * 16u, q_k16 = (uint32_t)(16 * p.stride) * 16u;                   // bytes per 16 positions
+    const uint32_t a_row_h = a_is_p ? p_row_h : q_row_h, a_k16 = a_is_p ? p_k16 : q_k16;
+    const uint32_t b_row_h = a_is_p ? q_row_h : p_row_h, b_k16 = a_is_p ? q_k16 : p_k16;
 
+    uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         int tt = t;
         const int wt = tt % p.nwt; tt /= p.nwt;
         const int ht = tt % p.nht; tt /= p.nht;
         const int dp = tt % p.Dp;
         const int b = tt / p.Dp;
-        const int h0 = ht * kWgTH, w0 = wt * kWgTW;
-        bool p_staged = false;
-        for (int kdi = 0; kdi < nkd; ++kdi) {
-            const int qd = dp * p.stride - 1 + kd0 + kdi;
-            if (qd < 0 || qd >= p.Dq) continue;                         // block-uniform: this tap plane lies in the zero padding
-            __syncthreads();                                            // everyone has finished reading the previous tiles
-            if (!p_staged) {                                            // the P tile (zeros outside the volume), once per tile
-                const int nP = p.PCB * kWgTH * kWgTW;
-                for (int i = threadIdx.x; i < nP; i += blockDim.x) {
-                    const int pcb = i / (kWgTH * kWgTW), r = i - pcb * (kWgTH * kWgTW);
-                    const int hh = r / kWgTW, ww = r - hh * kWgTW;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (h0 + hh < p.Hp && w0 + ww < p.Wp)
-                        v = __ldg(reinterpret_cast<const uint4*>(p.P) + ((((int64_t)b * p.PCB + pcb) * p.Dp + dp) * p.Hp + h0 + hh) * p.Wp + w0 + ww);
-                    *reinterpret_cast<uint4*>(sP + (size_t)i * 16) = v;
+        const int qd = dp * p.stride - 1 + kd;
+        if (qd < 0 || qd >= p.Dq) continue;                             // block-uniform: this tap plane lies in the zero padding
+        const int h0 = ht * p.TH, w0 = wt * kWgTW;
+        __syncthreads();                                                // everyone has finished reading the previous tiles
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wg_smem_u32(&bar)), "r"(p.p_bytes + p.q_bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                         ::"r"(sP32), "l"(&maps.p), "r"(wg_smem_u32(&bar)), "r"(0), "r"(w0), "r"(h0), "r"(dp), "r"(b * p.PCB) : "memory");
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                         ::"r"(sQ32), "l"(&maps.q), "r"(wg_smem_u32(&bar)), "r"(0), "r"(w0 * p.stride - 1), "r"(h0 * p.stride - 1), "r"(qd), "r"(b * p.QCB) : "memory");
+        }
+        asm volatile("{\n\t.reg .pred p;\n\tWG_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WG_DONE_%=;\n\tbra WG_WAIT_%=;\n\tWG_DONE_%=:\n\t}"
+                     ::"r"(wg_smem_u32(&bar)), "r"(phase) : "memory");
+        phase ^= 1u;
+        // ---- TH rows x 2 k-steps of 16 positions
+        for (int hh = 0; hh < p.TH; ++hh) {
+#pragma unroll
+            for (int kk = 0; kk < kWgTW / 16; ++kk) {
+                const uint32_t ao = (uint32_t)hh * a_row_h + (uint32_t)kk * a_k16, bo = (uint32_t)hh * b_row_h + (uint32_t)kk * b_k16;
+                uint32_t bfr[NB][2];
+#pragma unroll
+                for (int n = 0; n < NB; n += 2) {
+                    uint32_t f[4];
+                    ldmatrix_x4_trans(b_lane[n / 2] + bo, f);
+                    bfr[n][0] = f[0]; bfr[n][1] = f[1];
+                    if (n + 1 < NB) { bfr[n + 1 < NB ? n + 1 : n][0] = f[2]; bfr[n + 1 < NB ? n + 1 : n][1] = f[3]; }
                 }
-                p_staged = true;
-            }
-            {                                                           // plane qd of the Q tile with its halo
-                const int nQ = p.QCB * p.q_rows;
-                const int gh0 = h0 * p.stride - 1, gw0 = w0 * p.stride - 1;
-                for (int i = threadIdx.x; i < nQ; i += blockDim.x) {
-                    const int qcb = i / p.q_rows, r = i - qcb * p.q_rows;
-                    const int qh = r / p.TWq, qw = r - qh * p.TWq;
-                    const int gh = gh0 + qh, gw = gw0 + qw;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (gh >= 0 && gh < p.Hq && gw >= 0 && gw < p.Wq)
-                        v = __ldg(reinterpret_cast<const uint4*>(p.Q) + ((((int64_t)b * p.QCB + qcb) * p.Dq + qd) * p.Hq + gh) * p.Wq + gw);
-                    *reinterpret_cast<uint4*>(sQ + (size_t)i * 16) = v;
-                }
-            }
-            __syncthreads();
-            // ---- MMAs of this kd phase: 16 k-steps of 16 positions; the unshifted (P) operand is fetched once per k-step
-            for (int ks = 0; ks < kWgTH * kWgTW / 16; ++ks) {
-                const int hh = ks / (kWgTW / 16), wwb = (ks % (kWgTW / 16)) * 16;
-                const uint32_t p_row = (uint32_t)(hh * kWgTW + wwb) * 16u;                            // + k * 16
-                const uint32_t q_row = (uint32_t)(hh * p.stride * p.TWq + wwb * p.stride) * 16u;      // + k * stride * 16 + unit_shift
-                if (a_is_p) {
+#pragma unroll
+                for (int j = 0; j < MTW; ++j) {
                     uint32_t afrag[4];
-                    ldmatrix_x4_trans(sP32 + (uint32_t)a_cb * p_blk + p_row + (uint32_t)a_k * 16u, afrag);
-                    if (half_m) { afrag[1] = 0u; afrag[3] = 0u; }
+                    ldmatrix_x4_trans(a_lane[j] + ao, afrag);
+                    if (half_m[j]) { afrag[1] = 0u; afrag[3] = 0u; }
 #pragma unroll
-                    for (int j = 0; j < UPW; ++j) {
-                        if (unit_kd[j] != kdi) continue;
-                        const uint32_t qa = sQ32 + q_row + unit_shift[j] + (uint32_t)(b_k * p.stride) * 16u;
-#pragma unroll
-                        for (int n = 0; n < NB; n += 2) {
-                            uint32_t bfrag[4];
-                            ldmatrix_x4_trans(qa + (uint32_t)min(n + b_dn, NCB - 1) * q_blk, bfrag);
-                            const uint32_t b0[2] = {bfrag[0], bfrag[1]}, b1[2] = {bfrag[2], bfrag[3]};
-                            mma_16816<T>(acc[j][n], afrag, b0);
-                            if (n + 1 < NB) mma_16816<T>(acc[j][n + 1 < NB ? n + 1 : n], afrag, b1);
-                        }
-                    }
-                } else {
-                    uint32_t bfr[NB][2];
-#pragma unroll
-                    for (int n = 0; n < NB; n += 2) {
-                        uint32_t bfrag[4];
-                        ldmatrix_x4_trans(sP32 + (uint32_t)min(n + b_dn, NCB - 1) * p_blk + p_row + (uint32_t)b_k * 16u, bfrag);
-                        bfr[n][0] = bfrag[0]; bfr[n][1] = bfrag[1];
-                        if (n + 1 < NB) { bfr[n + 1 < NB ? n + 1 : n][0] = bfrag[2]; bfr[n + 1 < NB ? n + 1 : n][1] = bfrag[3]; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < UPW; ++j) {
-                        if (unit_kd[j] != kdi) continue;
-                        uint32_t afrag[4];
-                        ldmatrix_x4_trans(sQ32 + (uint32_t)a_cb * q_blk + q_row + unit_shift[j] + (uint32_t)(a_k * p.stride) * 16u, afrag);
-                        if (half_m) { afrag[1] = 0u; afrag[3] = 0u; }
-#pragma unroll
-                        for (int n = 0; n < NB; ++n) mma_16816<T>(acc[j][n], afrag, bfr[n]);
-                    }
+                    for (int n = 0; n < NB; ++n) mma_16816<T>(acc[j][n], afrag, bfr[n]);
                 }
             }
         }
     }
     // ---- write-out: C fragment (m = lane / 4 (+ 8), n = 2 (lane % 4) + {0, 1}) -> grad[pc][qc][tap], torch layout
     const int QC = p.QCreal, PC = p.PCreal;
+    const int tap = (kd * 3 + kh) * 3 + kw;
 #pragma unroll
-    for (int j = 0; j < UPW; ++j) {
-        const int u = warp + kWgWarps * j;
-        if (u >= units) continue;
-        const int tl = u / p.MT;
-        const int kw = tl % 3, khi = (tl / 3) % nkh, kdu = tl / (3 * nkh);
-        const int tap = ((kd0 + kdu) * 3 + (kh0 + khi)) * 3 + kw;
+    for (int j = 0; j < MTW; ++j)
 #pragma unroll
         for (int n = 0; n < NB; ++n)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int m = mt * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0), nn = n * 8 + 2 * (lane & 3) + (e & 1);
-                const int pc = p.a_is_p ? m : nn, qc = p.a_is_p ? nn : m;
+                const int m = (mt0 + j) * 16 + (lane >> 2) + ((e >> 1) ? 8 : 0), nn = n * 8 + 2 * (lane & 3) + (e & 1);
+                const int pc = a_is_p ? m : nn, qc = a_is_p ? nn : m;
                 if (pc < PC && qc < QC && acc[j][n][e] != 0.f) atomicAdd(p.grad + ((int64_t)pc * QC + qc) * 27 + tap, acc[j][n][e]);
             }
+}
+
+typedef CUresult (*WgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WgEncodeTiledFn wg_encode_tiled() {
+    static WgEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<WgEncodeTiledFn>(p);
     }
+    return fn;
+}
+
+// C8 volume [B][CB][D][H][W][8] as a 5-D tensor {8, W, H, D, B * CB}; box {8, bw, bh, 1, CB}: all channel blocks of one tile
+static int wg_make_map(CUtensorMap* m, const void* base, int is_bf16, int B, int CB, int D, int H, int W, int bw, int bh) {
+    WgEncodeTiledFn enc = wg_encode_tiled();
+    MVS_REQUIRE(enc, MVS_E_LAUNCH, "mvs_conv3d_wgrad_mma: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * CB};
+    const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1, (cuuint32_t)CB}, estr[5] = {1, 1, 1, 1, 1};
+    const CUresult cr = enc(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstr, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MVS_REQUIRE(cr == CUDA_SUCCESS, MVS_E_LAUNCH, "mvs_conv3d_wgrad_mma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return MVS_OK;
 }
 
 extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real,
@@ -434,52 +438,64 @@ extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, con
     MVS_REQUIRE(d->stride == 1 || d->stride == 2, MVS_E_SHAPE, "mvs_conv3d_wgrad_mma: stride must be 1 or 2");
     MVS_REQUIRE(cout_real >= 1 && cout_real <= d->Cout, MVS_E_ARG, "mvs_conv3d_wgrad_mma: bad cout_real");
     WgParams p;
+    memset(&p, 0, sizeof(p));
     const bool tr = d->transposed != 0;
-    p.P = tr ? x : grad_z; p.Q = tr ? grad_z : x; p.grad = grad_w;
-    p.B = d->B;
+    const void* P = tr ? x : grad_z;
+    const void* Q = tr ? grad_z : x;
+    p.grad = grad_w; p.B = d->B;
     const int PC = tr ? d->Cin : d->Cout, QC = tr ? d->Cout : d->Cin;
     p.PCB = PC / 8; p.QCB = QC / 8;
     p.PCreal = tr ? d->Cin : cout_real; p.QCreal = tr ? cout_real : d->Cin;
-    p.Dp = tr ? d->Din : d->Dout; p.Hp = tr ? d->Hin : d->Hout; p.Wp = tr ? d->Win : d->Wout;
-    p.Dq = tr ? d->Dout : d->Din; p.Hq = tr ? d->Hout : d->Hin; p.Wq = tr ? d->Wout : d->Win;
+    const int Hp = tr ? d->Hin : d->Hout, Wp = tr ? d->Win : d->Wout, Hq = tr ? d->Hout : d->Hin, Wq = tr ? d->Wout : d->Win;
+    p.Dp = tr ? d->Din : d->Dout; p.Dq = tr ? d->Dout : d->Din;
     p.stride = d->stride;
     // M side: a tensor whose channel count is a multiple of 16 (the wider one if both are); else P with its upper half empty
     if (PC % 16 == 0 && (QC % 16 != 0 || PC >= QC)) p.a_is_p = 1;
     else if (QC % 16 == 0) p.a_is_p = 0;
     else p.a_is_p = 1;
     const int MC = p.a_is_p ? PC : QC, NC = p.a_is_p ? QC : PC;
-    p.MT = (MC + 15) / 16; p.NB = NC / 8;
+    p.MT = (MC + 15) / 16;
+    const int NB = NC / 8;
     MVS_REQUIRE(p.MT == 1 || p.MT == 2 || p.MT == 4, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: %d channels on the M side (16, 32 or 64 supported)", MC);
-    // taps per CTA: the largest group whose accumulators fit (UPW * NB <= 16 -> <= 64 registers per thread)
-    const int tpcs[3] = {27, 9, 3};
-    int upw = 0;
-    p.tpc = 0;
-    for (int i = 0; i < 3 && !p.tpc; ++i) {
-        const int u = (tpcs[i] * p.MT + kWgWarps - 1) / kWgWarps;
-        if (u * p.NB <= 16) { p.tpc = tpcs[i]; upw = u; }
+    MVS_REQUIRE(NB == 1 || NB == 2 || NB == 4 || NB == 8, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: %d channels on the N side (8, 16, 32 or 64 supported)", NC);
+    // one warp per tap; when a warp's MT x NB accumulator tiles exceed 64 registers the CTA takes 3 taps and two warps share a tap
+    if (p.MT * NB <= 16) { p.tpc = 9; p.msplit = 1; } else { p.tpc = 3; p.msplit = 2; }
+    const int mtw = p.MT / p.msplit;
+    const int nwarps = p.tpc * p.msplit;
+    // tile rows: 16 when both tiles stay small (thin layers: amortises the per-tile TMA round trip), else 8
+    p.TH = 16;
+    for (;;) {
+        p.THq = p.TH * p.stride + 2; p.TWq = kWgTW * p.stride + 2; p.q_rows = p.THq * p.TWq;
+        p.p_bytes = (uint32_t)p.PCB * p.TH * kWgTW * 16u; p.q_bytes = (uint32_t)p.QCB * p.q_rows * 16u;
+        if (p.TH == 8 || p.p_bytes + p.q_bytes <= 56 * 1024) break;
+        p.TH = 8;
     }
-    MVS_REQUIRE(p.tpc, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: no tap grouping fits the registers for %d x %d channels", MC, NC);
-    p.ngroups = 27 / p.tpc;
-    p.nht = (p.Hp + kWgTH - 1) / kWgTH; p.nwt = (p.Wp + kWgTW - 1) / kWgTW;
+    const size_t smem = (size_t)p.p_bytes + p.q_bytes;
+    MVS_REQUIRE(smem <= 110 * 1024, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tiles of %d + %d channels at stride %d need %zu bytes of shared memory", PC, QC, p.stride, smem);
+    MVS_REQUIRE(p.TWq <= 256 && p.THq <= 256, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tile exceeds the TMA box limit");
+    p.nht = (Hp + p.TH - 1) / p.TH; p.nwt = (Wp + kWgTW - 1) / kWgTW;
     p.ntiles = p.B * p.Dp * p.nht * p.nwt;
-    p.THq = kWgTH * p.stride + 2; p.TWq = kWgTW * p.stride + 2;
-    p.q_rows = p.THq * p.TWq;
-    const size_t smem = ((size_t)p.PCB * kWgTH * kWgTW + (size_t)p.QCB * p.q_rows) * 16;
-    MVS_REQUIRE(smem <= 113 * 1024, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tiles of %d + %d channels at stride %d need %zu bytes of shared memory", PC, QC, p.stride, smem);
-    int gx = (2 * 148 * 2 + p.ngroups - 1) / p.ngroups;
+    WgMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const int is_bf16 = d->dtype_in == MVS_BF16;
+    int rc = wg_make_map(&maps.p, P, is_bf16, p.B, p.PCB, p.Dp, Hp, Wp, kWgTW, p.TH);
+    if (rc) return rc;
+    rc = wg_make_map(&maps.q, Q, is_bf16, p.B, p.QCB, p.Dq, Hq, Wq, p.TWq, p.THq);
+    if (rc) return rc;
+    const int ngroups = 27 / p.tpc;
+    const int per_sm = smem <= 36 * 1024 ? 4 : (smem <= 56 * 1024 ? 3 : 2);     // resident CTAs (shared memory; registers allow >= 2)
+    int gx = (148 * per_sm + ngroups - 1) / ngroups;
     if (gx > p.ntiles) gx = p.ntiles;
-    const dim3 grid((unsigned)gx, (unsigned)p.ngroups);
+    const dim3 grid((unsigned)gx, (unsigned)ngroups);
     cudaStream_t st = (cudaStream_t)stream;
-#define MVS_WG_LAUNCH(T, U, N) do { cudaFuncSetAttribute(conv3d_wgrad_mma_kernel<T, U, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                                    conv3d_wgrad_mma_kernel<T, U, N><<<grid, kWgWarps * 32, smem, st>>>(p); } while (0)
-#define MVS_WG_BY_SHAPE(T) do { \
-        if (p.NB == 1) { if (upw <= 4) MVS_WG_LAUNCH(T, 4, 1); else MVS_WG_LAUNCH(T, 7, 1); } \
-        else if (p.NB == 2) { if (upw <= 4) MVS_WG_LAUNCH(T, 4, 2); else MVS_WG_LAUNCH(T, 7, 2); } \
-        else if (p.NB == 4) { if (upw <= 2) MVS_WG_LAUNCH(T, 2, 4); else MVS_WG_LAUNCH(T, 4, 4); } \
-        else if (p.NB == 8) MVS_WG_LAUNCH(T, 2, 8); \
-        else return mvs_set_error(MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: %d n-blocks", p.NB); } while (0)
-    if (d->dtype_in == MVS_F16) MVS_WG_BY_SHAPE(__half); else MVS_WG_BY_SHAPE(__nv_bfloat16);
+#define MVS_WG_LAUNCH(T, M, N) do { cudaFuncSetAttribute(conv3d_wgrad_mma_kernel<T, M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                                    conv3d_wgrad_mma_kernel<T, M, N><<<grid, nwarps * 32, smem, st>>>(maps, p); } while (0)
+#define MVS_WG_BY_NB(T, M) do { if (NB == 1) MVS_WG_LAUNCH(T, M, 1); else if (NB == 2) MVS_WG_LAUNCH(T, M, 2); \
+                                else if (NB == 4) { if (M * 4 <= 16) MVS_WG_LAUNCH(T, M, 4); } else { if (M * 8 <= 16) MVS_WG_LAUNCH(T, (M * 8 <= 16 ? M : 1), 8); } } while (0)
+#define MVS_WG_BY_SHAPE(T) do { if (mtw == 1) MVS_WG_BY_NB(T, 1); else if (mtw == 2) MVS_WG_BY_NB(T, 2); else MVS_WG_BY_NB(T, 4); } while (0)
+    if (is_bf16) MVS_WG_BY_SHAPE(__nv_bfloat16); else MVS_WG_BY_SHAPE(__half);
 #undef MVS_WG_BY_SHAPE
+#undef MVS_WG_BY_NB
 #undef MVS_WG_LAUNCH
     return MVS_CHECK_LAUNCH("mvs_conv3d_wgrad_mma");
 }

@@ -145,9 +145,9 @@ def test_mvsnet_16bit_training_gradients_against_the_reference(gpu, golden, tdt,
     err, cos = {}, {}
     for k, v in g.items():
         if k.startswith("grad."):
-            a = params[k[5:]].grad.detach().float().cpu().flatten()
-            err[k] = nerr(a, v)
-            cos[k] = float(torch.dot(a, v.flatten()) / (a.norm() * v.norm() + 1e-30))
+            a, r = params[k[5:]].grad.detach().float().cpu().flatten(), v.float().flatten()
+            err[k] = nerr(a, r)
+            cos[k] = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
     print("%s training vs reference: depth %.3e; gradient norm-relative error median %.3e max %.3e; cosine min %.4f" % (
         tdt, derr, sorted(err.values())[len(err) // 2], max(err.values()), min(cos.values())))
     assert derr < 2e-2
