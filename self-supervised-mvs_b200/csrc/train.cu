@@ -287,9 +287,9 @@ template <typename T, int MTW, int NB>
 __global__ void __launch_bounds__(288, (MTW * NB >= 16) ? 1 : 2)
 conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams p) {
     extern __shared__ __align__(128) uint8_t wg_smem[];
-    __shared__ uint64_t bar;
-    uint8_t* sP = wg_smem;                                              // [PCB][TH * TW][8]
-    uint8_t* sQ = wg_smem + p.p_bytes;                                  // [QCB][THq * TWq][8]
+    __shared__ uint64_t bar[2];
+    uint8_t* sP = wg_smem;                                              // per buffer: [PCB][TH * TW][8] then [QCB][THq * TWq][8]
+    uint8_t* sQ = wg_smem + p.p_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.y;                                       // tap group: kd (tpc = 9) or kd * 3 + kh (tpc = 3)
     const int kd = p.tpc == 9 ? group : group / 3;
@@ -306,7 +306,8 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
             for (int e = 0; e < 4; ++e) acc[j][n][e] = 0.f;
 
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wg_smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wg_smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wg_smem_u32(&bar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.p) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q) : "memory");
@@ -342,32 +343,50 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
     const uint32_t a_row_h = a_is_p ? p_row_h : q_row_h, a_k16 = a_is_p ? p_k16 : q_k16;
     const uint32_t b_row_h = a_is_p ? q_row_h : p_row_h, b_k16 = a_is_p ? q_k16 : p_k16;
 
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    // Two tile buffers: the TMA of the NEXT tile of this CTA is in flight while the warps run the MMAs of the current one.
+    const uint32_t buf_bytes = p.p_bytes + p.q_bytes;
+    auto tile_coords = [&](int t, int& b, int& dp, int& h0, int& w0, int& qd) {
         int tt = t;
         const int wt = tt % p.nwt; tt /= p.nwt;
         const int ht = tt % p.nht; tt /= p.nht;
-        const int dp = tt % p.Dp;
-        const int b = tt / p.Dp;
-        const int qd = dp * p.stride - 1 + kd;
-        if (qd < 0 || qd >= p.Dq) continue;                             // block-uniform: this tap plane lies in the zero padding
-        const int h0 = ht * p.TH, w0 = wt * kWgTW;
-        __syncthreads();                                                // everyone has finished reading the previous tiles
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wg_smem_u32(&bar)), "r"(p.p_bytes + p.q_bytes) : "memory");
-            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                         ::"r"(sP32), "l"(&maps.p), "r"(wg_smem_u32(&bar)), "r"(0), "r"(w0), "r"(h0), "r"(dp), "r"(b * p.PCB) : "memory");
-            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                         ::"r"(sQ32), "l"(&maps.q), "r"(wg_smem_u32(&bar)), "r"(0), "r"(w0 * p.stride - 1), "r"(h0 * p.stride - 1), "r"(qd), "r"(b * p.QCB) : "memory");
-        }
+        dp = tt % p.Dp; b = tt / p.Dp;
+        h0 = ht * p.TH; w0 = wt * kWgTW;
+        qd = dp * p.stride - 1 + kd;
+        return qd >= 0 && qd < p.Dq;                                    // false: this tap plane lies in the zero padding (block-uniform)
+    };
+    auto next_valid = [&](int t) {                                      // first tile >= t of this CTA whose tap plane exists
+        int b, dp, h0, w0, qd;
+        while (t < p.ntiles && !tile_coords(t, b, dp, h0, w0, qd)) t += gridDim.x;
+        return t;
+    };
+    auto issue = [&](int t, int buf) {                                  // thread 0: both TMA loads of tile t into buffer buf
+        int b, dp, h0, w0, qd;
+        tile_coords(t, b, dp, h0, w0, qd);
+        const uint32_t mb = wg_smem_u32(&bar[buf]), dst = sP32 + (uint32_t)buf * buf_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(buf_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                     ::"r"(dst), "l"(&maps.p), "r"(mb), "r"(0), "r"(w0), "r"(h0), "r"(dp), "r"(b * p.PCB) : "memory");
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                     ::"r"(dst + p.p_bytes), "l"(&maps.q), "r"(mb), "r"(0), "r"(w0 * p.stride - 1), "r"(h0 * p.stride - 1), "r"(qd), "r"(b * p.QCB) : "memory");
+    };
+    int t = next_valid(blockIdx.x);
+    if (threadIdx.x == 0 && t < p.ntiles) issue(t, 0);
+    uint32_t phase[2] = {0u, 0u};
+    for (int it = 0; t < p.ntiles; ++it) {
+        const int buf = it & 1;
+        const int tn = next_valid(t + gridDim.x);
+        // buffer buf ^ 1 was last read in iteration it - 1; the barrier at the end of that iteration makes it free
+        if (threadIdx.x == 0 && tn < p.ntiles) issue(tn, buf ^ 1);
         asm volatile("{\n\t.reg .pred p;\n\tWG_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WG_DONE_%=;\n\tbra WG_WAIT_%=;\n\tWG_DONE_%=:\n\t}"
-                     ::"r"(wg_smem_u32(&bar)), "r"(phase) : "memory");
-        phase ^= 1u;
+                     ::"r"(wg_smem_u32(&bar[buf])), "r"(phase[buf]) : "memory");
+        phase[buf] ^= 1u;
+        const uint32_t bufo = (uint32_t)buf * buf_bytes;
         // ---- TH rows x 2 k-steps of 16 positions
+#pragma unroll 2
         for (int hh = 0; hh < p.TH; ++hh) {
 #pragma unroll
             for (int kk = 0; kk < kWgTW / 16; ++kk) {
-                const uint32_t ao = (uint32_t)hh * a_row_h + (uint32_t)kk * a_k16, bo = (uint32_t)hh * b_row_h + (uint32_t)kk * b_k16;
+                const uint32_t ao = bufo + (uint32_t)hh * a_row_h + (uint32_t)kk * a_k16, bo = bufo + (uint32_t)hh * b_row_h + (uint32_t)kk * b_k16;
                 uint32_t bfr[NB][2];
 #pragma unroll
                 for (int n = 0; n < NB; n += 2) {
@@ -386,6 +405,8 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
                 }
             }
         }
+        __syncthreads();                                                // every warp is done with buffer buf: it may be refilled next iteration
+        t = tn;
     }
     // ---- write-out: C fragment (m = lane / 4 (+ 8), n = 2 (lane % 4) + {0, 1}) -> grad[pc][qc][tap], torch layout
     const int QC = p.QCreal, PC = p.PCreal;
@@ -467,11 +488,11 @@ extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, con
     for (;;) {
         p.THq = p.TH * p.stride + 2; p.TWq = kWgTW * p.stride + 2; p.q_rows = p.THq * p.TWq;
         p.p_bytes = (uint32_t)p.PCB * p.TH * kWgTW * 16u; p.q_bytes = (uint32_t)p.QCB * p.q_rows * 16u;
-        if (p.TH == 8 || p.p_bytes + p.q_bytes <= 56 * 1024) break;
+        if (p.TH == 8 || p.p_bytes + p.q_bytes <= 48 * 1024) break;
         p.TH = 8;
     }
-    const size_t smem = (size_t)p.p_bytes + p.q_bytes;
-    MVS_REQUIRE(smem <= 110 * 1024, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tiles of %d + %d channels at stride %d need %zu bytes of shared memory", PC, QC, p.stride, smem);
+    const size_t smem = 2 * ((size_t)p.p_bytes + p.q_bytes);            // two tile buffers
+    MVS_REQUIRE(smem <= 220 * 1024, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tiles of %d + %d channels at stride %d need %zu bytes of shared memory", PC, QC, p.stride, smem);
     MVS_REQUIRE(p.TWq <= 256 && p.THq <= 256, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tile exceeds the TMA box limit");
     p.nht = (Hp + p.TH - 1) / p.TH; p.nwt = (Wp + kWgTW - 1) / kWgTW;
     p.ntiles = p.B * p.Dp * p.nht * p.nwt;
@@ -483,7 +504,7 @@ extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, con
     rc = wg_make_map(&maps.q, Q, is_bf16, p.B, p.QCB, p.Dq, Hq, Wq, p.TWq, p.THq);
     if (rc) return rc;
     const int ngroups = 27 / p.tpc;
-    const int per_sm = smem <= 36 * 1024 ? 4 : (smem <= 56 * 1024 ? 3 : 2);     // resident CTAs (shared memory; registers allow >= 2)
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;                      // resident CTAs (shared memory; registers allow 2 at most)
     int gx = (148 * per_sm + ngroups - 1) / ngroups;
     if (gx > p.ntiles) gx = p.ntiles;
     const dim3 grid((unsigned)gx, (unsigned)ngroups);

@@ -1,4 +1,5 @@
-"""BASELINE.json configs[3]: one JDACS training step (photometric loss, N = 5, 512x640, D = 192, fp32): forward / backward / Adam times."""
+"""BASELINE.json configs[3]: one JDACS training step (photometric loss, N = 5, 512x640, D = 192): forward / backward / Adam times and the
+top kernels.  `python tools/train_time.py [fp32|bf16|fp16]` selects the train dtype (default: the model default, bf16)."""
 import os
 import sys
 
@@ -14,7 +15,8 @@ from ssmvs_b200.jdacs.models.mvsnet import MVSNet  # noqa: E402
 dev = torch.device("cuda:0")
 ssmvs_b200._lib.bind()
 torch.manual_seed(0)
-model = MVSNet(refine=False).to(dev).train()
+tdt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}.get(sys.argv[1] if len(sys.argv) > 1 else "", None)
+model = MVSNet(refine=False, train_dtype=tdt).to(dev).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 crit = UnSupLoss()
 inp = {k: v.to(dev) for k, v in synth.mvsnet_inputs(1, 5, 512, 640, 192, seed=2).items()}
@@ -43,4 +45,4 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     loss = crit(inp["imgs"], inp["cams"], out["depth"])
     opt.zero_grad(); loss.backward(); opt.step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
