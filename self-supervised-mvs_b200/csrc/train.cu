@@ -264,7 +264,7 @@ struct WgParams {
     int tpc, msplit;                       // taps per CTA (9 / 3); warps = tpc * msplit, each owning MT / msplit m-tiles of one tap
     int TH, nht, nwt, ntiles, B;           // P tile rows; tiles per plane; tiles in total (B * Dp * nht * nwt)
     int THq, TWq, q_rows;                  // staged Q tile (with halo)
-    uint32_t p_bytes, q_bytes;             // bytes one TMA brings
+    uint32_t p_bytes, q_bytes, buf_stride; // bytes one TMA brings; distance between the two tile buffers (128-byte aligned)
 };
 struct WgMaps { CUtensorMap p, q; };
 
@@ -344,7 +344,7 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
     const uint32_t b_row_h = a_is_p ? q_row_h : p_row_h, b_k16 = a_is_p ? q_k16 : p_k16;
 
     // Two tile buffers: the TMA of the NEXT tile of this CTA is in flight while the warps run the MMAs of the current one.
-    const uint32_t buf_bytes = p.p_bytes + p.q_bytes;
+    const uint32_t buf_bytes = p.p_bytes + p.q_bytes, buf_stride = p.buf_stride;
     auto tile_coords = [&](int t, int& b, int& dp, int& h0, int& w0, int& qd) {
         int tt = t;
         const int wt = tt % p.nwt; tt /= p.nwt;
@@ -362,7 +362,7 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
     auto issue = [&](int t, int buf) {                                  // thread 0: both TMA loads of tile t into buffer buf
         int b, dp, h0, w0, qd;
         tile_coords(t, b, dp, h0, w0, qd);
-        const uint32_t mb = wg_smem_u32(&bar[buf]), dst = sP32 + (uint32_t)buf * buf_bytes;
+        const uint32_t mb = wg_smem_u32(&bar[buf]), dst = sP32 + (uint32_t)buf * buf_stride;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(buf_bytes) : "memory");
         asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                      ::"r"(dst), "l"(&maps.p), "r"(mb), "r"(0), "r"(w0), "r"(h0), "r"(dp), "r"(b * p.PCB) : "memory");
@@ -380,7 +380,7 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
         asm volatile("{\n\t.reg .pred p;\n\tWG_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WG_DONE_%=;\n\tbra WG_WAIT_%=;\n\tWG_DONE_%=:\n\t}"
                      ::"r"(wg_smem_u32(&bar[buf])), "r"(phase[buf]) : "memory");
         phase[buf] ^= 1u;
-        const uint32_t bufo = (uint32_t)buf * buf_bytes;
+        const uint32_t bufo = (uint32_t)buf * buf_stride;
         // ---- TH rows x 2 k-steps of 16 positions
 #pragma unroll 2
         for (int hh = 0; hh < p.TH; ++hh) {
@@ -491,7 +491,8 @@ extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, con
         if (p.TH == 8 || p.p_bytes + p.q_bytes <= 48 * 1024) break;
         p.TH = 8;
     }
-    const size_t smem = 2 * ((size_t)p.p_bytes + p.q_bytes);            // two tile buffers
+    p.buf_stride = (p.p_bytes + p.q_bytes + 127u) & ~127u;              // TMA destinations are 128-byte aligned
+    const size_t smem = 2 * (size_t)p.buf_stride;                       // two tile buffers
     MVS_REQUIRE(smem <= 220 * 1024, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tiles of %d + %d channels at stride %d need %zu bytes of shared memory", PC, QC, p.stride, smem);
     MVS_REQUIRE(p.TWq <= 256 && p.THq <= 256, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tile exceeds the TMA box limit");
     p.nht = (Hp + p.TH - 1) / p.TH; p.nwt = (Wp + kWgTW - 1) / kWgTW;
