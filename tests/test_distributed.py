@@ -40,6 +40,41 @@ def test_two_rank_sharding_and_gradient_allreduce():
     assert t0 == t1 == 11.0
 
 
+def _flat_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import ssmvs_b200
+    from ssmvs_b200 import parallel
+    from ssmvs_b200.trainer import FlatGrads
+    parallel.init_from_env("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    flat = FlatGrads(net.parameters())
+    opt = torch.optim.SGD(flat.params, lr=0.5)
+    for step in range(2):                                   # gradients accumulate into the views; zero() clears them between steps
+        flat.zero()
+        net(torch.full((2, 4), float(rank + 1 + step))).sum().backward()
+        assert all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)       # autograd wrote INTO the flat buffer
+        work = flat.allreduce()
+        if work is not None:
+            work.wait()
+        opt.step()
+    out[rank] = (flat.flat.clone(), [p.detach().clone() for p in net.parameters()])
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_allreduce_keeps_replicas_identical():
+    """trainer.FlatGrads: every .grad is a view of one flat fp32 buffer, ONE (async) all-reduce per optimiser step averages it
+    over the ranks, and ranks that see different data stay bit-identical in their weights."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_flat_worker, args=(world, 29617, out), nprocs=world, join=True)
+    (f0, p0), (f1, p1) = out[0], out[1]
+    assert torch.equal(f0, f1) and f0.abs().sum() > 0
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))
+
+
 def test_shard_items_covers_everything():
     from ssmvs_b200 import parallel
     for n in (1, 7, 8, 13):
