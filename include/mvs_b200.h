@@ -225,6 +225,24 @@ int mvs_invwarp_bwd(const float* img, const float* left_cam, const float* right_
                     const float* grad_warped, float* grad_depth, float* grad_img, float* cam_ws, int B, int H,
                     int W, int C, void* stream);
 
+/* ---- a11 / f2: the self-supervised photometric loss, fused ----------------------------------------------------- */
+/* UnSupLoss.forward (jdacs/losses/unsup_loss.py:24-83; jdacs-ms/losses/unsup_loss.py:23-86) on losses/modules.py:17-90 and
+ * the warp above: x0.25 resize of the views, inverse warp of every source view, masked smooth-L1 of colours and colour
+ * gradients per view, 3x3 SSIM (views 1 and 2), edge-aware depth smoothness, top-3 view selection per pixel.
+ *   imgs  [B][N][3][Hi][Wi] fp32 with (Hi, Wi) = (H, W) or 4x that (bilinear x0.25, as the jdacs tree does); cams [B][N][2][4][4];
+ *   depth [B][H][W]; N - 1 >= 3 source views (the reference's top-k with k = 3 fails below that: MVS_E_SHAPE).
+ *   out   [4] = { 12 rec + 6 ssim + smooth_weight smooth, rec (reconstr_loss), ssim (ssim_loss), smooth (smooth_loss) }.
+ * Buffers the backward reuses (caller-owned, written here): small [N][B][H][W][3], warped [N-1][B][H][W][3],
+ * mask [N-1][B][H][W], coef [2][B][H][W][9], cam_ws [(N-1) B][24], acc [MVS_LOSS_ACC_DOUBLES] doubles. */
+#define MVS_LOSS_ACC_DOUBLES 48
+int mvs_unsup_loss_fwd(const float* imgs, const float* cams, const float* depth, int B, int N, int Hi, int Wi, int H, int W,
+                       float smooth_lambda, float smooth_weight, float* small, float* warped, float* mask, float* coef,
+                       float* cam_ws, double* acc, float* out, void* stream);
+/* grad_out [4] = d L / d out (device); grad_depth [B][H][W] written.  The images carry no gradient. */
+int mvs_unsup_loss_bwd(const float* grad_out, const float* small, const float* depth, const float* warped, const float* mask,
+                       const float* coef, const float* cam_ws, const double* acc, float* grad_depth, int B, int N, int H, int W,
+                       float smooth_lambda, float smooth_weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

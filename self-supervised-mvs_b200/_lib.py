@@ -70,6 +70,8 @@ _SIGS = {
     "mvs_depth_hypo_refine": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "mvs_invwarp_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "mvs_invwarp_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "mvs_unsup_loss_fwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "mvs_unsup_loss_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P], _I),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -1,13 +1,12 @@
-"""Mirror of `losses/unsup_loss.py` (jdacs/losses/unsup_loss.py:19-83): UnSupLoss with the photometric warp on the
-B200 kernel; reconstruction / SSIM / smoothness / top-3 view selection stay PyTorch compositions."""
+"""Mirror of `losses/unsup_loss.py` (jdacs/losses/unsup_loss.py:19-83): UnSupLoss as ONE fused forward and ONE fused backward
+call of libmvs_b200.so (mvs_unsup_loss_fwd / _bwd, csrc/loss.cu): resize, photometric warp of every source view, masked
+smooth-L1 of colours and colour gradients, SSIM, depth smoothness and the top-3 view selection."""
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
-from .homography import inverse_warping
-from .modules import SSIM, compute_reconstr_loss, depth_smoothness
+from ... import ops
+from .modules import SSIM
 
 
 class UnSupLoss(nn.Module):
@@ -15,42 +14,21 @@ class UnSupLoss(nn.Module):
     .smooth_loss, .unsup_loss (read by jdacs/train.py:142,211-212).  Needs N >= 4: top-k with k=3 (hazard H5).
 
     downscale / smooth_weight / smooth_lambda select the variant: jdacs = (True, 0.18, args.smooth_lambda=1.0),
-    jdacs-ms = (False, 0.05, 1.0)."""
+    jdacs-ms = (False, 0.05, 1.0).  The gradient reaches `depth`; the views are data."""
 
     def __init__(self, downscale=True, smooth_weight=0.18, smooth_lambda=1.0):
         super().__init__()
-        self.ssim = SSIM()
+        self.ssim = SSIM()          # attribute kept for API parity (the reference builds it in __init__, :21-22)
         self.downscale = downscale
         self.smooth_weight = smooth_weight
         self.smooth_lambda = smooth_lambda
 
-    def _prep(self, img):
-        if self.downscale:
-            img = F.interpolate(img, scale_factor=0.25, mode='bilinear')
-        return img.permute(0, 2, 3, 1)
-
     def forward(self, imgs, cams, depth):
-        imgs = torch.unbind(imgs, 1)
-        cams = torch.unbind(cams, 1)
-        assert len(imgs) == len(cams), "Different number of images and projection matrices"
-        num_views = len(imgs)
-        ref_img, ref_cam = self._prep(imgs[0]), cams[0]
-        self.reconstr_loss = 0
-        self.ssim_loss = 0
-        self.smooth_loss = 0
-        reprojection_losses = []
-        for view in range(1, num_views):
-            view_img = self._prep(imgs[view])
-            warped_img, mask = inverse_warping(view_img, ref_cam, cams[view], depth)
-            reconstr_loss = compute_reconstr_loss(warped_img, ref_img, mask, simple=False)
-            reprojection_losses.append(reconstr_loss + 1e4 * (1 - mask))
-            if view < 3:
-                self.ssim_loss += torch.mean(self.ssim(ref_img, warped_img, mask))
-        self.smooth_loss += depth_smoothness(depth.unsqueeze(dim=-1), ref_img, self.smooth_lambda)
-        reprojection_volume = torch.stack(reprojection_losses).permute(1, 2, 3, 4, 0)
-        top_vals, _ = torch.topk(torch.neg(reprojection_volume), k=3, sorted=False)
-        top_vals = torch.neg(top_vals)
-        top_vals = top_vals * (top_vals < 1e4).float()
-        self.reconstr_loss = torch.mean(torch.sum(top_vals, dim=-1))
-        self.unsup_loss = 12 * self.reconstr_loss + 6 * self.ssim_loss + self.smooth_weight * self.smooth_loss
+        assert imgs.shape[1] == cams.shape[1], "Different number of images and projection matrices"
+        want = 4 if self.downscale else 1
+        if imgs.shape[-2] // want != depth.shape[-2] or imgs.shape[-1] // want != depth.shape[-1]:
+            raise ValueError("UnSupLoss(downscale=%s) needs views at %dx the depth map's size, got %s vs %s"
+                             % (self.downscale, want, tuple(imgs.shape[-2:]), tuple(depth.shape[-2:])))
+        out = ops.unsup_loss(imgs, cams, depth, self.smooth_lambda, self.smooth_weight)
+        self.unsup_loss, self.reconstr_loss, self.ssim_loss, self.smooth_loss = out[0], out[1], out[2], out[3]
         return self.unsup_loss

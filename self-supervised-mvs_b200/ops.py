@@ -648,3 +648,47 @@ class _InvWarp(torch.autograd.Function):
 def inverse_warp(img: Tensor, left_cam: Tensor, right_cam: Tensor, depth: Tensor) -> Tuple[Tensor, Tensor]:
     """img [B,H,W,C], cams [B,2,4,4], depth [B,H,W] -> (warped [B,H,W,C], mask [B,H,W,1])."""
     return _InvWarp.apply(img, left_cam, right_cam, depth)
+
+
+# ------------------------------------------------------------------------------------------------ fused self-supervised loss
+class _UnsupLoss(torch.autograd.Function):
+    """mvs_unsup_loss_fwd / _bwd: out [4] = (total, reconstr, ssim, smooth); the gradient reaches depth only."""
+
+    @staticmethod
+    def forward(ctx, depth: Tensor, imgs: Tensor, cams: Tensor, smooth_lambda: float, smooth_weight: float):
+        imgs_c, cams_c, depth_c = _f32c(imgs), _f32c(cams), _f32c(depth)
+        b, n, ch, hi, wi = imgs_c.shape
+        if ch != 3:
+            raise ValueError("UnSupLoss expects 3-channel views, got %d channels" % ch)
+        h, w = depth_c.shape[1], depth_c.shape[2]
+        dev, f32 = depth_c.device, torch.float32
+        small = torch.empty(n, b, h, w, 3, dtype=f32, device=dev)
+        warped = torch.empty(n - 1, b, h, w, 3, dtype=f32, device=dev)
+        mask = torch.empty(n - 1, b, h, w, dtype=f32, device=dev)
+        coef = torch.empty(2, b, h, w, 9, dtype=f32, device=dev)
+        cam_ws = torch.empty(max(n - 1, 1) * b, 24, dtype=f32, device=dev)
+        acc = torch.empty(48, dtype=torch.float64, device=dev)
+        out = torch.empty(4, dtype=f32, device=dev)
+        call("mvs_unsup_loss_fwd", depth_c, ptr(imgs_c), ptr(cams_c), ptr(depth_c), b, n, hi, wi, h, w, float(smooth_lambda),
+             float(smooth_weight), ptr(small), ptr(warped), ptr(mask), ptr(coef), ptr(cam_ws), ptr(acc), ptr(out))
+        ctx.save_for_backward(small, depth_c, warped, mask, coef, cam_ws, acc)
+        ctx.cfg = (b, n, h, w, float(smooth_lambda), float(smooth_weight))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out: Tensor):
+        small, depth, warped, mask, coef, cam_ws, acc = ctx.saved_tensors
+        b, n, h, w, lam, wsm = ctx.cfg
+        g = _f32c(g_out)
+        gdepth = torch.empty_like(depth)
+        call("mvs_unsup_loss_bwd", depth, ptr(g), ptr(small), ptr(depth), ptr(warped), ptr(mask), ptr(coef), ptr(cam_ws), ptr(acc),
+             ptr(gdepth), b, n, h, w, lam, wsm)
+        return gdepth, None, None, None, None
+
+
+def unsup_loss(imgs: Tensor, cams: Tensor, depth: Tensor, smooth_lambda: float = 1.0, smooth_weight: float = 0.18) -> Tensor:
+    """imgs [B,N,3,Hi,Wi] (at depth size or 4x it), cams [B,N,2,4,4], depth [B,H,W] -> [4] = (12 rec + 6 ssim + w smooth, rec, ssim,
+    smooth).  One C-ABI call forward, one backward; differentiable w.r.t. depth (the views are data)."""
+    if imgs.requires_grad:
+        raise NotImplementedError("the fused UnSupLoss sends no gradient to the images (they are data in the reference's training)")
+    return _UnsupLoss.apply(depth, imgs, cams, smooth_lambda, smooth_weight)
