@@ -326,7 +326,7 @@ def run_train(args):
     from ssmvs_b200 import ops, parallel, synth
     from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
     from ssmvs_b200.jdacs.models.mvsnet import MVSNet
-    from ssmvs_b200.trainer import TrainStep
+    from ssmvs_b200.trainer import GraphedTrainStep, TrainStep
     rank, world, local = parallel.init_from_env("nccl")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local)
@@ -345,18 +345,34 @@ def run_train(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     loss_host = torch.empty(2).pin_memory()
 
+    graphed = None
+    if not args.no_graph:
+        graphed = GraphedTrainStep(step, res, warmup=3)      # the whole batch (2 x forward / loss / backward / all-reduce / Adam) as one CUDA graph
+        graphed.load(res)
+
     def step_resident():
+        if graphed is not None:
+            return graphed.replay()
         return step(res["imgs"], res["imgs_aug"], res["cams"], res["proj_matrices"], res["depth_values"])
 
     def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        o = step(d["imgs"], d["imgs_aug"], d["cams"], d["proj_matrices"], d["depth_values"])
+        if graphed is not None:
+            graphed.load(pinned)                             # H2D from pinned memory straight into the graph's static inputs
+            o = graphed.replay()
+        else:
+            d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            o = step(d["imgs"], d["imgs_aug"], d["cams"], d["proj_matrices"], d["depth_values"])
         loss_host.copy_(torch.stack((o["loss"], o["augment_loss"])), non_blocking=True)
 
     l0 = ssmvs_b200._lib.launches
+    if graphed is None:
+        step_resident()
+    else:                                                    # count the C-ABI launches of one batch eagerly (a replay makes the same ones)
+        step(res["imgs"], res["imgs_aug"], res["cams"], res["proj_matrices"], res["depth_values"])
+    per_step_launches = ssmvs_b200._lib.launches - l0
     with ClockSampler(local) as clk:
         ms_total = _timed_steps(step_resident, args.steps, args.warmup, dev, flush, parallel)
-        launches = ssmvs_b200._lib.launches - l0
+        launches = per_step_launches * args.steps
         ms_e2e = _timed_steps(step_e2e, args.steps, 1, dev, flush, parallel)
     clocks = clk.summary()
     losses = step_resident()
@@ -413,7 +429,8 @@ def run_train(args):
                 "config": {"workload": "JDACS training batch, photometric loss (BASELINE.json configs[3]; N=5 per SURVEY H5; co-segmentation term out of scope, H10)",
                            "global_batch": world * PB, "per_gpu_batch": PB,
                            "parallelism": "dp%d: batch sharded, one flat-bucket NCCL all-reduce (%.2f MB fp32) per optimiser step, 2 per batch" % (world, step.grads.flat.numel() * 4 / 1e6),
-                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)", "launch": "python (no graph)"},
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
+                           "launch": "python (no graph)" if graphed is None else "cuda-graph replay of the whole batch (%d C-ABI launches + library kernels per batch)" % per_step_launches},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": items * SAMPLES_PER_ITEM / (ms_e2e * 1e-3), "unit": "depth-samples/s",
                         "h2d_bytes_per_step": world * sum(v.numel() * v.element_size() for v in pinned.values()),
@@ -487,7 +504,8 @@ def run_cvp(args):
                 "dtype": {torch.float16: "f16", torch.bfloat16: "bf16", torch.float32: "f32"}[dtype] + " storage, f32 accumulate", "data": "synthetic",
                 "config": {"workload": "CVP-MVSNet forward, 3 pyramid levels, 1 + 4 views of 512x640 (BASELINE.json configs[2])", "global_batch": world * PB,
                            "per_gpu_batch": PB, "parallelism": "dp%d (items sharded, no collective)" % world,
-                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)", "launch": "python (no graph)"},
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
+                           "launch": "python (no graph)" if graphed is None else "cuda-graph replay of the whole batch (%d C-ABI launches + library kernels per batch)" % per_step_launches},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": items * CVP_SAMPLES / (ms_e2e * 1e-3), "unit": "depth-samples/s",
                         "h2d_bytes_per_step": world * sum(v.numel() * v.element_size() for v in pinned.values()),

@@ -21,6 +21,33 @@
 
 // ------------------------------------------------------------------------------------------------ batch-norm passes, any storage type
 // C8 volumes [B][C/8][S][8]; blockIdx.y = b * CB + cb; threads stride over s.
+
+// Per-thread partial sums of 2 x 8 channels -> fp64 totals: a thread sums a few dozen values and a warp 32 threads in fp32;
+// everything above that is accumulated in fp64 (E[x^2] - E[x]^2 cancels when |mean| >> std).  The block's 8 warps
+// meet in shared memory, so a block issues 16 fp64 atomics (it was 128: on the small feature-extractor layers the same-address
+// atomics, not the 5-10 MB read, set the kernel time).
+__device__ __forceinline__ void bn_block_sums(float (&p0)[8], float (&p1)[8], double* dst0, double* dst1) {
+#ifndef MVS_CPU_EMU
+    __shared__ float part[8][16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { p0[k] += __shfl_xor_sync(0xffffffffu, p0[k], o); p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o); }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { part[warp][k] = p0[k]; part[warp][8 + k] = p1[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)part[w][threadIdx.x];
+        atomicAdd(threadIdx.x < 8 ? dst0 + threadIdx.x : dst1 + (threadIdx.x - 8), t);
+    }
+#else
+    for (int k = 0; k < 8; ++k) { atomicAdd(dst0 + k, (double)p0[k]); atomicAdd(dst1 + k, (double)p1[k]); }
+#endif
+}
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_stats_t_kernel(const T* __restrict__ z, double* __restrict__ sums, int C, int64_t S) {
@@ -36,17 +63,7 @@ bn_stats_t_kernel(const T* __restrict__ z, double* __restrict__ sums, int C, int
 #pragma unroll
         for (int k = 0; k < 8; ++k) { s1[k] += v[k]; s2[k] += v[k] * v[k]; }
     }
-    // a thread sums <= ~16 values and a warp 32 threads in fp32; everything above that is accumulated in fp64, so the variance
-    // S2/M - (S1/M)^2 is formed from sums that carry ~1e-7 relative error each (cancellation at |mean| >> std)
-#ifndef MVS_CPU_EMU
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o); s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o); }
-    if ((threadIdx.x & 31) != 0) return;
-#endif
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(sums + cb * 8 + k, (double)s1[k]); atomicAdd(sums + C + cb * 8 + k, (double)s2[k]); }
+    bn_block_sums(s1, s2, sums + cb * 8, sums + C + cb * 8);
 }
 
 // sums -> a = gamma * invstd, b = beta - mean * a, mean, invstd (fp32), and the running statistics exactly as nn.BatchNorm3d
@@ -117,15 +134,7 @@ bn_act_bwd_reduce_t_kernel(const T* __restrict__ z, const T* __restrict__ gy, co
             r0[k] += gg; r1[k] += gg * ((v[k] - m[k]) * is[k]);
         }
     }
-#ifndef MVS_CPU_EMU
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { r0[k] += __shfl_xor_sync(0xffffffffu, r0[k], o); r1[k] += __shfl_xor_sync(0xffffffffu, r1[k], o); }
-    if ((threadIdx.x & 31) != 0) return;
-#endif
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(red + cb * 8 + k, (double)r0[k]); atomicAdd(red + C + cb * 8 + k, (double)r1[k]); }
+    bn_block_sums(r0, r1, red + cb * 8, red + C + cb * 8);
 }
 
 // batch statistics: gz = a (g - red0/M - xhat red1/M);  frozen statistics (eval-mode fine-tuning): gz = a g.
@@ -167,6 +176,14 @@ __global__ void lift_c1_kernel(const float* __restrict__ src, T* __restrict__ ds
     V8<T>::store(dst + i * 8, v);
 }
 
+// blocks along s of a reduction pass: >= 8 voxels per thread, and about 8 resident blocks per SM over the whole grid
+static unsigned bn_reduce_blocks(int64_t S, int rows) {
+    int64_t bx = (S + 256 * 8 - 1) / (256 * 8);
+    const int64_t cap = (148 * 8 + rows - 1) / rows;
+    if (bx > cap) bx = cap;
+    return (unsigned)(bx < 1 ? 1 : bx);
+}
+
 static int check_bn_t(const char* who, int B, int C, int64_t S) {
     MVS_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && C <= 256 && S > 0, MVS_E_SHAPE, "%s: bad dims (C must be a multiple of 8, <= 256)", who);
     MVS_REQUIRE((int64_t)B * (C / 8) <= 65535, MVS_E_SHAPE, "%s: B*C/8 too large for the launch grid", who);
@@ -177,8 +194,7 @@ extern "C" int mvs_bn_stats_t(const void* z, int dtype, double* sums, int B, int
     MVS_REQUIRE(z && sums, MVS_E_ARG, "mvs_bn_stats_t: null pointer");
     int rc = check_bn_t("mvs_bn_stats_t", B, C, S);
     if (rc) return rc;
-    unsigned bx = mvs_cdiv(S, 256 * 16);
-    if (bx > 2048) bx = 2048;
+    const unsigned bx = bn_reduce_blocks(S, B * (C / 8));
     MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(bn_stats_t_kernel<T>, dim3(bx, (unsigned)(B * (C / 8))), dim3(256), stream, (const T*)z, sums, C, S));
     return MVS_CHECK_LAUNCH("mvs_bn_stats_t");
 }
@@ -209,8 +225,7 @@ extern "C" int mvs_bn_act_bwd_reduce_t(const void* z, const void* grad_y, const 
     MVS_REQUIRE(z && grad_y && a && b && mean && invstd && red, MVS_E_ARG, "mvs_bn_act_bwd_reduce_t: null pointer");
     int rc = check_bn_t("mvs_bn_act_bwd_reduce_t", B, C, S);
     if (rc) return rc;
-    unsigned bx = mvs_cdiv(S, 256 * 16);
-    if (bx > 2048) bx = 2048;
+    const unsigned bx = bn_reduce_blocks(S, B * (C / 8));
     MVS_DISPATCH_DTYPE(dtype, T, MVS_LAUNCH(bn_act_bwd_reduce_t_kernel<T>, dim3(bx, (unsigned)(B * (C / 8))), dim3(256), stream, (const T*)z,
                                             (const T*)grad_y, a, b, mean, invstd, red, C, S, relu));
     return MVS_CHECK_LAUNCH("mvs_bn_act_bwd_reduce_t");

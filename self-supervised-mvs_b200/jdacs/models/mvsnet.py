@@ -102,6 +102,20 @@ class FeatureNet(nn.Module):
         return x.view(n, b, *x.shape[1:])
 
 
+    def forward_train_tc(self, img, dtype, frozen=False):
+        """Differentiable path on the repo's own kernels (training, or eval-mode fine-tuning with `frozen` statistics):
+        img [B,3,H,W] of ONE view -> C8 feature maps [B, C/8, H/4, W/4, 8] in `dtype`.  The B images form a C8 volume whose depth
+        axis is the image index, every layer is the 3-D training op of CostRegNet with zero kd = 0, 2 taps (ops.conv2d_bn_relu_tc):
+        tcgen05 forward / input gradient, tensor-core weight gradient, fp64 batch statistics over the call's images -- per view,
+        as BatchNorm2d sees them in the reference (jdacs/models/mvsnet.py:115)."""
+        b, _, h, w = img.shape
+        x = ops.pack_images_c8(img.unsqueeze(1), dtype).view(1, 1, b, h, w, 8)
+        for blk in (self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6):
+            x = ops.conv2d_bn_relu_tc(x, blk.conv, blk.bn, frozen)
+        x = ops.conv2d_bias_tc(x, self.feature)
+        return x[0].permute(1, 0, 2, 3, 4).contiguous()
+
+
 class CostRegNet(nn.Module):
     """jdacs/models/mvsnet.py:37-74.  forward takes the variance volume (C8 or [B,32,D,H,W]) and returns
     cost_reg: [B,D,H,W] fp32 for a C8 input (internal), [B,1,D,H,W] for a plain input (reference shape).
@@ -204,7 +218,7 @@ class MVSNet(nn.Module):
         self.train_dtype = train_dtype
         self.align_corners = align_corners
         self.feature_autocast = True   # eval + 16-bit volume, feature_tc off: FeatureNet as folded 16-bit library convolutions
-        self.feature_tc = True         # eval + 16-bit volume: FeatureNet on the repo's tcgen05 convolution kernel
+        self.feature_tc = True         # 16-bit volumes: FeatureNet on the repo's tcgen05 convolution kernels (eval and training)
         self.keep_index = False        # also return "depth_index" (the truncated expected plane index, mvsnet.py:149-150)
 
     def forward(self, imgs, proj_matrices, depth_values):
@@ -233,7 +247,10 @@ class MVSNet(nn.Module):
             # each view is its own call in training mode: BatchNorm2d statistics are per call in the reference (:115).
             # With 16-bit activations the (library) feature extractor runs under autocast on channels-last tensors -- cuDNN's
             # tensor-core convolutions and NHWC BatchNorm kernels instead of its fp32 NCHW ones (10 ms -> ~3 ms per item at 512x640)
-            if dt != torch.float32 and imgs.is_cuda and self.feature_autocast:
+            if dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0:
+                # the feature extractor on the repo's tensor-core training kernels, emitting C8 maps for the sweep
+                features = [self.feature.forward_train_tc(imgs[:, v], dt, frozen=not self.training) for v in range(n)]
+            elif dt != torch.float32 and imgs.is_cuda and self.feature_autocast:
                 with torch.autocast("cuda", dtype=dt):
                     features = [self.feature(imgs[:, v].contiguous(memory_format=torch.channels_last)) for v in range(n)]
             else:

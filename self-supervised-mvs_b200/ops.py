@@ -157,20 +157,24 @@ class _WarpVariance(torch.autograd.Function):
         ref8 = pack_c8_padded(ref_fea, fdt)
         src8 = [pack_c8_padded(s, fdt) for s in src_feas]
         depth = _f32c(depth)
-        b, c, h, w = ref_fea.shape
+        c8_in = ref_fea.dim() == 5                     # C8 maps [B, C/8, H, W, 8] (already in `fdt`) instead of [B, C, H, W]
+        if c8_in:
+            b, c, h, w = ref_fea.shape[0], ref_fea.shape[1] * 8, ref_fea.shape[2], ref_fea.shape[3]
+        else:
+            b, c, h, w = ref_fea.shape
         d = depth.shape[1]
         per_pixel = int(depth.dim() == 4)
         var = torch.empty(b, c // 8, d, h, w, 8, dtype=dtype, device=ref_fea.device)
         call("mvs_warp_var_fwd", ref8, ptr(ref8), _ptr_array(src8), len(src8), ptr(rt), ptr(depth), per_pixel, ptr(var),
              b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), int(align_corners), int(ref_sq_in_sum), 1)
         ctx.save_for_backward(rt, depth, ref8, *src8)
-        ctx.meta = (b, c, d, h, w, per_pixel, fdt, dtype, int(align_corners), int(ref_sq_in_sum))
+        ctx.meta = (b, c, d, h, w, per_pixel, fdt, dtype, int(align_corners), int(ref_sq_in_sum), c8_in)
         return var
 
     @staticmethod
     def backward(ctx, grad_var: Tensor):
         rt, depth, ref8, *src8 = ctx.saved_tensors
-        b, c, d, h, w, per_pixel, fdt, dtype, ac, rsq = ctx.meta
+        b, c, d, h, w, per_pixel, fdt, dtype, ac, rsq, c8_in = ctx.meta
         g = grad_var.detach().to(dtype).contiguous()
         need = ctx.needs_input_grad
         gref = torch.zeros(b, c // 8, h, w, 8, dtype=torch.float32, device=g.device) if need[5] else None
@@ -178,14 +182,15 @@ class _WarpVariance(torch.autograd.Function):
                 for i in range(len(src8))]
         call("mvs_warp_var_bwd", g, ptr(g), ptr(ref8), _ptr_array(src8), len(src8), ptr(rt), ptr(depth), per_pixel,
              ptr(gref), _ptr_array(gsrc), b, c, d, h, w, dtype_code(fdt), dtype_code(dtype), ac, rsq, 1)
-        outs = [None if t is None else unpack_c8(t) for t in [gref] + gsrc]
+        outs = [None if t is None else (t if c8_in else unpack_c8(t)) for t in [gref] + gsrc]
         return (None, None, None, None, None, *outs)
 
 
 def warp_variance(ref_fea: Tensor, src_feas: Sequence[Tensor], rt: Tensor, depth: Tensor,
                   dtype: torch.dtype = torch.float32, align_corners: bool = False, ref_sq_in_sum: bool = False) -> Tensor:
     """Variance cost volume (C8, `dtype`) of the reference map and nsrc warped source maps ([B,C,H,W] each; fp32, or
-    channels-last `dtype` as the library feature extractor emits them)."""
+    channels-last `dtype` as the library feature extractor emits them; or C8 maps [B,C/8,H,W,8] in `dtype`, whose gradients
+    come back as fp32 C8 maps)."""
     if len(src_feas) < 1 or len(src_feas) > _lib.MAX_SRC:
         raise ValueError("need 1..%d source views, got %d" % (_lib.MAX_SRC, len(src_feas)))
     return _WarpVariance.apply(rt.contiguous(), depth, dtype, align_corners, ref_sq_in_sum, ref_fea, *src_feas)
@@ -560,6 +565,87 @@ class _ConvBiasTC(torch.autograd.Function):
 
 def conv_bias_tc(x: Tensor, conv: torch.nn.Conv3d) -> Tensor:
     return _ConvBiasTC.apply(x, conv.weight, conv.bias)
+
+
+class _ConvTC(torch.autograd.Function):
+    """z = conv(x) [+ bias] on a 16-bit C8 volume, stride 1, 3x3x3, differentiable: forward and input gradient on the tcgen05
+    kernel, weight gradient on the warp-level MMA kernel (the un-normalised last layer of the 2-D feature extractor)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+        x = x.contiguous()
+        cout = weight.shape[0]
+        y = conv3d_raw(x, pack_conv3d_weight(weight, False), cout, 1, False, shift=None if bias is None else _f32c(bias), algo=0)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x, weight = ctx.saved_tensors
+        cout = weight.shape[0]
+        g16 = gy.detach().to(x.dtype).contiguous()
+        w32 = _f32c(weight)
+        gx = _adjoint_conv(g16, w32, x.shape[1] * 8, 1, False) if ctx.needs_input_grad[0] else None
+        gw = _wgrad_mma(x, g16, w32, cout, 1, False, cout) if ctx.needs_input_grad[1] else None
+        gb = gy.detach().float().sum(dim=(0, 2, 3, 4)).reshape(-1) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
+# 2-D layers of the feature extractor in TRAINING: a batch of images is a C8 volume whose depth axis is the image index
+# ([1, C/8, M, H, W, 8]); a k x k Conv2d is the 3x3x3 convolution whose kd = 0, 2 taps are zero, so that every kernel of the
+# 3-D training path (tcgen05 forward / input gradient, MMA weight gradient, fp64 BatchNorm statistics) serves unchanged and the
+# images never mix.  5x5 stride-2 layers run as 3x3 stride-1 layers over the space-to-depth (2x2 parity) form of their input.
+def space_to_depth_c8(x: Tensor) -> Tensor:
+    """[1, Cb, M, H, W, 8] -> [1, 4 Cb, M, H/2, W/2, 8]; new channel block = (row parity * 2 + column parity) * Cb + block."""
+    _, cb, m, h, w, _ = x.shape
+    if h % 2 or w % 2:
+        raise ValueError("stride-2 feature layers need even extents, got %dx%d" % (h, w))
+    return x.view(1, cb, m, h // 2, 2, w // 2, 2, 8).permute(0, 4, 6, 1, 2, 3, 5, 7).reshape(1, 4 * cb, m, h // 2, w // 2, 8)
+
+
+def embed_conv2d_weight(weight: Tensor, stride: int) -> Tensor:
+    """torch Conv2d weight -> the [Cout, Cin', 3, 3, 3] weight of the equivalent stride-1 3-D layer (differentiable):
+    3x3 stride 1 pad 1: Cin' = Cin padded to 8, taps at kd = 1;  5x5 stride 2 pad 2: Cin' = 4 Cin (parity-major, as
+    space_to_depth_c8 orders them), parity (a, b) holds taps W[.., a::2, b::2] (3 or 2 per axis, zero-padded to 3)."""
+    cout, cin, k, _ = weight.shape
+    F = torch.nn.functional
+    if k == 3 and stride == 1:
+        w2 = F.pad(weight, (0, 0, 0, 0, 0, (-cin) % 8))
+    elif k == 5 and stride == 2:
+        if cin % 8:
+            raise ValueError("5x5 stride-2 layers need Cin divisible by 8, got %d" % cin)
+        parts = []
+        for a in (0, 1):
+            for b in (0, 1):
+                sub = weight[:, :, a::2, b::2]
+                parts.append(F.pad(sub, (0, 3 - sub.shape[3], 0, 3 - sub.shape[2])))
+        w2 = torch.cat(parts, dim=1)
+    else:
+        raise ValueError("feature layers on the path are 3x3 stride 1 or 5x5 stride 2 (got %dx%d stride %d)" % (k, k, stride))
+    return F.pad(w2.unsqueeze(2), (0, 0, 0, 0, 1, 1))
+
+
+def conv2d_bn_relu_tc(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.modules.batchnorm._BatchNorm, frozen: bool) -> Tensor:
+    """relu(bn(conv2d(x))) over an image volume [1, Cin/8, M, H, W, 8] (16-bit), differentiable; batch statistics over the M
+    images unless `frozen`."""
+    stride = conv.stride[0]
+    if stride == 2:
+        x = space_to_depth_c8(x)
+    w3 = embed_conv2d_weight(conv.weight, stride)
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    track = bn.track_running_stats and bn.running_mean is not None
+    y = _ConvBnActTC.apply(x, w3, bn.weight, bn.bias, None, bn.running_mean if track else None, bn.running_var if track else None,
+                           1, False, bn.eps, mom, frozen)
+    if track and not frozen and bn.num_batches_tracked is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+    return y
+
+
+def conv2d_bias_tc(x: Tensor, conv: torch.nn.Conv2d) -> Tensor:
+    """conv2d(x) + bias over an image volume (3x3, stride 1), differentiable."""
+    return _ConvTC.apply(x, embed_conv2d_weight(conv.weight, conv.stride[0]), conv.bias)
 
 
 def fold_bn(bn: torch.nn.modules.batchnorm._BatchNorm) -> Tuple[Tensor, Tensor]:

@@ -1,0 +1,43 @@
+"""trainer.TrainStep (one JDACS batch: train_sample + train_sample_aug, jdacs/train.py:189-291) on the host-emulation build:
+the device-side mask box and the gather-free augmentation loss equal the reference's formulation, and a step trains."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def test_mask_box_matches_slicing():
+    from ssmvs_b200.trainer import draw_mask_box, mask_reference_view
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.randn(2, 4, 3, 24, 36, generator=g)
+    for _ in range(5):
+        box = draw_mask_box(24, 36, g)
+        x, y = int(box[0]), int(box[1])
+        want_mask = torch.ones(2, 3, 24, 36)
+        want_mask[:, :, y:y + 8, x:x + 12] = 0          # models/augmentations.py:107-124
+        out, mask = mask_reference_view(imgs, box)
+        assert torch.equal(mask.expand(2, 3, 24, 36), want_mask)
+        assert torch.equal(out[:, 0], imgs[:, 0] * want_mask) and torch.equal(out[:, 1:], imgs[:, 1:])
+
+
+def test_train_step_runs_and_matches_gather_form(emu):
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200.trainer import TrainStep, mask_reference_view
+    torch.manual_seed(0)
+    model = MVSNet(refine=False, train_dtype=torch.float32)
+    step = TrainStep(model, UnSupLoss(), lr=1e-3)
+    inp = synth.mvsnet_inputs(1, 4, 32, 64, 8, seed=1)
+    inp["imgs_aug"] = inp["imgs"] + 0.05 * torch.randn(inp["imgs"].shape, generator=torch.Generator().manual_seed(2))
+    before = [p.detach().clone() for p in model.parameters()]
+    out = step(inp["imgs"], inp["imgs_aug"], inp["cams"], inp["proj_matrices"], inp["depth_values"])
+    assert torch.isfinite(out["loss"]) and torch.isfinite(out["augment_loss"]) and out["loss"] > 0
+    assert sum(int(not torch.equal(a, b)) for a, b in zip(before, model.parameters())) > 10     # both optimiser steps moved weights
+    # the augmentation loss without the boolean gather == the reference's depth_aug[mask] form (train.py:262-266)
+    g = torch.Generator().manual_seed(5)
+    da, de = torch.rand(1, 8, 16, generator=g) * 50 + 400, torch.rand(1, 8, 16, generator=g) * 50 + 400
+    _, fmask = mask_reference_view(inp["imgs"], torch.tensor([10, 5]))
+    fm = F.interpolate(fmask.float(), scale_factor=0.25)[:, 0] > 0.5
+    want = F.smooth_l1_loss(da[fm], de[fm])
+    got = (F.smooth_l1_loss(da, de, reduction="none") * fm.float()).sum() / fm.float().sum()
+    assert abs(float(want) - float(got)) < 1e-5 * float(want)

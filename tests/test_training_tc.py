@@ -125,8 +125,9 @@ def test_sweep_backward_16bit_matches_fp32_scatter(gpu, dtype, channels, nsrc, r
         assert nerr(a, b) < (2e-2 if dtype == torch.bfloat16 else 3e-3)
 
 
+@pytest.mark.parametrize("feature_tc", [False, True])
 @pytest.mark.parametrize("tdt,max_err,min_cos", [(torch.float16, 0.25, 0.97), (torch.bfloat16, 0.6, 0.85)])
-def test_mvsnet_16bit_training_gradients_against_the_reference(gpu, golden, tdt, max_err, min_cos):
+def test_mvsnet_16bit_training_gradients_against_the_reference(gpu, golden, tdt, max_err, min_cos, feature_tc):
     """Whole MVSNet in train() mode on the tensor-core training path against the depth map and the parameter gradients the
     unmodified reference produced in fp32 (tests/golden/jdacs_mvsnet.npz).  The fixture is a deliberately hard case for reduced
     precision (8 planes, peaky softmax, batch statistics over a tiny volume): the per-layer tests above pin every kernel to 1-3 %;
@@ -135,7 +136,8 @@ def test_mvsnet_16bit_training_gradients_against_the_reference(gpu, golden, tdt,
     from ssmvs_b200.jdacs.models.mvsnet import MVSNet
     g = golden("jdacs_mvsnet")
     model = MVSNet(refine=False, train_dtype=tdt)
-    model.feature_autocast = False      # the library FeatureNet in fp32: what is measured here are this repo's kernels
+    model.feature_autocast = False      # feature_tc False: the library FeatureNet in fp32, so that only the 3-D half is 16-bit;
+    model.feature_tc = feature_tc       # True: the feature extractor on the tensor-core training kernels as well (the default)
     model.load_state_dict(state_dict_of(g), strict=False)
     model = model.to(gpu.device).train()
     args = [gpu.to(g[k]) for k in ("imgs", "proj_matrices", "depth_values")]
@@ -149,10 +151,76 @@ def test_mvsnet_16bit_training_gradients_against_the_reference(gpu, golden, tdt,
             a, r = params[k[5:]].grad.detach().float().cpu().flatten(), v.float().flatten()
             err[k] = nerr(a, r)
             cos[k] = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
-    print("%s training vs reference: depth %.3e; gradient norm-relative error median %.3e max %.3e; cosine min %.4f" % (
-        tdt, derr, sorted(err.values())[len(err) // 2], max(err.values()), min(cos.values())))
-    assert derr < 2e-2
+    print("%s (feature_tc=%s) training vs reference: depth %.3e; gradient norm-relative error median %.3e max %.3e; cosine min %.4f" % (
+        tdt, feature_tc, derr, sorted(err.values())[len(err) // 2], max(err.values()), min(cos.values())))
+    if feature_tc:      # eight more 16-bit layers (batch statistics over ONE 64 x 96 image per view) in front of the volume: measured
+        # fp16 0.30 / cos 0.955, bf16 0.93 / cos 0.63 on this fixture (the library's autocast feature extractor, the previous
+        # default, rounds the same tensors to the same 16 bits); the fixture is the worst case, see the docstring
+        max_err, min_cos = (0.4, 0.93) if tdt == torch.float16 else (1.1, 0.55)
+    assert derr < (3e-2 if feature_tc else 2e-2)
     assert max(err.values()) < max_err and min(cos.values()) > min_cos, (err, cos)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("batch,h,w", [(2, 128, 192), (1, 64, 160), (3, 40, 72)])
+def test_feature_net_training_path_matches_aten(gpu, dtype, batch, h, w):
+    """FeatureNet.forward_train_tc (2-D layers as zero-kd 3-D layers over an image volume, 5x5 stride-2 layers through
+    space-to-depth) against the same module run by ATen in fp32 (jdacs/models/mvsnet.py:17-34): features, the gradient of every
+    parameter, running statistics."""
+    import copy
+    from ssmvs_b200 import ops
+    from ssmvs_b200.jdacs.models.mvsnet import FeatureNet
+    torch.manual_seed(3)
+    net = FeatureNet().to(gpu.device).train()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+    ref = copy.deepcopy(net)
+    img = torch.randn(batch, 3, h, w, device=gpu.device).to(dtype).float()
+    want = ref(img)
+    gout = torch.randn_like(want)
+    want.backward(gout)
+    got8 = net.forward_train_tc(img, dtype)                         # [B, 4, h/4, w/4, 8]
+    got = ops.unpack_c8(got8)
+    got8.backward(ops.pack_c8(gout, torch.float32).to(dtype))
+    tol = 6e-2 if dtype == torch.bfloat16 else 1e-2
+    assert nerr(got, want) < tol, nerr(got, want)
+    rp = dict(ref.named_parameters())
+    errs = {k: nerr(p.grad, rp[k].grad) for k, p in net.named_parameters()}
+    coss = {k: float(torch.dot(p.grad.flatten(), rp[k].grad.flatten()) / (p.grad.norm() * rp[k].grad.norm() + 1e-30)) for k, p in net.named_parameters()}
+    print(dtype, (batch, h, w), "feature-net gradient errors: last layer %.3e, median %.3e, max %.3e; cosine min %.4f" % (
+        errs["feature.weight"], sorted(errs.values())[len(errs) // 2], max(errs.values()), min(coss.values())))
+    # the un-normalised last layer sees fp32-exact inputs to its gradient: tight.  Towards the first layer every BatchNorm + ReLU
+    # adds the effect of 16-bit z (mask flips at z ~ 0, batch statistics of rounded values) on sums with heavy cancellation:
+    # the bound is on direction and size of the whole gradient, as for the 3-D stack in the whole-model test below
+    assert errs["feature.weight"] < tol and errs["feature.bias"] < tol
+    assert max(errs.values()) < (0.6 if dtype == torch.bfloat16 else 0.2) and min(coss.values()) > (0.85 if dtype == torch.bfloat16 else 0.98), (errs, coss)
+    for k, buf in net.named_buffers():
+        r = dict(ref.named_buffers())[k]
+        if k.endswith("running_var"):
+            assert nerr(buf, r) < 2 * tol, k
+        elif k.endswith("num_batches_tracked"):
+            assert int(buf) == int(r) == 1
+
+
+def test_space_to_depth_embedding_is_the_strided_convolution(gpu):
+    """embed_conv2d_weight + space_to_depth_c8: a 5x5 stride-2 pad-2 Conv2d equals the 3x3 stride-1 convolution of the parity
+    planes with the re-ordered weight (checked with ATen in fp32, no kernels of ours involved)."""
+    from ssmvs_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 12, 20, device=gpu.device)
+    wt = torch.randn(16, 8, 5, 5, device=gpu.device)
+    want = F.conv2d(x, wt, None, 2, 2)
+    x8 = ops.pack_c8(x.unsqueeze(2), torch.float32).permute(2, 1, 0, 3, 4, 5).contiguous()      # [1, 1, M=2, H, W, 8]
+    xs = ops.space_to_depth_c8(x8)                                                               # [1, 4, 2, 6, 10, 8]
+    xs_nchw = xs[0].permute(1, 0, 4, 2, 3).reshape(2, 32, 6, 10)
+    w3 = ops.embed_conv2d_weight(wt, 2)
+    assert w3.shape == (16, 32, 3, 3, 3) and float(w3[:, :, 0].abs().max()) == 0 and float(w3[:, :, 2].abs().max()) == 0
+    got = F.conv2d(xs_nchw, w3[:, :, 1], None, 1, 1)
+    assert rel_err(got, want) < 1e-5
+    w33 = torch.randn(8, 3, 3, 3, device=gpu.device)
+    assert ops.embed_conv2d_weight(w33, 1).shape == (8, 8, 3, 3, 3)
 
 
 def test_eval_mode_fine_tuning_uses_frozen_statistics(gpu):
