@@ -243,6 +243,22 @@ int mvs_unsup_loss_bwd(const float* grad_out, const float* small, const float* d
                        const float* coef, const float* cam_ws, const double* acc, float* grad_depth, int B, int N, int H, int W,
                        float smooth_lambda, float smooth_weight, void* stream);
 
+/* ---- f3: inference output side --------------------------------------------------------------------------------- */
+/* F.interpolate(map.unsqueeze(1), size=(Ho, Wo)) in the default 'nearest' mode for M maps [M][H][W] -> [M][Ho][Wo]
+ * (jdacs/eval_dense.py:150-153).  flip_rows != 0 stores the rows bottom-up: the order of a .pfm body (data_io.py:53-80). */
+int mvs_upsample_nearest(const float* src, float* dst, int M, int H, int W, int Ho, int Wo, int flip_rows, void* stream);
+/* write_depth_img (jdacs/eval_dense.py:110-121): out = clamp((depth - offset) / scale, 0, 255) truncated to 8 bits. */
+int mvs_depth_preview_u8(const float* depth, uint8_t* out, int64_t n, float offset, float scale, void* stream);
+/* reproject_with_depth + check_geometric_consistency (jdacs/eval_dense.py:177-232) for B (reference, source) pairs of depth maps
+ * [B][H][W].  cams [B][60] doubles = inv(K_ref) 3x3 | (E_src inv(E_ref))[:3] 3x4 | K_src | inv(K_src) | (E_ref inv(E_src))[:3] | K_ref,
+ * row-major, computed by the caller in float32 as the reference does.  Outputs (any may be NULL): mask [B][H][W] bytes
+ * (dist < dist_thresh and |d_reproj - d| / d < rel_thresh), depth_reprojected (zeroed outside the mask when apply_mask),
+ * the float32 source coordinates, the float32 re-projected coordinates.  cv2.remap's 1/32-pixel bilinear sampling is
+ * reproduced exactly. */
+int mvs_geo_consistency(const float* depth_ref, const float* depth_src, const double* cams, uint8_t* mask,
+                        float* depth_reprojected, float* x_src, float* y_src, float* x_reprojected, float* y_reprojected,
+                        int B, int H, int W, float dist_thresh, float rel_thresh, int apply_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -778,3 +778,40 @@ def unsup_loss(imgs: Tensor, cams: Tensor, depth: Tensor, smooth_lambda: float =
     if imgs.requires_grad:
         raise NotImplementedError("the fused UnSupLoss sends no gradient to the images (they are data in the reference's training)")
     return _UnsupLoss.apply(depth, imgs, cams, smooth_lambda, smooth_weight)
+
+
+# ------------------------------------------------------------------------------------------------ inference output side
+def upsample_nearest(maps: Tensor, size: Tuple[int, int], flip_rows: bool = False) -> Tensor:
+    """[M,H,W] fp32 -> [M,Ho,Wo]: F.interpolate(maps.unsqueeze(1), size=size) in the default nearest mode; flip_rows stores the
+    rows bottom-up (the body of a .pfm file)."""
+    x = _f32c(maps)
+    m, h, w = x.shape
+    ho, wo = int(size[0]), int(size[1])
+    out = torch.empty(m, ho, wo, dtype=torch.float32, device=x.device)
+    call("mvs_upsample_nearest", x, ptr(x), ptr(out), m, h, w, ho, wo, int(flip_rows))
+    return out
+
+
+def depth_preview_u8(depth: Tensor, offset: float = 500.0, scale: float = 2.0) -> Tensor:
+    """write_depth_img's 8-bit preview: clamp((depth - offset) / scale, 0, 255), truncated."""
+    x = _f32c(depth)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    call("mvs_depth_preview_u8", x, ptr(x), ptr(out), x.numel(), float(offset), float(scale))
+    return out
+
+
+def geo_consistency(depth_ref: Tensor, depth_src: Tensor, cams: Tensor, dist_thresh: float = 1.0, rel_thresh: float = 0.01,
+                    apply_mask: bool = True):
+    """depth_ref, depth_src [B,H,W] fp32; cams [B,60] float64 (see include/mvs_b200.h) ->
+    (mask bool [B,H,W], depth_reprojected, x_src, y_src, x_reprojected, y_reprojected) as check_geometric_consistency /
+    reproject_with_depth return them."""
+    dr, ds = _f32c(depth_ref), _f32c(depth_src)
+    cams = cams.detach().to(torch.float64).contiguous()
+    b, h, w = dr.shape
+    if ds.shape != dr.shape or cams.shape != (b, 60):
+        raise ValueError("geo_consistency: depth maps must share [B,H,W] and cams be [B,60] (got %s, %s, %s)" % (tuple(dr.shape), tuple(ds.shape), tuple(cams.shape)))
+    mask = torch.empty(b, h, w, dtype=torch.uint8, device=dr.device)
+    outs = [torch.empty(b, h, w, dtype=torch.float32, device=dr.device) for _ in range(5)]
+    call("mvs_geo_consistency", dr, ptr(dr), ptr(ds), ptr(cams), ptr(mask), *[ptr(o) for o in outs], b, h, w, float(dist_thresh),
+         float(rel_thresh), int(apply_mask))
+    return (mask.bool(), *outs)

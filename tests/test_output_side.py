@@ -1,0 +1,132 @@
+"""Inference output side (csrc/output.cu, jdacs/eval_dense.py mirror, datasets/data_io.py mirror) against the
+fixture produced by the reference's own functions (oracle/gen_golden_output.py -> tests/golden/jdacs_output_side.npz) and the
+NumPy oracle (oracle/output_side.py)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def side():
+    spec = importlib.util.spec_from_file_location("output_side_oracle", os.path.join(ROOT, "oracle", "output_side.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def gold():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "jdacs_output_side.npz"))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def be(request):
+    return request.getfixturevalue(request.param)
+
+
+def test_oracle_matches_reference_fixture(side, gold):
+    for s in (1, 2):
+        args = (gold["depth_ref"], gold["intrinsics"], gold["extrinsics_ref"], gold["depth_src%d" % s], gold["intrinsics"], gold["extrinsics_src%d" % s])
+        mask, drep, xs, ys = side.check_geometric_consistency(*args)
+        assert np.array_equal(mask, gold["mask%d" % s]) and 0.1 < mask.mean() < 0.9
+        assert np.allclose(drep, gold["depth_reprojected_masked%d" % s], rtol=1e-6, atol=1e-5)
+        assert np.allclose(xs, gold["x2d_src%d" % s], rtol=1e-6, atol=1e-5) and np.allclose(ys, gold["y2d_src%d" % s], rtol=1e-6, atol=1e-5)
+    assert np.array_equal(side.remap_bilinear(gold["remap_img"], gold["remap_x"], gold["remap_y"]), gold["remap_out"])      # == cv2.remap
+    assert np.array_equal(side.upsample_nearest(gold["small"], gold["upsampled"].shape[1:]), gold["upsampled"])
+    assert side.pfm_bytes(gold["upsampled"][0]) == gold["pfm_bytes"].tobytes()
+    assert np.array_equal(side.depth_preview(gold["upsampled"][0]), gold["preview"])
+
+
+def test_remap_restatement_equals_opencv(side):
+    cv2 = pytest.importorskip("cv2")
+    g = np.random.default_rng(3)
+    img = g.normal(0, 1, (37, 29)).astype(np.float32)
+    xs, ys = g.uniform(-2, 31, (64, 64)).astype(np.float32), g.uniform(-2, 39, (64, 64)).astype(np.float32)
+    assert np.array_equal(cv2.remap(img, xs, ys, interpolation=cv2.INTER_LINEAR), side.remap_bilinear(img, xs, ys))
+
+
+def test_geo_consistency_kernel_matches_reference(be, gold):
+    from ssmvs_b200.jdacs import eval_dense as ed
+    k, er = gold["intrinsics"], gold["extrinsics_ref"]
+    for s in (1, 2):
+        es, dsrc = gold["extrinsics_src%d" % s], gold["depth_src%d" % s]
+        dref_t, dsrc_t = be.to(torch.from_numpy(gold["depth_ref"])), be.to(torch.from_numpy(dsrc))
+        mask, drep, xs, ys = ed.check_geometric_consistency(dref_t, k, er, dsrc_t, k, es)
+        assert mask.dtype == torch.bool and torch.equal(mask.cpu(), torch.from_numpy(gold["mask%d" % s]))      # bit-exact decision
+        assert np.allclose(drep.cpu().numpy(), gold["depth_reprojected_masked%d" % s], rtol=1e-6, atol=1e-5)
+        assert np.allclose(xs.cpu().numpy(), gold["x2d_src%d" % s], rtol=1e-6, atol=1e-5)
+        assert np.allclose(ys.cpu().numpy(), gold["y2d_src%d" % s], rtol=1e-6, atol=1e-5)
+        drep2, xr, yr, xs2, ys2 = ed.reproject_with_depth(dref_t, k, er, dsrc_t, k, es)
+        assert np.allclose(drep2.cpu().numpy(), gold["depth_reprojected%d" % s], rtol=1e-6, atol=1e-5)
+        assert np.allclose(xr.cpu().numpy(), gold["x_reprojected%d" % s], rtol=1e-6, atol=1e-4, equal_nan=True)
+        assert np.allclose(yr.cpu().numpy(), gold["y_reprojected%d" % s], rtol=1e-6, atol=1e-4, equal_nan=True)
+    # all source views of a reference view in one launch == the per-pair calls
+    dref_t = be.to(torch.from_numpy(gold["depth_ref"]))
+    srcs = [be.to(torch.from_numpy(gold["depth_src%d" % s])) for s in (1, 2)]
+    m, d, _, _ = ed.check_geometric_consistency_batch(dref_t, k, er, srcs, [k, k], [gold["extrinsics_src1"], gold["extrinsics_src2"]])
+    assert torch.equal(m[1].cpu(), torch.from_numpy(gold["mask2"])) and m.shape[0] == 2
+
+
+def test_remap_sampling_inside_the_kernel_is_opencvs(be, gold, side):
+    """Identity cameras turn the kernel into a pure remap of the source map at the reference pixel grid scaled by the depth
+    ratio; more directly: feed coordinates through a camera pair whose projection is a known shift and compare the sampled
+    depth with the restated cv2.remap."""
+    from ssmvs_b200 import ops
+    h, w = 20, 28
+    g = np.random.default_rng(5)
+    dsrc = g.uniform(400, 900, (h, w)).astype(np.float32)
+    dref = np.full((h, w), 500.0, np.float32)
+    k = np.array([[300, 0, 13.3], [0, 300, 9.7], [0, 0, 1]], np.float32)
+    e0 = np.eye(4, dtype=np.float32)
+    e1 = np.eye(4, dtype=np.float32)
+    e1[0, 3], e1[1, 3] = 2.137, -1.291           # pure translation: x_src = x + 300 * 2.137 / 500, a fractional shift
+    from ssmvs_b200.jdacs.eval_dense import _pair_cams
+    cams = torch.from_numpy(_pair_cams(k, e0, k, e1)[None])
+    out = ops.geo_consistency(be.to(torch.from_numpy(dref))[None], be.to(torch.from_numpy(dsrc))[None], be.to(cams), apply_mask=False)
+    xs, ys = out[2][0].cpu().numpy(), out[3][0].cpu().numpy()
+    sampled = side.remap_bilinear(dsrc, xs, ys)
+    # depth_reprojected = z of the back-projected sample = sampled depth (the cameras differ by an in-plane translation only)
+    assert np.allclose(out[1][0].cpu().numpy(), sampled, rtol=1e-6, atol=1e-4)
+    assert (sampled == 0).any() and (sampled > 0).any()        # the border is exercised
+
+
+def test_upsample_preview_and_pfm_files(be, gold, tmp_path):
+    from ssmvs_b200 import ops
+    from ssmvs_b200.jdacs import eval_dense as ed
+    from ssmvs_b200.jdacs.datasets.data_io import read_pfm, save_pfm
+    from ssmvs_b200.jdacs_ms.dataset.data_io import save_pfm as save_pfm_ms
+    small = be.to(torch.from_numpy(gold["small"]))
+    size = gold["upsampled"].shape[1:]
+    up = ops.upsample_nearest(small, size)
+    assert np.array_equal(up.cpu().numpy(), gold["upsampled"])                                   # ATen nearest, bit-exact
+    flipped = ops.upsample_nearest(small, size, flip_rows=True)
+    assert np.array_equal(flipped.cpu().numpy(), gold["upsampled"][:, ::-1])
+    assert np.array_equal(ops.depth_preview_u8(up[0]).cpu().numpy(), gold["preview"])
+    # full-size: 128 x 160 -> 1200 x 1600 as eval_dense.py does, against ATen
+    g = torch.Generator().manual_seed(1)
+    d = torch.rand(1, 128, 160, generator=g) * 500 + 400
+    want = torch.nn.functional.interpolate(d.unsqueeze(1), size=(1200, 1600)).squeeze(1)
+    assert torch.equal(ops.upsample_nearest(be.to(d), (1200, 1600)).cpu(), want)
+    # files: the reference's bytes, through both writers and the batch writer
+    p = str(tmp_path / "a.pfm")
+    save_pfm(p, gold["upsampled"][0])
+    assert open(p, "rb").read() == gold["pfm_bytes"].tobytes()
+    back, scale = read_pfm(p)
+    assert np.array_equal(back, gold["upsampled"][0]) and scale == 1.0
+    save_pfm_ms(p, gold["upsampled"][0])
+    assert open(p, "rb").read() == gold["pfm_bytes"].tobytes()
+    outputs = {"depth": small, "photometric_confidence": small * 0.001}
+    ed.save_depth_outputs(outputs, ["scan1/{}/00000000{}", "scan1/{}/00000001{}"], str(tmp_path), size=size)
+    assert open(tmp_path / "scan1" / "depth_est" / "00000000.pfm", "rb").read() == gold["pfm_bytes"].tobytes()
+    conf, _ = read_pfm(str(tmp_path / "scan1" / "confidence" / "00000001.pfm"))
+    assert np.array_equal(conf, (gold["small"] * np.float32(0.001))[1][np.minimum((np.arange(size[0], dtype=np.float32) * (np.float32(12) / np.float32(size[0]))).astype(int), 11)][:, np.minimum((np.arange(size[1], dtype=np.float32) * (np.float32(16) / np.float32(size[1]))).astype(int), 15)])
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "scan1" / "depth_est" / "00000000.pfm.png")), gold["preview"])
+    with pytest.raises(Exception):
+        save_pfm(p, gold["upsampled"][0].astype(np.float64))
