@@ -259,6 +259,18 @@ int mvs_geo_consistency(const float* depth_ref, const float* depth_src, const do
                         float* depth_reprojected, float* x_src, float* y_src, float* x_reprojected, float* y_reprojected,
                         int B, int H, int W, float dist_thresh, float rel_thresh, int apply_mask, void* stream);
 
+/* ---- f1: fused full-resolution front of FeatureNet (jdacs/models/mvsnet.py:20-23, 39-40) ------------------------------ */
+/* conv0 3x3 (3->8) + BN + ReLU -> conv1 3x3 (8->8) + BN + ReLU -> conv2 5x5 stride 2 (8->16) + BN + ReLU in one kernel (eval mode,
+ * BatchNorm folded to per-channel affines): the 8-channel full-resolution maps stay in shared memory.
+ *   imgs [B][N][3][H][W] in img_dtype (fp32 or the volume dtype); out = C8 stack [2][M = N*B][H/2][W/2][8] in `dtype` (fp16 / bf16),
+ *   image m = v * B + b (the input layout of mvs_conv2d_fwd);  affine [3][32] = per layer scale[16] | shift[16] (fp32);
+ *   wfrag = mvs_featnet_front_workspace_bytes() bytes written by mvs_featnet_front_pack from the torch weights
+ *   w0 [8][3][3][3], w1 [8][8][3][3], w2 [16][8][5][5] (fp32). */
+int64_t mvs_featnet_front_workspace_bytes(void);
+int mvs_featnet_front_pack(const float* w0, const float* w1, const float* w2, void* wfrag, int dtype, void* stream);
+int mvs_featnet_front(const void* imgs, int img_dtype, const void* wfrag, const float* affine, void* out, int B, int N,
+                      int H, int W, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

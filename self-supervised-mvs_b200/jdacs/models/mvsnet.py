@@ -34,6 +34,7 @@ class FeatureNet(nn.Module):
         self.conv5 = ConvBnReLU(16, 32, 5, 2, 2)
         self.conv6 = ConvBnReLU(32, 32, 3, 1, 1)
         self.feature = nn.Conv2d(32, 32, 3, 1, 1)
+        self.fused_front = True     # forward_maps: conv0 + conv1 + conv2 as one kernel (False: one tcgen05 launch per layer)
 
     def forward(self, x):
         x = self.conv1(self.conv0(x))
@@ -92,13 +93,22 @@ class FeatureNet(nn.Module):
                                scale, shift, True))
             layers.append((ops.pack_conv2d_weight(self.feature.weight), self.feature.out_channels, 3, 1, None,
                            self.feature.bias.detach().float().contiguous(), False))
-            hit = (sig, layers, {})
+            # the three full-resolution layers as one kernel (csrc/featnet_front.cu): weight fragments + affine table
+            front = ops.featnet_front_pack(self.conv0.conv.weight, self.conv1.conv.weight, self.conv2.conv.weight,
+                                           [(l[4], l[5]) for l in layers[:3]], dtype)
+            hit = (sig, layers, {}, front)
             if keep:
                 self._folded[key] = hit
         b, n = imgs.shape[0], imgs.shape[1]
-        x = ops.pack_images_c8(imgs, dtype)
+        first = 0
+        if self.fused_front:
+            x = ops.featnet_front(imgs, hit[3][0], hit[3][1], dtype)
+            first = 3
+        else:
+            x = ops.pack_images_c8(imgs, dtype)
         for i, (g, cout, k, stride, scale, shift, relu) in enumerate(hit[1]):
-            x = ops.conv2d_raw(x, g, cout, k, stride, scale, shift, relu, out_padded=(i == len(hit[1]) - 1), tile_cache=hit[2])
+            if i >= first:
+                x = ops.conv2d_raw(x, g, cout, k, stride, scale, shift, relu, out_padded=(i == len(hit[1]) - 1), tile_cache=hit[2])
         return x.view(n, b, *x.shape[1:])
 
 

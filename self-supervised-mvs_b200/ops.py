@@ -330,6 +330,33 @@ def conv2d_raw(x: Tensor, g: Tensor, cout: int, ksize: int, stride: int, scale: 
     return y
 
 
+def featnet_front_pack(w0: Tensor, w1: Tensor, w2: Tensor, affines: Sequence[Tuple[Tensor, Tensor]], dtype: torch.dtype):
+    """Weights of FeatureNet.conv0/1/2 and their folded-BN (scale, shift) pairs -> (fragment buffer, affine table [3,32]) for
+    featnet_front."""
+    w0, w1, w2 = _f32c(w0), _f32c(w1), _f32c(w2)
+    if tuple(w0.shape) != (8, 3, 3, 3) or tuple(w1.shape) != (8, 8, 3, 3) or tuple(w2.shape) != (16, 8, 5, 5):
+        raise ValueError("featnet_front: expected FeatureNet's conv0 / conv1 / conv2 weights")
+    frag = torch.empty(_lib.lib().mvs_featnet_front_workspace_bytes(), dtype=torch.uint8, device=w0.device)
+    call("mvs_featnet_front_pack", w0, ptr(w0), ptr(w1), ptr(w2), ptr(frag), dtype_code(dtype))
+    aff = torch.zeros(3, 32, dtype=torch.float32, device=w0.device)
+    for i, (scale, shift) in enumerate(affines):
+        aff[i, :scale.numel()] = scale
+        aff[i, 16:16 + shift.numel()] = shift
+    return frag, aff
+
+
+def featnet_front(imgs: Tensor, frag: Tensor, aff: Tensor, dtype: torch.dtype) -> Tensor:
+    """images [B,N,3,H,W] (fp32 or `dtype`) -> relu(bn(conv2(relu(bn(conv1(relu(bn(conv0(x))))))))) as the C8 stack
+    [2, N*B, H/2, W/2, 8] in `dtype`: one launch, the 8-channel full-resolution maps never reach HBM."""
+    x = imgs.detach().contiguous() if imgs.dtype == dtype else _f32c(imgs)
+    b, n, c, h, w = x.shape
+    if c != 3 or h % 2 or w % 2:
+        raise ValueError("featnet_front: expected 3-channel images with even extents, got %s" % (tuple(x.shape),))
+    out = torch.empty(2, n * b, h // 2, w // 2, 8, dtype=dtype, device=x.device)
+    call("mvs_featnet_front", x, ptr(x), dtype_code(x.dtype), ptr(frag), ptr(aff), ptr(out), b, n, h, w, dtype_code(dtype))
+    return out
+
+
 def _pad_single_channel(t: Tensor) -> Tensor:
     """plain [B,D,H,W] -> C8 [B,1,D,H,W,8] with the value in channel 0."""
     out = torch.zeros(t.shape[0], 1, t.shape[1], t.shape[2], t.shape[3], 8, dtype=torch.float32, device=t.device)

@@ -175,6 +175,62 @@ def test_feature_net_on_tcgen05(gpu, oracle, dtype, tol):
     assert rel_err(got, want) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("batch,views,h,w,img16", [(2, 3, 64, 96, False), (1, 2, 52, 76, True), (1, 5, 128, 160, False), (3, 1, 36, 34, False)])
+def test_fused_featnet_front_matches_the_layered_path_and_aten(gpu, dtype, batch, views, h, w, img16):
+    """mvs_featnet_front (conv0 + conv1 + conv2 of FeatureNet in one kernel: mma.sync stages over shared-memory tiles with
+    recomputed halos) against (a) the three tcgen05 launches it replaces -- same operands, same fp32 accumulation, so equal up
+    to the summation order: a few 16-bit ulps -- and (b) ATen in fp32 on the rounded image / weights.  Ragged tiles (extents not
+    multiples of 32 x 16), one and several images per item, fp32 and 16-bit images."""
+    from ssmvs_b200 import ops
+    from ssmvs_b200.jdacs.models.mvsnet import FeatureNet
+    torch.manual_seed(h + w)
+    net = FeatureNet().eval()
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5); mod.weight.uniform_(0.7, 1.3); mod.bias.normal_(0, 0.2)
+            if isinstance(mod, torch.nn.Conv2d):
+                mod.weight.copy_(mod.weight.to(dtype).float())
+    net = net.to(gpu.device)
+    imgs = torch.randn(batch, views, 3, h, w, device=gpu.device).to(dtype)
+    layers = []
+    for blk in (net.conv0, net.conv1, net.conv2):
+        scale, shift = ops.fold_bn(blk.bn)
+        layers.append((ops.pack_conv2d_weight(blk.conv.weight), blk.conv.out_channels, blk.conv.kernel_size[0], blk.conv.stride[0], scale, shift))
+    frag, aff = ops.featnet_front_pack(net.conv0.conv.weight, net.conv1.conv.weight, net.conv2.conv.weight, [(l[4], l[5]) for l in layers], dtype)
+    got = ops.featnet_front(imgs if img16 else imgs.float(), frag, aff, dtype)
+    x = ops.pack_images_c8(imgs.float(), dtype)
+    for g, cout, k, stride, scale, shift in layers:
+        x = ops.conv2d_raw(x, g, cout, k, stride, scale, shift, True)
+    assert got.shape == x.shape == (2, views * batch, h // 2, w // 2, 8)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert rel_err(got, x) < 4 * ulp, rel_err(got, x)
+    # (b) ATen fp32 on the same rounded inputs, rounding every layer's output like the kernels do
+    y = imgs.float().transpose(0, 1).reshape(views * batch, 3, h, w)
+    with torch.no_grad():
+        for blk in (net.conv0, net.conv1, net.conv2):
+            y = F.relu(blk.bn(blk.conv(y))).to(dtype).float()
+    want = y.view(views * batch, 2, 8, h // 2, w // 2).permute(1, 0, 3, 4, 2)
+    assert rel_err(got, want) < 8 * ulp, rel_err(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_feature_net_fused_front_switch_is_transparent(gpu, dtype):
+    """FeatureNet.forward_maps with and without the fused front: the same zero-bordered maps up to 16-bit rounding."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.models.mvsnet import FeatureNet
+    torch.manual_seed(0)
+    net = FeatureNet().to(gpu.device).eval()
+    synth.randomise_bn(net, 3)
+    imgs = synth.mvsnet_inputs(2, 3, 64, 96, 8, seed=3)["imgs"].to(gpu.device)
+    with torch.no_grad():
+        a = net.forward_maps(imgs, dtype)
+        net.fused_front = False
+        b = net.forward_maps(imgs, dtype)
+    assert a.shape == b.shape and rel_err(a, b) < (4e-3 if dtype == torch.float16 else 3e-2)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 8e-2)])
 def test_feature_pyramid_on_tcgen05(gpu, oracle, dtype, tol):
     """FeaturePyramid.forward_maps (9 launches per level) against the oracle's fp32 pyramid (jdacs-ms/models/network.py:16-41)."""
