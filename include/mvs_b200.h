@@ -42,7 +42,8 @@ int mvs_is_emulation(void);
 /* Test / tuning knobs (kernel-variant selection for A/B parity tests and the tools/ sweeps).  The product path never needs this
  * call and the library never reads the environment.  value < 0 restores the built-in default.  Names: warp_tma (0 = gather from
  * global memory instead of TMA-staged windows), warp_dc, warp_tma_minb, warp_cpt, warp_minb, warp_dz, tc_kdfold (0 = off),
- * tc_planes (1 = one image plane per step), tc_nm, tc_stages, tc_nseg. */
+ * tc_planes (1 = one image plane per step), tc_nm, tc_stages, tc_nseg, warp_bwd_split (0 = sweep backward with one thread per
+ * (pixel, channel block) instead of one per (pixel, channel block, source)). */
 int mvs_set_knob(const char* name, int value);
 
 /* ---- layout ------------------------------------------------------------------------------------------- */
@@ -196,6 +197,10 @@ int mvs_lift_c1(const float* src, void* dst, int dtype, int64_t n, void* stream)
  * or, transposed, [Cin][Cout][27], fp32, zero-initialised by the caller, with cout_real <= d->Cout output channels (1 for a lifted
  * single-channel gradient). */
 int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real, void* stream);
+/* The same for the 2-D layers of the feature extractor run as zero-kd 3-D layers over an image volume (depth axis = image index,
+ * jdacs/models/mvsnet.py:17-34 in training): only the kd = 1 taps are computed; grad_w keeps the [.][.][3][3][3] shape, its
+ * kd = 0, 2 planes are left untouched. */
+int mvs_conv2d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real, void* stream);
 
 /* ---- a7/a8: softmax + soft-argmin + photometric confidence ------------------------------------------------------ */
 /* cost [B][D][H][W] fp32; depth [B][D] or [B][D][H][W]; outputs (any may be NULL): depth_out [B][H][W] fp32,

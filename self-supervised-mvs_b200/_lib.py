@@ -65,6 +65,7 @@ _SIGS = {
     "mvs_bn_act_bwd_apply_t": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _I, _P], _I),
     "mvs_lift_c1": ([_P, _P, _I, _L, _P], _I),
     "mvs_conv3d_wgrad_mma": ([C.POINTER(Conv3dDesc), _P, _P, _P, _I, _P], _I),
+    "mvs_conv2d_wgrad_mma": ([C.POINTER(Conv3dDesc), _P, _P, _P, _I, _P], _I),
     "mvs_softargmin_fwd": ([_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "mvs_softargmin_bwd": ([_P, _P, _I, _P, _P, _I, _I, _I, _I, _P], _I),
     "mvs_depth_hypo_refine": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),

@@ -279,6 +279,7 @@ struct WgParams {
     int tpc, msplit;                       // taps per CTA (9 / 3); warps = tpc * msplit, each owning MT / msplit m-tiles of one tap
     int TH, nht, nwt, ntiles, B;           // P tile rows; tiles per plane; tiles in total (B * Dp * nht * nwt)
     int THq, TWq, q_rows;                  // staged Q tile (with halo)
+    int kd0;                               // first kd plane of taps this launch covers (0; 1 for planar = 2-D layers: kd = 1 only)
     uint32_t p_bytes, q_bytes, buf_stride; // bytes one TMA brings; distance between the two tile buffers (128-byte aligned)
 };
 struct WgMaps { CUtensorMap p, q; };
@@ -306,7 +307,7 @@ conv3d_wgrad_mma_kernel(const __grid_constant__ WgMaps maps, const __grid_consta
     uint8_t* sP = wg_smem;                                              // per buffer: [PCB][TH * TW][8] then [QCB][THq * TWq][8]
     uint8_t* sQ = wg_smem + p.p_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = blockIdx.y;                                       // tap group: kd (tpc = 9) or kd * 3 + kh (tpc = 3)
+    const int group = blockIdx.y + (p.tpc == 9 ? p.kd0 : 3 * p.kd0);    // tap group: kd (tpc = 9) or kd * 3 + kh (tpc = 3)
     const int kd = p.tpc == 9 ? group : group / 3;
     const int tapl = warp % p.tpc, mslice = warp / p.tpc;               // this warp's tap inside the group, and its slice of the m-tiles
     const int kh = p.tpc == 9 ? tapl / 3 : group % 3, kw = tapl % 3;
@@ -465,8 +466,8 @@ static int wg_make_map(CUtensorMap* m, const void* base, int is_bf16, int B, int
     return MVS_OK;
 }
 
-extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real,
-                                    void* stream) {
+static int wgrad_mma_impl(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real, int planar,
+                          void* stream) {
     MVS_REQUIRE(d && x && grad_z && grad_w, MVS_E_ARG, "mvs_conv3d_wgrad_mma: null pointer");
     MVS_REQUIRE(d->dtype_in == MVS_F16 || d->dtype_in == MVS_BF16, MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: 16-bit storage only (fp32 takes mvs_conv3d_bwd_weight)");
     MVS_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->Cin <= 64 && d->Cout <= 64, MVS_E_SHAPE,
@@ -519,7 +520,9 @@ extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, con
     if (rc) return rc;
     rc = wg_make_map(&maps.q, Q, is_bf16, p.B, p.QCB, p.Dq, Hq, Wq, p.TWq, p.THq);
     if (rc) return rc;
-    const int ngroups = 27 / p.tpc;
+    // planar: the depth axis indexes independent images (2-D layers run as zero-kd 3-D layers): only the kd = 1 taps exist
+    p.kd0 = planar ? 1 : 0;
+    const int ngroups = (planar ? 9 : 27) / p.tpc;
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;                      // resident CTAs (shared memory; registers allow 2 at most)
     int gx = (148 * per_sm + ngroups - 1) / ngroups;
     if (gx > p.ntiles) gx = p.ntiles;
@@ -536,7 +539,20 @@ extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, con
 #undef MVS_WG_LAUNCH
     return MVS_CHECK_LAUNCH("mvs_conv3d_wgrad_mma");
 }
+
+extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real,
+                                    void* stream) {
+    return wgrad_mma_impl(d, x, grad_z, grad_w, cout_real, 0, stream);
+}
+
+extern "C" int mvs_conv2d_wgrad_mma(const mvs_conv3d_desc* d, const void* x, const void* grad_z, float* grad_w, int cout_real,
+                                    void* stream) {
+    return wgrad_mma_impl(d, x, grad_z, grad_w, cout_real, 1, stream);
+}
 #else
+extern "C" int mvs_conv2d_wgrad_mma(const mvs_conv3d_desc*, const void*, const void*, float*, int, void*) {
+    return mvs_set_error(MVS_E_UNSUPPORTED, "mvs_conv2d_wgrad_mma: tensor-core kernels do not exist in the emulation build");
+}
 extern "C" int mvs_conv3d_wgrad_mma(const mvs_conv3d_desc*, const void*, const void*, float*, int, void*) {
     return mvs_set_error(MVS_E_UNSUPPORTED, "mvs_conv3d_wgrad_mma: tensor-core kernels do not exist in the emulation build");
 }

@@ -484,10 +484,11 @@ def _adjoint_conv(g: Tensor, weight: Tensor, cin: int, stride: int, transposed: 
     return conv3d_raw(g, g_adj, cin, stride, not transposed, algo=0)
 
 
-def _wgrad_mma(x: Tensor, gz: Tensor, weight: Tensor, cout: int, stride: int, transposed: bool, cout_real: int) -> Tensor:
+def _wgrad_mma(x: Tensor, gz: Tensor, weight: Tensor, cout: int, stride: int, transposed: bool, cout_real: int, planar: bool = False) -> Tensor:
+    """planar: a 2-D layer run as a zero-kd 3-D layer over an image volume -- only the kd = 1 taps are computed."""
     d = _desc(x, cout, stride, transposed, x.dtype, False, 0)
     gw = torch.zeros_like(weight, dtype=torch.float32)
-    call("mvs_conv3d_wgrad_mma", x, C.byref(d), ptr(x), ptr(gz), ptr(gw), cout_real)
+    call("mvs_conv2d_wgrad_mma" if planar else "mvs_conv3d_wgrad_mma", x, C.byref(d), ptr(x), ptr(gz), ptr(gw), cout_real)
     return gw
 
 
@@ -498,7 +499,8 @@ class _ConvBnActTC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor, skip: Optional[Tensor], running_mean: Optional[Tensor],
-                running_var: Optional[Tensor], stride: int, transposed: bool, eps: float, momentum: float, frozen: bool) -> Tensor:
+                running_var: Optional[Tensor], stride: int, transposed: bool, eps: float, momentum: float, frozen: bool,
+                planar: bool = False) -> Tensor:
         x = x.contiguous()
         dt = x.dtype
         cout = weight.shape[1] if transposed else weight.shape[0]
@@ -523,13 +525,13 @@ class _ConvBnActTC(torch.autograd.Function):
         skip_c = None if skip is None else skip.contiguous()
         call("mvs_bn_act_fwd_t", z, ptr(z), ptr(stats[0]), ptr(stats[1]), ptr(skip_c), ptr(y), dtype_code(dt), b, cout, s, 1)
         ctx.save_for_backward(x, weight, z, stats)
-        ctx.meta = (stride, transposed, cout, skip is not None, frozen)
+        ctx.meta = (stride, transposed, cout, skip is not None, frozen, planar)
         return y
 
     @staticmethod
     def backward(ctx, gy: Tensor):
         x, weight, z, stats = ctx.saved_tensors
-        stride, transposed, cout, has_skip, frozen = ctx.meta
+        stride, transposed, cout, has_skip, frozen, planar = ctx.meta
         dt = z.dtype
         gy = gy.detach().to(dt).contiguous()
         b = z.shape[0]
@@ -543,9 +545,9 @@ class _ConvBnActTC(torch.autograd.Function):
              ptr(gpar[0]), ptr(gpar[1]), dtype_code(dt), b, cout, s, 1, int(frozen))
         w32 = _f32c(weight)
         gx = _adjoint_conv(gz, w32, x.shape[1] * 8, stride, transposed) if ctx.needs_input_grad[0] else None
-        gw = _wgrad_mma(x, gz, w32, cout, stride, transposed, cout) if ctx.needs_input_grad[1] else None
+        gw = _wgrad_mma(x, gz, w32, cout, stride, transposed, cout, planar) if ctx.needs_input_grad[1] else None
         return (gx, gw, gpar[0] if ctx.needs_input_grad[2] else None, gpar[1] if ctx.needs_input_grad[3] else None,
-                gy if has_skip else None, None, None, None, None, None, None, None)
+                gy if has_skip else None, None, None, None, None, None, None, None, None)
 
 
 def conv_bn_act_tc(x: Tensor, conv: torch.nn.Module, bn: torch.nn.modules.batchnorm._BatchNorm, skip: Optional[Tensor], frozen: bool) -> Tensor:
@@ -599,12 +601,12 @@ class _ConvTC(torch.autograd.Function):
     kernel, weight gradient on the warp-level MMA kernel (the un-normalised last layer of the 2-D feature extractor)."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], planar: bool = False) -> Tensor:
         x = x.contiguous()
         cout = weight.shape[0]
         y = conv3d_raw(x, pack_conv3d_weight(weight, False), cout, 1, False, shift=None if bias is None else _f32c(bias), algo=0)
         ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
+        ctx.has_bias, ctx.planar = bias is not None, planar
         return y
 
     @staticmethod
@@ -614,9 +616,9 @@ class _ConvTC(torch.autograd.Function):
         g16 = gy.detach().to(x.dtype).contiguous()
         w32 = _f32c(weight)
         gx = _adjoint_conv(g16, w32, x.shape[1] * 8, 1, False) if ctx.needs_input_grad[0] else None
-        gw = _wgrad_mma(x, g16, w32, cout, 1, False, cout) if ctx.needs_input_grad[1] else None
+        gw = _wgrad_mma(x, g16, w32, cout, 1, False, cout, ctx.planar) if ctx.needs_input_grad[1] else None
         gb = gy.detach().float().sum(dim=(0, 2, 3, 4)).reshape(-1) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 # 2-D layers of the feature extractor in TRAINING: a batch of images is a C8 volume whose depth axis is the image index
@@ -663,7 +665,7 @@ def conv2d_bn_relu_tc(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.modules.bat
     mom = bn.momentum if bn.momentum is not None else 0.1
     track = bn.track_running_stats and bn.running_mean is not None
     y = _ConvBnActTC.apply(x, w3, bn.weight, bn.bias, None, bn.running_mean if track else None, bn.running_var if track else None,
-                           1, False, bn.eps, mom, frozen)
+                           1, False, bn.eps, mom, frozen, True)
     if track and not frozen and bn.num_batches_tracked is not None:
         with torch.no_grad():
             bn.num_batches_tracked += 1
@@ -672,7 +674,7 @@ def conv2d_bn_relu_tc(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.modules.bat
 
 def conv2d_bias_tc(x: Tensor, conv: torch.nn.Conv2d) -> Tensor:
     """conv2d(x) + bias over an image volume (3x3, stride 1), differentiable."""
-    return _ConvTC.apply(x, embed_conv2d_weight(conv.weight, conv.stride[0]), conv.bias)
+    return _ConvTC.apply(x, embed_conv2d_weight(conv.weight, conv.stride[0]), conv.bias, True)
 
 
 def fold_bn(bn: torch.nn.modules.batchnorm._BatchNorm) -> Tuple[Tensor, Tensor]:

@@ -103,11 +103,16 @@ def test_wgrad_mma_matches_the_fp32_simt_weight_gradient(gpu, dtype, cin, cout, 
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("channels,nsrc,ref_sq,per_pixel", [(32, 4, False, False), (16, 3, True, True), (8, 1, False, False), (32, 6, False, False)])
-def test_sweep_backward_16bit_matches_fp32_scatter(gpu, dtype, channels, nsrc, ref_sq, per_pixel):
-    """warp_var_bwd16_kernel (run-length merged vector reductions) against the fp32 scalar-atomic kernel on the same rounded
-    feature maps and the same upstream gradient."""
+@pytest.mark.parametrize("split", [1, 0])
+@pytest.mark.parametrize("channels,nsrc,ref_sq,per_pixel", [(32, 4, False, False), (16, 3, True, True), (8, 1, False, False), (32, 6, False, False),
+                                                            (16, 2, False, False), (8, 8, True, False)])
+def test_sweep_backward_16bit_matches_fp32_scatter(gpu, knob, dtype, channels, nsrc, ref_sq, per_pixel, split):
+    """warp_var_bwd16s_kernel (one thread per (pixel, channel block, source), butterfly-summed S1; split = 1, the default) and
+    warp_var_bwd16_kernel (one thread per (pixel, channel block); split = 0), both with run-length merged vector reductions,
+    against the fp32 scalar-atomic kernel on the same rounded feature maps and the same upstream gradient.  19 x 45 maps: the
+    last block of every row of blocks is ragged."""
     from ssmvs_b200 import ops, synth
+    knob("warp_bwd_split", split)
     inp = synth.feature_inputs(2, nsrc + 1, channels, 19, 45, 20, seed=9)
     f = [t.to(dtype).float().to(gpu.device) for t in inp["features"]]
     depth = inp["depth_values"].to(gpu.device)
