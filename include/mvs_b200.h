@@ -276,6 +276,15 @@ int mvs_featnet_front_pack(const float* w0, const float* w1, const float* w2, vo
 int mvs_featnet_front(const void* imgs, int img_dtype, const void* wfrag, const float* affine, void* out, int B, int N,
                       int H, int W, int dtype, void* stream);
 
+/* ---- f4: depth-map fusion (vendored Gipuma fusibile, jdacs/fusion/fusibile/fusibile.cu:138-277) ----------------------- */
+/* normals_depths [V][H][W][4] = (nx, ny, nz, depth) per view; images [V][H][W][4] colours or NULL; cams [V][32] floats =
+ * P 3x4 | inv(P[:, :3]) 3x3 | P[:, 3] | camera centre C | focal length f | pad; subset [nsub] view indices to test against view
+ * `ref`.  points [H][W][12] = fused coordinate (xyz0) | normal (xyz0) | colour (rgb0), valid [H][W] = 1 where at least
+ * num_consistent views agreed (disparity difference < depth_thresh, normal angle < normal_thresh radians). */
+int mvs_fusibile(const float* normals_depths, const float* images, const float* cams, const int* subset, int nsub, int V,
+                 int H, int W, int ref, float depth_thresh, float normal_thresh, int num_consistent, float* points,
+                 uint8_t* valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,7 @@ _SIGS = {
     "mvs_featnet_front_workspace_bytes": ([], _L),
     "mvs_featnet_front_pack": ([_P, _P, _P, _P, _I, _P], _I),
     "mvs_featnet_front": ([_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "mvs_fusibile": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P], _I),
     "mvs_upsample_nearest": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "mvs_depth_preview_u8": ([_P, _P, _L, _F, _F, _P], _I),
     "mvs_geo_consistency": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),

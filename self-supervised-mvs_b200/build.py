@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmvs_b200.so")
-SOURCES = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "conv3d_tc.cu", "invwarp.cu", "loss.cu", "output.cu", "featnet_front.cu", "train.cu"]
+SOURCES = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "conv3d_tc.cu", "invwarp.cu", "loss.cu", "output.cu", "fusion.cu", "featnet_front.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

@@ -844,3 +844,22 @@ def geo_consistency(depth_ref: Tensor, depth_src: Tensor, cams: Tensor, dist_thr
     call("mvs_geo_consistency", dr, ptr(dr), ptr(ds), ptr(cams), ptr(mask), *[ptr(o) for o in outs], b, h, w, float(dist_thresh),
          float(rel_thresh), int(apply_mask))
     return (mask.bool(), *outs)
+
+
+# ------------------------------------------------------------------------------------------------ depth-map fusion
+def fusibile(normals_depths: Tensor, cams: Tensor, ref: int, subset: Sequence[int], depth_thresh: float = 0.25,
+             normal_thresh: float = 0.52, num_consistent: int = 3, images: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """normals_depths [V,H,W,4] (nx, ny, nz, depth), cams [V,32] (include/mvs_b200.h), optional images [V,H,W,4] ->
+    (points [H,W,12] = coordinate | normal | colour, valid bool [H,W]) for reference view `ref` against the views in `subset`."""
+    nd = _f32c(normals_depths)
+    cams = _f32c(cams)
+    v, h, w, c = nd.shape
+    if c != 4 or cams.shape != (v, 32):
+        raise ValueError("fusibile: normals_depths must be [V,H,W,4] and cams [V,32]")
+    img = None if images is None else _f32c(images)
+    sub = torch.tensor(list(subset), dtype=torch.int32, device=nd.device)
+    points = torch.empty(h, w, 12, dtype=torch.float32, device=nd.device)
+    valid = torch.empty(h, w, dtype=torch.uint8, device=nd.device)
+    call("mvs_fusibile", nd, ptr(nd), ptr(img), ptr(cams), ptr(sub), sub.numel(), v, h, w, int(ref), float(depth_thresh), float(normal_thresh),
+         int(num_consistent), ptr(points), ptr(valid))
+    return points, valid.bool()

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "self-supervised-mvs_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmvs_emu.so")
-SOURCES = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "invwarp.cu", "loss.cu", "output.cu", "featnet_front.cu", "train.cu"]
+SOURCES = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "invwarp.cu", "loss.cu", "output.cu", "fusion.cu", "featnet_front.cu", "train.cu"]
 
 
 def build_emu() -> str:

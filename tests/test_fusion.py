@@ -1,0 +1,84 @@
+"""Depth-map fusion (csrc/fusion.cu rebuilt from the vendored Gipuma fusibile kernel) against its NumPy restatement
+(oracle/fusion.py -- parity unpinned: the original binary cannot be built or run here) and through scene-level properties: a
+consistent synthetic scene fuses back onto its own surface, an inconsistent view is voted out."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fusion_oracle():
+    spec = importlib.util.spec_from_file_location("fusion_oracle", os.path.join(ROOT, "oracle", "fusion.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def be(request):
+    return request.getfixturevalue(request.param)
+
+
+def _scene(views=5, h=24, w=32):
+    """A plane z = 600 + 0.3 x_world seen by `views` DTU-like cameras: exact per-view depth maps by ray / plane intersection."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.fusion.fusibile import camera_block
+    k = synth.intrinsics(w, h).astype(np.float64)
+    n_w, d_w = np.array([-0.3, 0.0, 1.0]), 600.0                       # plane n . X = d in world coordinates
+    cams, depths = [], []
+    for v in range(views):
+        e = synth.extrinsics(v).astype(np.float64)
+        cams.append(camera_block(k, e))
+        r, t = e[:3, :3], e[:3, 3]
+        ys, xs = np.mgrid[0:h, 0:w]
+        rays_c = np.linalg.inv(k) @ np.stack([xs.ravel(), ys.ravel(), np.ones(h * w)])      # camera-space rays with z = 1
+        c_w = -r.T @ t
+        rays_w = r.T @ rays_c
+        lam = (d_w - n_w @ c_w) / (n_w @ rays_w)                      # depth along z of the camera
+        depths.append(lam.reshape(h, w).astype(np.float32))
+    return torch.stack(cams), torch.from_numpy(np.stack(depths)), (n_w, d_w)
+
+
+def test_fusion_matches_restatement(be, fusion_oracle):
+    from ssmvs_b200.jdacs.fusion import fusibile as fz
+    cams, depths, _ = _scene()
+    g = torch.Generator().manual_seed(0)
+    depths = depths + 0.3 * torch.randn(depths.shape, generator=g)                          # noise: some votes fail
+    depths[3, 5:12] *= 1.2                                                                   # a band of outliers in view 3
+    nd = fz.constant_normals(depths)
+    nd[..., :3] += 0.2 * torch.randn(nd[..., :3].shape, generator=g)
+    nd[..., :3] /= nd[..., :3].norm(dim=-1, keepdim=True)
+    imgs = torch.rand(5, 24, 32, 4, generator=g)
+    for ref, subset in ((0, [0, 1, 2, 3, 4]), (3, [4, 0, 1])):
+        want_p, want_v = fusion_oracle.fusibile(nd.numpy(), cams.numpy(), ref, subset, 0.25, 0.52, 2, imgs.numpy())
+        pts, valid = fz.fuse_view(be.to(nd), be.to(cams), ref, subset, 0.25, 0.52, 2, be.to(imgs))
+        agree = (valid.cpu().numpy() == want_v)
+        assert agree.mean() > 0.995, agree.mean()                     # decisions on a threshold may flip on the last fp32 bit
+        both = torch.from_numpy(want_v & valid.cpu().numpy())
+        assert 0.2 < both.float().mean() < 1.0
+        err = (pts.cpu()[both] - torch.from_numpy(want_p)[both]).abs().max() / torch.from_numpy(want_p)[both].abs().max()
+        assert err < 1e-5, err
+
+
+def test_consistent_scene_fuses_onto_its_surface_and_outliers_are_voted_out(be):
+    from ssmvs_b200.jdacs.fusion import fusibile as fz
+    cams, depths, (n_w, d_w) = _scene()
+    nd = fz.constant_normals(depths)
+    pts, valid = fz.fuse_view(be.to(nd), be.to(cams), 0, None, 0.25, 0.52, 3)
+    assert valid.float().mean() > 0.5                                  # pixels seen by >= 3 other views
+    xyz = pts[valid][:, :3].cpu().double().numpy()
+    # fused points lie on the plane up to fusibile's own slack: an accepted view contributes the point of its TRUNCATED pixel with
+    # the depth INTERPOLATED at the un-truncated position (fusibile.cu:236-238), i.e. up to a pixel (~1.7 mm here) of lateral error
+    assert np.abs(xyz @ n_w - d_w).max() < 3.0 and np.abs(xyz @ n_w - d_w).mean() < 1.0
+    bad = depths.clone()
+    bad[0] *= 1.1                                                      # the reference view disagrees with everybody
+    _, valid_bad = fz.fuse_view(be.to(fz.constant_normals(bad)), be.to(cams), 0, None, 0.25, 0.52, 3)
+    assert valid_bad.float().mean() < 0.02
+    x, n, c = fz.fuse_scene(be.to(nd), be.to(cams), num_consistent=3)
+    assert x.shape[1] == 3 and x.shape[0] == n.shape[0] == c.shape[0] > 1000
+    assert np.abs(x.cpu().double().numpy() @ n_w - d_w).max() < 3.0
