@@ -112,18 +112,22 @@ class FeatureNet(nn.Module):
         return x.view(n, b, *x.shape[1:])
 
 
-    def forward_train_tc(self, img, dtype, frozen=False):
+    def forward_train_tc(self, imgs, dtype, frozen=False):
         """Differentiable path on the repo's own kernels (training, or eval-mode fine-tuning with `frozen` statistics):
-        img [B,3,H,W] of ONE view -> C8 feature maps [B, C/8, H/4, W/4, 8] in `dtype`.  The B images form a C8 volume whose depth
-        axis is the image index, every layer is the 3-D training op of CostRegNet with zero kd = 0, 2 taps (ops.conv2d_bn_relu_tc):
-        tcgen05 forward / input gradient, tensor-core weight gradient, fp64 batch statistics over the call's images -- per view,
-        as BatchNorm2d sees them in the reference (jdacs/models/mvsnet.py:115)."""
-        b, _, h, w = img.shape
-        x = ops.pack_images_c8(img.unsqueeze(1), dtype).view(1, 1, b, h, w, 8)
+        imgs [B,N,3,H,W] -> one C8 feature map [B, C/8, H/4, W/4, 8] in `dtype` per view.  The B images of a view form a C8 volume
+        whose depth axis is the image index and the N views are the batch entries of that volume; every layer is the 3-D training
+        op of CostRegNet with zero kd = 0, 2 taps (ops.conv2d_bn_relu_tc): tcgen05 forward / input gradient, tensor-core weight
+        gradient, fp64 batch statistics PER VIEW -- as BatchNorm2d sees them in the reference, which calls the extractor once
+        per view (jdacs/models/mvsnet.py:115) -- all views in one launch per layer."""
+        b, n, _, h, w = imgs.shape
+        if n * 32 > 256:                                   # the BatchNorm kernels take <= 256 (view, channel) pairs: view by view
+            return [self.forward_train_tc(imgs[:, v:v + 1], dtype, frozen)[0] for v in range(n)]
+        x = ops.pack_images_c8(imgs, dtype).view(n, 1, b, h, w, 8)         # image m = v * B + b
         for blk in (self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6):
             x = ops.conv2d_bn_relu_tc(x, blk.conv, blk.bn, frozen)
-        x = ops.conv2d_bias_tc(x, self.feature)
-        return x[0].permute(1, 0, 2, 3, 4).contiguous()
+        x = ops.conv2d_bias_tc(x, self.feature)                           # [N, C/8, B, H/4, W/4, 8]
+        x = x.permute(0, 2, 1, 3, 4, 5).contiguous()
+        return [x[v] for v in range(n)]
 
 
 class CostRegNet(nn.Module):
@@ -259,7 +263,7 @@ class MVSNet(nn.Module):
             # tensor-core convolutions and NHWC BatchNorm kernels instead of its fp32 NCHW ones (10 ms -> ~3 ms per item at 512x640)
             if dt != torch.float32 and imgs.is_cuda and self.feature_tc and imgs.shape[-1] % 4 == 0 and imgs.shape[-2] % 4 == 0:
                 # the feature extractor on the repo's tensor-core training kernels, emitting C8 maps for the sweep
-                features = [self.feature.forward_train_tc(imgs[:, v], dt, frozen=not self.training) for v in range(n)]
+                features = self.feature.forward_train_tc(imgs, dt, frozen=not self.training)
             elif dt != torch.float32 and imgs.is_cuda and self.feature_autocast:
                 with torch.autocast("cuda", dtype=dt):
                     features = [self.feature(imgs[:, v].contiguous(memory_format=torch.channels_last)) for v in range(n)]

@@ -500,7 +500,11 @@ class _ConvBnActTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor, skip: Optional[Tensor], running_mean: Optional[Tensor],
                 running_var: Optional[Tensor], stride: int, transposed: bool, eps: float, momentum: float, frozen: bool,
-                planar: bool = False) -> Tensor:
+                planar: bool = False, per_item_stats: bool = False) -> Tensor:
+        """per_item_stats: every batch entry of x normalises with its OWN batch statistics (the feature extractor in training:
+        one entry = the images of one view, which the reference runs as separate calls).  The layout [V][C/8][S][8] of V entries
+        is that of ONE entry with V C channels, so the BatchNorm kernels simply see B = 1, C' = V C; the running statistics take
+        the V momentum updates the separate calls would have made, in order."""
         x = x.contiguous()
         dt = x.dtype
         cout = weight.shape[1] if transposed else weight.shape[0]
@@ -509,45 +513,63 @@ class _ConvBnActTC(torch.autograd.Function):
         s = z[0, 0].numel() // 8
         dev = z.device
         gamma_c, beta_c = _f32c(gamma), _f32c(beta)
-        stats = torch.empty(4, cout, dtype=torch.float32, device=dev)       # a, b, mean, invstd
+        groups = b if (per_item_stats and b > 1) else 1
+        if groups > 1:
+            b, ceff = 1, groups * cout
+            gamma_c, beta_c = gamma_c.repeat(groups), beta_c.repeat(groups)
+        else:
+            ceff = cout
+        stats = torch.empty(4, ceff, dtype=torch.float32, device=dev)       # a, b, mean, invstd
         if frozen:
-            inv = torch.rsqrt(running_var.detach().float() + eps)
+            inv = torch.rsqrt(running_var.detach().float() + eps).repeat(groups)
             stats[0] = gamma_c * inv
-            stats[1] = beta_c - running_mean.detach().float() * stats[0]
-            stats[2] = running_mean.detach().float()
+            stats[1] = beta_c - running_mean.detach().float().repeat(groups) * stats[0]
+            stats[2] = running_mean.detach().float().repeat(groups)
             stats[3] = inv
         else:
-            sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
-            call("mvs_bn_stats_t", z, ptr(z), dtype_code(dt), ptr(sums), b, cout, s)
+            sums = torch.zeros(2, ceff, dtype=torch.float64, device=dev)
+            call("mvs_bn_stats_t", z, ptr(z), dtype_code(dt), ptr(sums), b, ceff, s)
+            direct = groups == 1
             call("mvs_bn_finalize", z, ptr(sums), ptr(gamma_c), ptr(beta_c), float(eps), float(momentum), float(b * s), ptr(stats[0]), ptr(stats[1]),
-                 ptr(stats[2]), ptr(stats[3]), ptr(running_mean), ptr(running_var), cout)
+                 ptr(stats[2]), ptr(stats[3]), ptr(running_mean) if direct else None, ptr(running_var) if direct else None, ceff)
+            if not direct and running_mean is not None:
+                # V sequential updates r <- (1 - m) r + m x_v  ==  (1 - m)^V r + sum_v m (1 - m)^(V - 1 - v) x_v
+                # (built on the device: no host-to-device copy, the step may be under CUDA-graph capture)
+                wts = (momentum * torch.pow(1.0 - momentum, torch.arange(groups - 1, -1, -1, dtype=torch.float32, device=dev))).view(groups, 1)
+                n = float(s)
+                var_unbiased = (stats[3].pow(-2) - eps).clamp_min_(0.0) * (n / max(n - 1.0, 1.0))
+                running_mean.mul_((1.0 - momentum) ** groups).add_((wts * stats[2].view(groups, cout)).sum(0))
+                running_var.mul_((1.0 - momentum) ** groups).add_((wts * var_unbiased.view(groups, cout)).sum(0))
         y = torch.empty_like(z)
         skip_c = None if skip is None else skip.contiguous()
-        call("mvs_bn_act_fwd_t", z, ptr(z), ptr(stats[0]), ptr(stats[1]), ptr(skip_c), ptr(y), dtype_code(dt), b, cout, s, 1)
+        call("mvs_bn_act_fwd_t", z, ptr(z), ptr(stats[0]), ptr(stats[1]), ptr(skip_c), ptr(y), dtype_code(dt), b, ceff, s, 1)
         ctx.save_for_backward(x, weight, z, stats)
-        ctx.meta = (stride, transposed, cout, skip is not None, frozen, planar)
+        ctx.meta = (stride, transposed, cout, skip is not None, frozen, planar, groups)
         return y
 
     @staticmethod
     def backward(ctx, gy: Tensor):
         x, weight, z, stats = ctx.saved_tensors
-        stride, transposed, cout, has_skip, frozen, planar = ctx.meta
+        stride, transposed, cout, has_skip, frozen, planar, groups = ctx.meta
         dt = z.dtype
         gy = gy.detach().to(dt).contiguous()
-        b = z.shape[0]
+        b = z.shape[0] if groups == 1 else 1
+        ceff = cout * groups
         s = z[0, 0].numel() // 8
-        red = torch.zeros(2, cout, dtype=torch.float64, device=z.device)
+        red = torch.zeros(2, ceff, dtype=torch.float64, device=z.device)
         call("mvs_bn_act_bwd_reduce_t", z, ptr(z), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]), ptr(red), dtype_code(dt),
-             b, cout, s, 1)
+             b, ceff, s, 1)
         gz = torch.empty_like(z)
-        gpar = torch.empty(2, cout, dtype=torch.float32, device=z.device)
+        gpar = torch.empty(2, ceff, dtype=torch.float32, device=z.device)
         call("mvs_bn_act_bwd_apply_t", z, ptr(z), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]), ptr(red), ptr(gz),
-             ptr(gpar[0]), ptr(gpar[1]), dtype_code(dt), b, cout, s, 1, int(frozen))
+             ptr(gpar[0]), ptr(gpar[1]), dtype_code(dt), b, ceff, s, 1, int(frozen))
+        if groups > 1:
+            gpar = gpar.view(2, groups, cout).sum(1)
         w32 = _f32c(weight)
         gx = _adjoint_conv(gz, w32, x.shape[1] * 8, stride, transposed) if ctx.needs_input_grad[0] else None
         gw = _wgrad_mma(x, gz, w32, cout, stride, transposed, cout, planar) if ctx.needs_input_grad[1] else None
         return (gx, gw, gpar[0] if ctx.needs_input_grad[2] else None, gpar[1] if ctx.needs_input_grad[3] else None,
-                gy if has_skip else None, None, None, None, None, None, None, None, None)
+                gy if has_skip else None, None, None, None, None, None, None, None, None, None)
 
 
 def conv_bn_act_tc(x: Tensor, conv: torch.nn.Module, bn: torch.nn.modules.batchnorm._BatchNorm, skip: Optional[Tensor], frozen: bool) -> Tensor:
@@ -626,11 +648,11 @@ class _ConvTC(torch.autograd.Function):
 # 3-D training path (tcgen05 forward / input gradient, MMA weight gradient, fp64 BatchNorm statistics) serves unchanged and the
 # images never mix.  5x5 stride-2 layers run as 3x3 stride-1 layers over the space-to-depth (2x2 parity) form of their input.
 def space_to_depth_c8(x: Tensor) -> Tensor:
-    """[1, Cb, M, H, W, 8] -> [1, 4 Cb, M, H/2, W/2, 8]; new channel block = (row parity * 2 + column parity) * Cb + block."""
-    _, cb, m, h, w, _ = x.shape
+    """[V, Cb, M, H, W, 8] -> [V, 4 Cb, M, H/2, W/2, 8]; new channel block = (row parity * 2 + column parity) * Cb + block."""
+    v, cb, m, h, w, _ = x.shape
     if h % 2 or w % 2:
         raise ValueError("stride-2 feature layers need even extents, got %dx%d" % (h, w))
-    return x.view(1, cb, m, h // 2, 2, w // 2, 2, 8).permute(0, 4, 6, 1, 2, 3, 5, 7).reshape(1, 4 * cb, m, h // 2, w // 2, 8)
+    return x.view(v, cb, m, h // 2, 2, w // 2, 2, 8).permute(0, 4, 6, 1, 2, 3, 5, 7).reshape(v, 4 * cb, m, h // 2, w // 2, 8)
 
 
 def embed_conv2d_weight(weight: Tensor, stride: int) -> Tensor:
@@ -656,8 +678,8 @@ def embed_conv2d_weight(weight: Tensor, stride: int) -> Tensor:
 
 
 def conv2d_bn_relu_tc(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.modules.batchnorm._BatchNorm, frozen: bool) -> Tensor:
-    """relu(bn(conv2d(x))) over an image volume [1, Cin/8, M, H, W, 8] (16-bit), differentiable; batch statistics over the M
-    images unless `frozen`."""
+    """relu(bn(conv2d(x))) over image volumes [V, Cin/8, M, H, W, 8] (16-bit), differentiable; unless `frozen`, each of the V
+    entries (one view's M images) normalises with its own batch statistics, as V separate calls of the layer would."""
     stride = conv.stride[0]
     if stride == 2:
         x = space_to_depth_c8(x)
@@ -665,10 +687,10 @@ def conv2d_bn_relu_tc(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.modules.bat
     mom = bn.momentum if bn.momentum is not None else 0.1
     track = bn.track_running_stats and bn.running_mean is not None
     y = _ConvBnActTC.apply(x, w3, bn.weight, bn.bias, None, bn.running_mean if track else None, bn.running_var if track else None,
-                           1, False, bn.eps, mom, frozen, True)
+                           1, False, bn.eps, mom, frozen, True, True)
     if track and not frozen and bn.num_batches_tracked is not None:
         with torch.no_grad():
-            bn.num_batches_tracked += 1
+            bn.num_batches_tracked += x.shape[0]
     return y
 
 
