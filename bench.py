@@ -686,7 +686,7 @@ def main():
     stages = stage_times()
     peaks = load_peaks()
     try:   # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), per item
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             traffic = json.load(f)
     except Exception:
         traffic = {}
@@ -697,7 +697,7 @@ def main():
     roof_wv = {"kernel": "warp_var_fwd_tma_kernel (fused warp + bilinear gather + variance, TMA-staged source windows)", "bound": "hbm", "achieved": wv_gbs, "peak": peaks["hbm_gbs"],
                "unit": "GB/s", "frac": wv_gbs / peaks["hbm_gbs"], "traffic": traffic.get("warp_var_fwd"), "ms": stages["warp_var"],
                "peak_source": peaks["source"], "algorithmic_bytes": PB * warp_var_bytes(elem),
-               "note": "co-limited on chip: 4 taps x 64 B per (voxel, source) = 31.5 M wavefronts per item through the 128 B/clk L1/shared pipe (ncu: 69 %), FMA pipe 67 %, issue 59 %; DRAM traffic is the algorithmic minimum"}
+               "note": "bound on chip three ways at once: 4 taps x 64 B per (voxel, source) = 31.5 M wavefronts per item through the 128 B/clk L1/shared pipe (ncu: 73 %), FMA pipe 69 % (HFMA2 issues at half rate), issue 67 %; traffic = DRAM reads + SM->L2 write sectors of one ncu --set full capture: 1.008 x the algorithmic bytes (the volume is written exactly once)"}
     roof_conv0 = {"kernel": "conv3d_tc_kernel (conv0: 32->8, 3x3x3, full D x H x W)", "bound": "tensor", "achieved": conv0_tfs,
                   "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": conv0_tfs / peaks["bf16_tflops"],
                   "traffic": traffic.get("conv0"), "ms": stages["conv0"], "peak_source": peaks["source"],

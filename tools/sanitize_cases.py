@@ -106,4 +106,49 @@ def _():
     assert torch.isfinite(x.grad).all()
 
 
+@case("train_16bit")
+def _():
+    """The tensor-core training path: 16-bit CostRegNet (tcgen05 forward / dgrad, MMA wgrad, fp64 BN), FeatureNet on the same
+    kernels with per-view statistics, the split-by-source sweep backward (2, 4 and 8 lanes per pixel)."""
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    for dt in (torch.bfloat16, torch.float16):
+        model = MVSNet(refine=False, train_dtype=dt).to(dev).train()
+        inp = {k: v.to(dev) for k, v in synth.mvsnet_inputs(1, 3, 64, 96, 8, seed=2).items()}
+        model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])["depth"].sum().backward()
+        assert all(p.grad is None or torch.isfinite(p.grad).all() for p in model.parameters())
+    for nsrc in (1, 3, 6):
+        inp = synth.feature_inputs(1, nsrc + 1, 16, 13, 29, 12, seed=4)
+        f = [t.to(dev).requires_grad_(True) for t in inp["features"]]
+        rt = ops.compose_proj(inp["proj_matrices"].to(dev))
+        ops.warp_variance(f[0], f[1:], rt, inp["depth_values"].to(dev), torch.float16).float().sum().backward()
+        assert all(torch.isfinite(t.grad).all() for t in f)
+
+
+@case("loss_output_fusion")
+def _():
+    """Fused UnSupLoss forward / backward, the fused FeatureNet front, the output side and the fusion kernel."""
+    from ssmvs_b200.jdacs.eval_dense import _pair_cams
+    from ssmvs_b200.jdacs.fusion import fusibile as fz
+    from ssmvs_b200.jdacs.models.mvsnet import FeatureNet
+    inp = synth.mvsnet_inputs(2, 5, 64, 80, 8, seed=3)
+    depth = synth.plausible_depth(2, 16, 20, seed=3).to(dev).requires_grad_(True)
+    out = ops.unsup_loss(inp["imgs"].to(dev), inp["cams"].to(dev), depth, 1.0, 0.18)
+    out[0].backward()
+    assert torch.isfinite(out).all() and torch.isfinite(depth.grad).all()
+    net = FeatureNet().to(dev).eval()
+    with torch.no_grad():
+        maps = net.forward_maps(torch.randn(1, 3, 3, 36, 52, device=dev), torch.float16)       # ragged tiles of the fused front
+    assert torch.isfinite(maps.float()).all()
+    import numpy as np
+    k, e0, e1 = synth.intrinsics(40, 32).astype(np.float32), synth.extrinsics(0).astype(np.float32), synth.extrinsics(1).astype(np.float32)
+    d = torch.rand(2, 32, 40, device=dev) * 300 + 500
+    res = ops.geo_consistency(d, d.flip(0), torch.from_numpy(np.stack([_pair_cams(k, e0, k, e1)] * 2)).to(dev))
+    assert torch.isfinite(res[1]).all()
+    up = ops.upsample_nearest(d, (75, 100), flip_rows=True)
+    assert ops.depth_preview_u8(up).dtype == torch.uint8
+    cams = torch.stack([fz.camera_block(k, synth.extrinsics(v)) for v in range(4)]).to(dev)
+    pts, valid = fz.fuse_view(fz.constant_normals(torch.rand(4, 32, 40, device=dev) * 50 + 600), cams, 0, None, 0.25, 0.52, 1)
+    assert torch.isfinite(pts).all()
+
+
 print("sanitize_cases: done")
