@@ -177,6 +177,31 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .256): the two w-parity voxels of a transposed stride-2 output row are adjacent
+// 16-byte vectors, so one lane moves both with one instruction and a warp's access is 1 KB contiguous instead of 32 half-used
+// 32-byte sectors per instruction.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+template <typename T> __device__ __forceinline__ uint4 pack8(const float (&v)[8]);
+template <> __device__ __forceinline__ uint4 pack8<__half>(const float (&v)[8]) {
+    uint4 r; __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    return r;
+}
+template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&v)[8]) {
+    uint4 r; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return r;
+}
+
 struct TensorMaps { CUtensorMap m[4]; };
 
 #ifdef MVS_TC_TRACE
@@ -222,7 +247,18 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
 #pragma unroll
         for (int o0 = 0; o0 < NOV; o0 += NB) {
             uint4 sk[NT][NB];
-            if (SKIP) {
+            constexpr bool PAIR = (NOV == 8) && !C1;       // transposed stride 2, C8 output: voxels q, q + 1 (w parity) are adjacent
+            if (SKIP && PAIR) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int q = 0; q < NB; q += 2) {
+                        const int ov = o0 + q;
+                        sk[t][q] = sk[t][q + 1] = make_uint4(0u, 0u, 0u, 0u);
+                        const int64_t off = off0[t] + ((ov >> 2) * plane + ((ov >> 1) & 1) * row) * vs;
+                        if (ra[t].valid) ldg256(reinterpret_cast<const T*>(p.skip) + off, sk[t][q], sk[t][q + 1]);
+                    }
+            } else if (SKIP) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
 #pragma unroll
@@ -278,7 +314,11 @@ __device__ __forceinline__ void epilogue_rows_v(const TcParams& p, const float* 
 #pragma unroll
                         for (int k = 0; k < 8; ++k) o[k] += sv[k];
                     }
-                    if (ra[t].valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
+                    if (PAIR) {
+                        // the even voxel's vector waits in sk[t][q] (its skip value is consumed); the odd one stores both
+                        if ((q & 1) == 0) sk[t][q] = pack8<T>(o);
+                        else if (ra[t].valid) stg256(reinterpret_cast<T*>(p.y) + off - 8, sk[t][q - 1], pack8<T>(o));
+                    } else if (ra[t].valid) V8<T>::store(reinterpret_cast<T*>(p.y) + off, o);
                 }
         }
     }
