@@ -332,6 +332,8 @@ def run_train(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ssmvs_b200._lib.bind()
+    for kv in args.knob:
+        ssmvs_b200._lib.set_knob(kv.split("=")[0], int(kv.split("=")[1]))
     tdt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.train_dtype]
     PB = args.batch if args.batch_given else 2
     torch.manual_seed(0)
@@ -465,6 +467,8 @@ def run_cvp(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ssmvs_b200._lib.bind()
+    for kv in args.knob:
+        ssmvs_b200._lib.set_knob(kv.split("=")[0], int(kv.split("=")[1]))
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype if args.dtype_given else "bf16"]
     PB = args.batch if args.batch_given else 4
     torch.manual_seed(0)
@@ -505,7 +509,7 @@ def run_cvp(args):
                 "config": {"workload": "CVP-MVSNet forward, 3 pyramid levels, 1 + 4 views of 512x640 (BASELINE.json configs[2])", "global_batch": world * PB,
                            "per_gpu_batch": PB, "parallelism": "dp%d (items sharded, no collective)" % world,
                            "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)",
-                           "launch": "python (no graph)" if graphed is None else "cuda-graph replay of the whole batch (%d C-ABI launches + library kernels per batch)" % per_step_launches},
+                           "launch": "python (no graph)"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": items * CVP_SAMPLES / (ms_e2e * 1e-3), "unit": "depth-samples/s",
                         "h2d_bytes_per_step": world * sum(v.numel() * v.element_size() for v in pinned.values()),
@@ -534,6 +538,7 @@ def main():
     ap.add_argument("--img-dtype", choices=["same", "fp32"], default="same",
                     help="storage of the images handed to MVSNet.forward: 'same' = the volume dtype (16-bit images give bit-identical "
                          "results to fp32 images on the 16-bit path, whose first layer rounds its input anyway, at half the upload)")
+    ap.add_argument("--knob", action="append", default=[], metavar="NAME=VALUE", help="kernel-variant knob for tuning runs (mvs_set_knob); not used by the driver")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -559,6 +564,8 @@ def main():
     dev = torch.device("cuda", local)
     numa_bound = parallel.bind_to_gpu_numa(local) if world > 1 else False    # before any pinned allocation
     ssmvs_b200._lib.bind()
+    for kv in args.knob:
+        ssmvs_b200._lib.set_knob(kv.split("=")[0], int(kv.split("=")[1]))
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
     elem = 4 if dtype == torch.float32 else 2
     model = make_model(dtype).to(dev)

@@ -760,7 +760,7 @@ bool kdfold_of(const Spec* d) {
 }
 // Stride-1 programs fold the 3 kw taps into N (3 column blocks) unless that makes the accumulators so wide that only one
 // M-tile fits in TMEM (2-D layers with 64 output channels): those run 9 entries with shifted A views, like the stride-2 program.
-bool kwfold_of(const Spec* d) { return mode_of(d) == MODE_S1 && !(d->two_d && 3 * cop_of(d) > 128); }
+bool kwfold_of(const Spec* d) { return mode_of(d) == MODE_S1 && !(d->two_d && 3 * cop_of(d) > mvs_knob(MVS_KNOB_TC_KWFOLD_MAX, 128)); }
 int nblk_of(const Spec* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : (kwfold_of(d) ? 3 : 1)) : (mode_of(d) == MODE_T2 ? 8 : 1); }
 int n_of(const Spec* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 // Thin 2-D layers (N <= 32: the 8-channel full-resolution layers of FeatureNet) take TWO image planes per step: a step costs
@@ -959,6 +959,15 @@ bool make_plan(const Spec* d, Plan& pl) {
         // single slot in flight per SM (0.8 TB/s), so every byte of shared memory left over goes to more slots in flight.
         int stages_fit = (int)(((size_t)kSmemLimit - kTail - bbytes) / p.slot_bytes);
         if (stages_fit > kMaxStages) stages_fit = kMaxStages;
+        // ... up to a point: the ring competes with the L1 for the same 256 KB, and the epilogue's skip loads / stores go through
+        // the L1.  Measured per layer at the headline sizes (tools/layer_time.py tc_stages=N, 8 items, us): transposed stride 2
+        // conv11 415 (12 slots) -> 336 (3), conv9 142 -> 123; kd-folded conv0 750 -> 727 (3); stride 1 conv4 74 -> 60 (4-5),
+        // conv2 171 -> 150 (5) / 138 (8); stride 2 conv1 220 -> 212 (5) but 295 at its minimum of 4; the 2-D feature layers
+        // 1.11 -> 1.02 ms per step (4).  So: the minimum for the transposed and kd-folded programs, 5 slots otherwise, 4 in 2-D.
+        {
+            const int cap = (p.mode == MODE_T2 || p.kdfold) ? min_stages : (d->two_d ? max(min_stages, 4) : max(min_stages, 5));
+            if (stages_fit > cap) stages_fit = cap;
+        }
         const int fs = mvs_knob(MVS_KNOB_TC_STAGES, 0);        // test / tuning knob
         if (fs >= min_stages && fs <= stages_fit) stages_fit = fs;
         pl.stages_chosen = stages_fit;

@@ -17,9 +17,9 @@ int mvs_set_error(int code, const char* fmt, ...) {
     return code;
 }
 
-int g_mvs_knobs[MVS_KNOB_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+int g_mvs_knobs[MVS_KNOB_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 static const char* const kKnobNames[MVS_KNOB_COUNT] = {"warp_tma", "warp_dc", "warp_tma_minb", "warp_cpt", "warp_minb", "warp_dz",
-                                                      "tc_kdfold", "tc_planes", "tc_nm", "tc_stages", "tc_nseg", "warp_bwd_split"};
+                                                      "tc_kdfold", "tc_planes", "tc_nm", "tc_stages", "tc_nseg", "warp_bwd_split", "tc_kwfold_max"};
 extern "C" int mvs_set_knob(const char* name, int value) {
     MVS_REQUIRE(name, MVS_E_ARG, "mvs_set_knob: null name");
     for (int i = 0; i < MVS_KNOB_COUNT; ++i)

@@ -66,7 +66,7 @@ static inline int mvs_check_launch(const char* name) {
 // ------------------------------------------------------------------ test / tuning knobs (mvs_set_knob; never read from the environment)
 enum { MVS_KNOB_WARP_TMA, MVS_KNOB_WARP_DC, MVS_KNOB_WARP_TMA_MINB, MVS_KNOB_WARP_CPT, MVS_KNOB_WARP_MINB, MVS_KNOB_WARP_DZ,
        MVS_KNOB_TC_KDFOLD, MVS_KNOB_TC_PLANES, MVS_KNOB_TC_NM, MVS_KNOB_TC_STAGES, MVS_KNOB_TC_NSEG, MVS_KNOB_WARP_BWD_SPLIT,
-       MVS_KNOB_COUNT };
+       MVS_KNOB_TC_KWFOLD_MAX, MVS_KNOB_COUNT };
 extern int g_mvs_knobs[MVS_KNOB_COUNT];   // -1 = unset: the built-in (measured best) default applies
 static inline int mvs_knob(int id, int dflt) { return g_mvs_knobs[id] < 0 ? dflt : g_mvs_knobs[id]; }
 

@@ -9,7 +9,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ssmvs_b200
 from ssmvs_b200 import ops
 
-ssmvs_b200._lib.bind(sys.argv[1] if len(sys.argv) > 1 else None)
+ssmvs_b200._lib.bind(next((a for a in sys.argv[1:] if a.endswith(".so")), None))
+for a in sys.argv[1:]:
+    if "=" in a:
+        ssmvs_b200._lib.set_knob(a.split("=")[0], int(a.split("=")[1]))
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 B = 8
@@ -42,6 +45,9 @@ def layer(name, cin, cout, stride, tr, shape, skip):
 
 
 layer("conv0", 32, 8, 1, False, (192, 128, 160), False)
+layer("conv4", 32, 32, 1, False, (48, 32, 40), False)
+layer("conv6", 64, 64, 1, False, (24, 16, 20), False)
+layer("conv7", 64, 32, 2, True, (24, 16, 20), True)
 layer("conv1", 8, 16, 2, False, (192, 128, 160), False)
 layer("conv2", 16, 16, 1, False, (96, 64, 80), False)
 layer("conv3", 16, 32, 2, False, (96, 64, 80), False)
