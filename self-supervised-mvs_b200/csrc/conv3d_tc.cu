@@ -975,7 +975,9 @@ bool make_plan(const Spec* d, Plan& pl) {
         p.nwt = (p.Wt + kTW - 1) / kTW;
         p.nht = (p.Ht + p.TH - 1) / p.TH;
         const int64_t tiles_nm = (int64_t)p.B * p.nwt * p.nht;
-        found = nM == 1 || nM == forced || tiles_nm * ((p.Dt + 3) / 4) >= 2 * 148;
+        // (stride 2: 4 waves -- with 2, MVSNet's conv3 took 16 x 30 tiles and 158 us where 8 x 30 tiles take 113 us; the other
+        // programs measured equal or slower with the smaller tile)
+        found = nM == 1 || nM == forced || tiles_nm * ((p.Dt + 3) / 4) >= (p.mode == MODE_S2 ? 4 : 2) * 148;
     }
     if (!found) return false;
     p.stages = pl.stages_chosen;
