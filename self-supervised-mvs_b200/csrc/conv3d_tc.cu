@@ -760,7 +760,9 @@ bool kdfold_of(const Spec* d) {
 }
 // Stride-1 programs fold the 3 kw taps into N (3 column blocks) unless that makes the accumulators so wide that only one
 // M-tile fits in TMEM (2-D layers with 64 output channels): those run 9 entries with shifted A views, like the stride-2 program.
-bool kwfold_of(const Spec* d) { return mode_of(d) == MODE_S1 && !(d->two_d && 3 * cop_of(d) > mvs_knob(MVS_KNOB_TC_KWFOLD_MAX, 128)); }
+// (2-D layers with 32 output channels as well: measured 1.02 -> 0.98 ms over FeatureNet, the folded epilogue's three TMEM loads and
+// shuffles per channel block cost more than the extra MMAs; knob tc_kwfold_max = widest folded N)
+bool kwfold_of(const Spec* d) { return mode_of(d) == MODE_S1 && !(d->two_d && 3 * cop_of(d) > mvs_knob(MVS_KNOB_TC_KWFOLD_MAX, 48)); }
 int nblk_of(const Spec* d) { return mode_of(d) == MODE_S1 ? (kdfold_of(d) ? 12 : (kwfold_of(d) ? 3 : 1)) : (mode_of(d) == MODE_T2 ? 8 : 1); }
 int n_of(const Spec* d) { return (nblk_of(d) * cop_of(d) + 15) / 16 * 16; }
 // Thin 2-D layers (N <= 32: the 8-channel full-resolution layers of FeatureNet) take TWO image planes per step: a step costs
