@@ -41,3 +41,47 @@ def test_train_step_runs_and_matches_gather_form(emu):
     want = F.smooth_l1_loss(da[fm], de[fm])
     got = (F.smooth_l1_loss(da, de, reduction="none") * fm.float()).sum() / fm.float().sum()
     assert abs(float(want) - float(got)) < 1e-5 * float(want)
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_equals_the_eager_step(gpu):
+    """GraphedTrainStep (the whole batch -- two forward / fused loss / backward / Adam passes -- captured in one CUDA graph) against
+    the eager TrainStep from the same initial weights, on the same batches and mask boxes (the warm-up steps the graphed step takes
+    before the capture are mirrored): same losses and parameters up to the run-to-run spread of the atomic gradient reductions,
+    over several replays (the graph must pick up new inputs and new boxes)."""
+    import copy
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200.trainer import GraphedTrainStep, TrainStep, draw_mask_box
+    torch.manual_seed(0)
+    dev = gpu.device
+    model_a = MVSNet(refine=False, train_dtype=torch.bfloat16).to(dev)
+    model_b = copy.deepcopy(model_a)
+    init = [p.detach().clone() for p in model_a.parameters()]
+    batches = []
+    for seed in (1, 2, 3):
+        b = {k: v.to(dev) for k, v in synth.mvsnet_inputs(1, 4, 64, 96, 8, seed=seed).items()}
+        b["imgs_aug"] = b["imgs"] + 0.05 * torch.randn_like(b["imgs"])
+        batches.append(b)
+    keys = ("imgs", "imgs_aug", "cams", "proj_matrices", "depth_values")
+    eager = TrainStep(model_a, UnSupLoss(), lr=1e-4)
+    graphed_step = TrainStep(model_b, UnSupLoss(), lr=1e-4)
+    eager.gen.manual_seed(7)
+    graphed_step.gen.manual_seed(7)
+    warm = 2
+    graphed = GraphedTrainStep(graphed_step, batches[0], warmup=warm)        # draws one box, takes `warm` eager steps with it, captures
+    model_a.train()
+    box0 = draw_mask_box(64, 96, eager.gen).to(dev)
+    for _ in range(warm):
+        eager.run(*[batches[0][k] for k in keys], box0)
+    for b in batches:
+        la = eager(*[b[k] for k in keys])
+        lb = graphed(*[b[k] for k in keys])
+        assert torch.isfinite(lb["loss"]) and abs(float(la["loss"]) - float(lb["loss"])) < 3e-2 * abs(float(la["loss"])) + 1e-3
+        assert abs(float(la["augment_loss"]) - float(lb["augment_loss"])) < 0.2 * abs(float(la["augment_loss"])) + 1e-3
+    # both trained, and to (nearly) the same place: distance between the two runs against the distance travelled, over all
+    # parameters (Adam turns the noise of a near-zero gradient into full-size steps, so single entries may differ)
+    moved = sum(float((p.detach() - p0).double().pow(2).sum()) for p, p0 in zip(model_b.parameters(), init)) ** 0.5
+    apart = sum(float((pa.detach() - pb.detach()).double().pow(2).sum()) for pa, pb in zip(model_a.parameters(), model_b.parameters())) ** 0.5
+    assert moved > 1e-3 and apart < 0.5 * moved, (moved, apart)

@@ -9,10 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = os.path.join(ROOT, "self-supervised-mvs_b200")
 lib = os.environ.get("MVS_TRACE_LIB", os.path.join(pkg, "libmvs_b200_trace.so"))
-srcs = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "conv3d_tc.cu", "invwarp.cu"]
+srcs = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "conv3d_tc.cu", "invwarp.cu", "loss.cu", "output.cu", "fusion.cu", "featnet_front.cu", "train.cu"]
 if "--build" in sys.argv:
     subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-                           "-DMVS_TC_TRACE"] + [a for a in sys.argv if a.startswith("-D")] + ["-shared", "-o", lib] + [os.path.join(pkg, "csrc", s) for s in srcs] + ["-lcudart"])
+                           "-DMVS_TC_TRACE"] + [a for a in sys.argv if a.startswith("-D")] + ["-shared", "-o", lib] + [os.path.join(pkg, "csrc", s) for s in srcs] + ["-lcudart", "-lcuda", "--expt-relaxed-constexpr"])
     sys.exit(0)
 import torch
 import ssmvs_b200
