@@ -13,7 +13,7 @@
 //     conv1 on 19 x 35 positions (zero outside the image = conv2's padding)   -> smem [665][8]
 //     conv2 on  8 x 16 positions                                              -> global, C8 stack [2][M][H/2][W/2][8]
 // Every stage is an implicit GEMM on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32 accumulate): M = 16 positions, K = two
-// filter taps x 8 channels, N = 8 output channels.  The 16-byte channel rows of the staged maps are exactly ldmatrix rows, so the A
+// filter taps x 8 channels, N = 8 output channels (the 3x3 stages fold kw into N: see stage3x3).  The 16-byte channel rows of the staged maps are exactly ldmatrix rows, so the A
 // fragment of a (tap pair, 16 positions) is one ldmatrix.x4 whose 32 row addresses carry the tap shifts (and, for conv2, the
 // stride); B fragments (weights in the storage type, packed on the host in fragment order) sit in shared memory.  Folded
 // BatchNorm + ReLU run on the accumulator registers.  Arithmetic is the layered path's: 16-bit operands, fp32 accumulation,
@@ -23,12 +23,16 @@
 #ifndef MVS_CPU_EMU
 namespace {
 
+#ifndef FF_MINB
+#define FF_MINB 3
+#endif
 constexpr int kTOH = 8, kTOW = 16;                         // conv2 output tile
 constexpr int kR1H = 2 * kTOH + 3, kR1W = 2 * kTOW + 3;    // 19 x 35 conv1 outputs
 constexpr int kR0H = kR1H + 2, kR0W = kR1W + 2;            // 21 x 37 conv0 outputs
 constexpr int kRIH = kR0H + 2, kRIW = kR0W + 2;            // 23 x 39 image pixels
-constexpr int kKS3 = 5, kKS5 = 13;                         // k-steps (tap pairs) of a 3x3 / 5x5 filter
-constexpr int kFragWords = (kKS3 + kKS3 + 2 * kKS5) * 32 * 2;   // B fragments: per k-step (and n-tile) 32 lanes x 2 words
+constexpr int kU3 = 6, kKS5 = 13;                          // B-fragment units of a 3x3 stage (2 kh pairs x 3 kw); k-steps (tap pairs) of the 5x5 filter
+constexpr int kFragWords = (kU3 + kU3 + 2 * kKS5) * 32 * 2;     // B fragments: per unit 32 lanes x 2 words
+constexpr int kR1Even = (kR1W + 1) / 2;                    // conv1's output is staged de-interleaved by column parity: even columns first
 
 __device__ __forceinline__ uint32_t ff_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ff_ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -51,62 +55,74 @@ template <> __device__ __forceinline__ float ff_to_float<float>(float v) { retur
 template <> __device__ __forceinline__ float ff_to_float<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float ff_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// One 3x3 stage: out region OH x OW (row-major positions) from the input region (OH + 2) x (OW + 2), both staged as 16-byte rows.
-// Positions outside the image are written as zeros (they are the NEXT layer's padding).
-template <typename T, int OH, int OW>
+// One 3x3 stage: out region OH x OW from the input region (OH + 2) x IW (IW = OW + 2), both staged as 16-byte channel rows.
+// The kw taps are folded into N, as in the tcgen05 kernel: an m-tile is 16 CONSECUTIVE INPUT positions p (pitch-linear over the
+// input region), one ldmatrix.x4 per kh pair brings rows p + kh IW, and three MMAs (one per kw) give
+//     D_kw[p][co] = sum_{kh, ci} in[p + kh IW][ci] W[kh][kw][ci][co],       out[o] = D_0[o] + D_1[o + 1] + D_2[o + 2]
+// -- 2 fragment loads per m-tile instead of 5 (the shared-memory pipe bounds this kernel), at the price of 8 shuffles that
+// fetch rows o + 1, o + 2 from the neighbouring lanes, 14 finished outputs per 16-row tile, and junk at the two columns where a
+// row of the region wraps.  Positions outside the image are written as zeros (they are the NEXT layer's padding).
+// PAR: store the output de-interleaved by column parity (the stride-2 layer that reads it then gets contiguous ldmatrix rows).
+template <typename T, int OH, int OW, bool PAR>
 __device__ __forceinline__ void stage3x3(uint32_t in_base, uint8_t* out, const uint32_t* __restrict__ frag, const float* __restrict__ aff,
                                          int y0, int x0, int H, int W, int warp, int lane) {
-    constexpr int IW = OW + 2, M = OH * OW, MT = (M + 15) / 16;
+    // tiles whose whole output region lies inside the image (all but the border tiles) skip the per-position bounds test
+    const bool interior = y0 >= 0 && x0 >= 0 && y0 + OH <= H && x0 + OW <= W;
+    constexpr int IW = OW + 2, NPOS = OH * IW, MT = (NPOS + 13) / 14;
     const int lj = lane >> 3, li = lane & 7, g = lane >> 2, q = lane & 3;
     const float sc0 = aff[2 * q], sc1 = aff[2 * q + 1], sh0 = aff[16 + 2 * q], sh1 = aff[16 + 2 * q + 1];
-    uint2 bfr[kKS3];                                                      // the stage's weights stay in registers: the shared-memory pipe is
-#pragma unroll                                                            // what bounds this kernel (ncu: 73 % against 20 % tensor pipe)
-    for (int ks = 0; ks < kKS3; ++ks) bfr[ks] = *reinterpret_cast<const uint2*>(frag + (ks * 32 + lane) * 2);
-    uint32_t toff[kKS3];                                                  // byte offset of this lane's tap in every k-step
+    uint2 bfr[2][3];                                                     // the stage's weights stay in registers
 #pragma unroll
-    for (int ks = 0; ks < kKS3; ++ks) {
-        const int tap = min(2 * ks + (lj >> 1), 8);                       // k-step ks = taps 2 ks, 2 ks + 1 (the 10th "tap" has zero weights)
-        toff[ks] = (uint32_t)((tap / 3) * IW + tap % 3) * 16u;
-    }
-    // two m-tiles per iteration: two independent MMA chains per warp hide the ldmatrix -> mma latency
-    for (int mt = 2 * warp; mt < MT; mt += 16) {
-        uint32_t row0[2];
+    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int pm = min((mt + u) * 16 + li + (lj & 1) * 8, M - 1);  // the position whose row address this lane supplies
-            const int ry = pm / OW, rx = pm - ry * OW;
-            row0[u] = in_base + (uint32_t)(ry * IW + rx) * 16u;
+        for (int kw = 0; kw < 3; ++kw) bfr[ks][kw] = *reinterpret_cast<const uint2*>(frag + ((ks * 3 + kw) * 32 + lane) * 2);
+    // this lane's ldmatrix row: position li (+ 8 for matrices 1, 3), tap row kh = 2 ks + (lj >> 1) (kh = 3 has zero weights: reads row 2)
+    const uint32_t lane_row = in_base + (uint32_t)(li + (lj & 1) * 8) * 16u;
+    const uint32_t koff0 = (uint32_t)((lj >> 1) * IW) * 16u, koff1 = (uint32_t)(2 * IW) * 16u;
+    const int src4 = (lane + 4) & 31, src8 = (lane + 8) & 31;
+    for (int mt = warp; mt < MT; mt += 8) {
+        const int p0 = mt * 14;
+        float acc[3][4];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) { acc[kw][0] = acc[kw][1] = acc[kw][2] = acc[kw][3] = 0.f; }
+        uint32_t a[4];
+        ff_ldmatrix_x4(lane_row + (uint32_t)p0 * 16u + koff0, a);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) ff_mma<T>(acc[kw], a, bfr[0][kw].x, bfr[0][kw].y);
+        ff_ldmatrix_x4(lane_row + (uint32_t)p0 * 16u + koff1, a);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) ff_mma<T>(acc[kw], a, bfr[1][kw].x, bfr[1][kw].y);
+        // rows o + 1 / o + 2 of D_1 / D_2: lane g + 1 / g + 2, or (rows 8, 9) the second half of lanes g = 0, 1
+        float o1[2], o2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float a1 = __shfl_sync(0xffffffffu, acc[1][e], src4), b1 = __shfl_sync(0xffffffffu, acc[1][2 + e], src4);
+            const float a2 = __shfl_sync(0xffffffffu, acc[2][e], src8), b2 = __shfl_sync(0xffffffffu, acc[2][2 + e], src8);
+            o1[e] = acc[0][e] + (g < 7 ? a1 : b1) + (g < 6 ? a2 : b2);     // row g
+            o2[e] = acc[0][2 + e] + b1 + b2;                               // row g + 8 (complete for g <= 5)
         }
-        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-        for (int ks = 0; ks < kKS3; ++ks) {
-            uint32_t a0[4], a1[4];
-            ff_ldmatrix_x4(row0[0] + toff[ks], a0);
-            ff_ldmatrix_x4(row0[1] + toff[ks], a1);
-            ff_mma<T>(acc[0], a0, bfr[ks].x, bfr[ks].y);
-            ff_mma<T>(acc[1], a1, bfr[ks].x, bfr[ks].y);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-                const int p = (mt + u) * 16 + g + hrow * 8;
-                if (p < M) {
-                    const int py = p / OW, px = p - py * OW;
-                    const bool inside = (unsigned)(y0 + py) < (unsigned)H && (unsigned)(x0 + px) < (unsigned)W;
-                    const float v0 = fmaxf(acc[u][2 * hrow] * sc0 + sh0, 0.f), v1 = fmaxf(acc[u][2 * hrow + 1] * sc1 + sh1, 0.f);
-                    *reinterpret_cast<uint32_t*>(out + (size_t)p * 16 + q * 4) = inside ? ff_pack2<T>(v0, v1) : 0u;
-                }
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int o = p0 + g + hrow * 8;
+            const int py = o / IW, px = o - py * IW;
+            if ((hrow == 0 || g <= 5) && o < NPOS && px < OW) {
+                const bool inside = interior || ((unsigned)(y0 + py) < (unsigned)H && (unsigned)(x0 + px) < (unsigned)W);
+                const float v0 = fmaxf((hrow ? o2[0] : o1[0]) * sc0 + sh0, 0.f), v1 = fmaxf((hrow ? o2[1] : o1[1]) * sc1 + sh1, 0.f);
+                const int idx = PAR ? py * OW + (px & 1) * ((OW + 1) / 2) + (px >> 1) : py * OW + px;
+                *reinterpret_cast<uint32_t*>(out + (size_t)idx * 16 + q * 4) = inside ? ff_pack2<T>(v0, v1) : 0u;
             }
+        }
     }
 }
 
 template <typename T, typename TS>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, FF_MINB)
 featnet_front_kernel(const TS* __restrict__ imgs, const uint32_t* __restrict__ wfrag, const float* __restrict__ affine, T* __restrict__ out,
                      int B, int N, int H, int W, int tiles_x, int tiles_y) {
-    __shared__ __align__(16) uint8_t s_img[kRIH * kRIW * 16];
-    __shared__ __align__(16) uint8_t s_r0[kR0H * kR0W * 16];
+    // (+16 rows: the last m-tile of a 3x3 stage reads up to 15 + 2 IW rows past its first position; those rows only feed
+    // accumulator rows that are never stored)
+    __shared__ __align__(16) uint8_t s_img[(kRIH * kRIW + 16) * 16];
+    __shared__ __align__(16) uint8_t s_r0[(kR0H * kR0W + 16) * 16];
     __shared__ __align__(16) uint8_t s_r1[kR1H * kR1W * 16];
     __shared__ __align__(16) uint32_t s_frag[kFragWords];
     __shared__ float s_aff[3][32];                                         // per layer: scale[16] | shift[16]
@@ -138,22 +154,23 @@ featnet_front_kernel(const TS* __restrict__ imgs, const uint32_t* __restrict__ w
             *reinterpret_cast<uint4*>(s_img + (size_t)i * 16) = row;
         }
         __syncthreads();
-        stage3x3<T, kR0H, kR0W>(ff_smem_u32(s_img), s_r0, s_frag, s_aff[0], iy0 + 1, ix0 + 1, H, W, warp, lane);
+        stage3x3<T, kR0H, kR0W, false>(ff_smem_u32(s_img), s_r0, s_frag, s_aff[0], iy0 + 1, ix0 + 1, H, W, warp, lane);
         __syncthreads();
-        stage3x3<T, kR1H, kR1W>(ff_smem_u32(s_r0), s_r1, s_frag + kKS3 * 64, s_aff[1], iy0 + 2, ix0 + 2, H, W, warp, lane);
+        stage3x3<T, kR1H, kR1W, true>(ff_smem_u32(s_r0), s_r1, s_frag + kU3 * 64, s_aff[1], iy0 + 2, ix0 + 2, H, W, warp, lane);
         __syncthreads();
         // ---- conv2: 5x5, stride 2, 8 -> 16: one m-tile (16 of the 128 output positions = one tile row) per warp, two n-tiles
         {
             const int lj = lane >> 3, li = lane & 7, g = lane >> 2, q = lane & 3;
             const int ox_l = li + (lj & 1) * 8;                            // m-tile = output row `warp`, position = column ox_l
-            const uint32_t row0 = ff_smem_u32(s_r1) + (uint32_t)((2 * warp) * kR1W + 2 * ox_l) * 16u;
-            const uint32_t* f2 = s_frag + 2 * kKS3 * 64;
+            // conv1's output is de-interleaved by column parity: column 2 ox + kw sits at (kw & 1) * kR1Even + ox + (kw >> 1)
+            const uint32_t row0 = ff_smem_u32(s_r1) + (uint32_t)((2 * warp) * kR1W + ox_l) * 16u;
+            const uint32_t* f2 = s_frag + 2 * kU3 * 64;
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int ks = 0; ks < kKS5; ++ks) {
                 const int tap = min(2 * ks + (lj >> 1), 24);               // (unrolled: the tap arithmetic folds to one select per k-step)
                 uint32_t a[4];
-                ff_ldmatrix_x4(row0 + (uint32_t)((tap / 5) * kR1W + tap % 5) * 16u, a);
+                ff_ldmatrix_x4(row0 + (uint32_t)((tap / 5) * kR1W + ((tap % 5) & 1) * kR1Even + ((tap % 5) >> 1)) * 16u, a);
 #pragma unroll
                 for (int n = 0; n < 2; ++n) {
                     const uint2 bb = *reinterpret_cast<const uint2*>(f2 + ((ks * 2 + n) * 32 + lane) * 2);
@@ -188,19 +205,24 @@ __global__ void featnet_front_pack_kernel(const float* __restrict__ w0, const fl
                                           uint32_t* __restrict__ frag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;                   // one 32-bit word each
     if (i >= kFragWords) return;
-    const int word = i & 1, lane = (i >> 1) & 31, unit = i >> 6;          // unit = k-step (x n-tile) index over the three layers
+    const int word = i & 1, lane = (i >> 1) & 31, unit = i >> 6;          // unit over the three layers: 6 + 6 + 26
     const int g = lane >> 2, q = lane & 3;
-    int layer, ks, nt = 0;
-    if (unit < kKS3) { layer = 0; ks = unit; }
-    else if (unit < 2 * kKS3) { layer = 1; ks = unit - kKS3; }
-    else { layer = 2; ks = (unit - 2 * kKS3) >> 1; nt = (unit - 2 * kKS3) & 1; }
     float v[2];
     for (int e = 0; e < 2; ++e) {
-        const int k = 2 * q + e + word * 8, tap = 2 * ks + k / 8, c = k % 8, n = nt * 8 + g;
+        const int k = 2 * q + e + word * 8, c = k % 8;
         float w = 0.f;
-        if (layer == 0) { if (tap < 9 && c < 3) w = w0[(n * 3 + c) * 9 + tap]; }
-        else if (layer == 1) { if (tap < 9) w = w1[(n * 8 + c) * 9 + tap]; }
-        else { if (tap < 25) w = w2[(n * 8 + c) * 25 + tap]; }
+        if (unit < 2 * kU3) {
+            // 3x3 stages, kw folded into N: unit = ks * 3 + kw, K = kh pair (2 ks, 2 ks + 1) x 8 channels, N = 8 output channels
+            const int layer = unit / kU3, u = unit % kU3, ks = u / 3, kw = u % 3, kh = 2 * ks + k / 8, n = g;
+            if (kh < 3) {
+                if (layer == 0) { if (c < 3) w = w0[(n * 3 + c) * 9 + kh * 3 + kw]; }
+                else w = w1[(n * 8 + c) * 9 + kh * 3 + kw];
+            }
+        } else {
+            // 5x5 stride 2: unit = ks * 2 + n-tile, K = tap pair (2 ks, 2 ks + 1) x 8 channels
+            const int u = unit - 2 * kU3, ks = u >> 1, nt = u & 1, tap = 2 * ks + k / 8, n = nt * 8 + g;
+            if (tap < 25) w = w2[(n * 8 + c) * 25 + tap];
+        }
         v[e] = w;
     }
     frag[i] = ff_pack2<T>(v[0], v[1]);
@@ -227,7 +249,7 @@ extern "C" int mvs_featnet_front(const void* imgs, int img_dtype, const void* wf
     const int tiles_x = (W / 2 + kTOW - 1) / kTOW, tiles_y = (H / 2 + kTOH - 1) / kTOH;
     const int64_t total = (int64_t)tiles_x * tiles_y * B * N;
     MVS_REQUIRE(total < (1ll << 31), MVS_E_SHAPE, "mvs_featnet_front: too many tiles");
-    const unsigned grid = (unsigned)(total < 148 * 3 ? total : 148 * 3);
+    const unsigned grid = (unsigned)(total < 148 * FF_MINB ? total : 148 * FF_MINB);
     cudaStream_t st = (cudaStream_t)stream;
 #define MVS_FF_LAUNCH(T, TS) featnet_front_kernel<T, TS><<<grid, 256, 0, st>>>((const TS*)imgs, (const uint32_t*)wfrag, affine, (T*)out, B, N, H, W, tiles_x, tiles_y)
     if (dtype == MVS_F16) {

@@ -617,8 +617,11 @@ warp_var_fwd_tma_kernel(const __grid_constant__ WvMaps maps, const T* __restrict
         const int s = threadIdx.x;
         // one pixel of slack on the low side and two on the high side (the +1 tap and the rounding of interior pixels, whose
         // coordinates are fused differently from the corners' by at most an ulp)
-        const int bx = max((int)floorf(__int_as_float(s_min[s][0]) - 0.01f), 0), by = max((int)floorf(__int_as_float(s_min[s][1]) - 0.01f), 0);
-        const int ex = (int)floorf(__int_as_float(s_max[s][0]) + 0.01f) + 1, ey = (int)floorf(__int_as_float(s_max[s][1]) + 0.01f) + 1;
+        // (slack grows with the coordinate magnitude: the interior pixels' fused arithmetic and rcp.approx agree with the corners'
+        // to a few ulps of the coordinate, 2^-22 relative -- 0.01 px covers maps up to ~4000 px, beyond that the term takes over)
+        const float slack = 0.01f + 4.0e-6f * fmaxf(xmax, ymax);
+        const int bx = max((int)floorf(__int_as_float(s_min[s][0]) - slack), 0), by = max((int)floorf(__int_as_float(s_min[s][1]) - slack), 0);
+        const int ex = (int)floorf(__int_as_float(s_max[s][0]) + slack) + 1, ey = (int)floorf(__int_as_float(s_max[s][1]) + slack) + 1;
         s_org[s][0] = bx; s_org[s][1] = by;
         s_staged[s] = (!s_bad[s] && ex - bx < kBW && ey - by < kBH) ? 1 : 0;
     }

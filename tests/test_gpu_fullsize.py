@@ -291,3 +291,49 @@ def test_streamed_forward_pipeline_matches_direct_calls(gpu):
             assert len(got) == n
             for g, w in zip(got, want):
                 assert torch.equal(g["depth"], w["depth"].cpu()) and torch.equal(g["photometric_confidence"], w["photometric_confidence"].cpu())
+
+
+def test_fused_loss_at_full_size_against_the_oracle(gpu, oracle):
+    """UnSupLoss at the headline size (N = 5 views of 512x640, 128x160 depth map) against oracle.unsup_loss on the CPU: the four
+    scalars and d/d depth (the fp64 block-reduced sums vs torch's fp32 reductions: 1e-5 / 1e-4 as on the small fixtures)."""
+    from ssmvs_b200 import ops, synth
+    inp = synth.mvsnet_inputs(1, 5, 512, 640, 8, seed=4)
+    depth = synth.plausible_depth(1, 128, 160, seed=4)
+    d_ref = depth.clone().requires_grad_(True)
+    want = oracle.unsup_loss(inp["imgs"], inp["cams"], d_ref, True, 0.18)
+    want["total"].backward()
+    d = depth.to(gpu.device).requires_grad_(True)
+    out = ops.unsup_loss(inp["imgs"].to(gpu.device), inp["cams"].to(gpu.device), d, 1.0, 0.18)
+    out[0].backward()
+    for i, k in enumerate(("total", "reconstr", "ssim", "smooth")):
+        assert rel_err(out[i], want[k]) < 1e-5, k
+    assert rel_err(d.grad, d_ref.grad) < 2e-4
+
+
+def test_geometric_filter_at_output_size_against_the_oracle(gpu):
+    """mvs_geo_consistency on 1200 x 1600 maps (the size eval_dense.py writes) against the NumPy restatement that the golden
+    fixture pins to the reference's own functions: identical masks, identical coordinates."""
+    import importlib.util
+    import numpy as np
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs import eval_dense as ed
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("output_side_oracle", os.path.join(root, "oracle", "output_side.py"))
+    side = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(side)
+    h, w = 1200, 1600
+    k = synth.intrinsics(w, h).astype(np.float32)
+    e0, e1 = synth.extrinsics(0).astype(np.float32), synth.extrinsics(1).astype(np.float32)
+    g = np.random.default_rng(0)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    d_ref = (620 + 40 * np.sin(xx / 90.0) * np.cos(yy / 70.0)).astype(np.float32)
+    d_src = (d_ref + g.normal(0, 1.5, (h, w))).astype(np.float32)
+    d_src[300:340] = 0
+    want = side.check_geometric_consistency(d_ref, k, e0, d_src, k, e1)
+    got = ed.check_geometric_consistency(torch.from_numpy(d_ref).to(gpu.device), k, e0, torch.from_numpy(d_src).to(gpu.device), k, e1)
+    mism = int((got[0].cpu().numpy() != want[0]).sum())
+    assert mism <= 2, mism                               # a threshold decision may sit on the last bit of an fp64 product
+    assert 0.02 < want[0].mean() < 0.98
+    same = got[0].cpu().numpy() & want[0]
+    assert np.allclose(got[1].cpu().numpy()[same], want[1][same], rtol=1e-6, atol=1e-4)
+    assert np.allclose(got[2].cpu().numpy(), want[2], rtol=1e-6, atol=1e-3, equal_nan=True)
