@@ -416,7 +416,7 @@ def run_train(args):
         t_wb = _event_ms(lambda: torch.autograd.grad(v, feats, gv, retain_graph=True), dev, flush)
         bwd_bytes = PB * (elem * CHANNELS * SAMPLES_PER_ITEM + VIEWS * CHANNELS * HF * WF * (elem + 4))
         gbs = bwd_bytes / (t_wb * 1e-3) / 1e9
-        rooflines["roofline_sweep_bwd"] = {"kernel": "warp_var_bwd16_kernel (+ unpack of the 5 gradient maps)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+        rooflines["roofline_sweep_bwd"] = {"kernel": "warp_var_bwd16s_kernel (sweep backward, one thread per (pixel, channel block, source); + unpack of the 5 gradient maps)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                            "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "ms": t_wb, "peak_source": peaks["source"],
                                            "algorithmic_bytes": bwd_bytes}
     dominant = max(rooflines.values(), key=lambda r: r["ms"]) if rooflines else None
