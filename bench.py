@@ -521,13 +521,103 @@ def run_cvp(args):
     parallel.barrier()
 
 
+def run_output(args):
+    """The inference output side at the size eval_dense.py writes (1200 x 1600 maps): the geometric-consistency
+    filter of one reference view against 10 source views per step (jdacs/eval_dense.py:177-232) is the timed path; the nearest
+    resize of depth + confidence (:150-153) and the fusibile consensus kernel (fusion/fusibile/fusibile.cu:138-277) are timed
+    beside it.  cpu_baseline = the NumPy restatement of the reference's own functions (oracle/output_side.py, pinned to them by
+    tests/golden/jdacs_output_side.npz) on the host, one pair."""
+    import importlib.util
+    import numpy as np
+    import ssmvs_b200
+    from ssmvs_b200 import ops, parallel, synth
+    from ssmvs_b200.jdacs.eval_dense import _pair_cams
+    from ssmvs_b200.jdacs.fusion import fusibile as fz
+    rank, world, local = parallel.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ssmvs_b200._lib.bind()
+    H, W, S = 1200, 1600, 10
+    k = synth.intrinsics(W, H).astype(np.float32)
+    ex = [synth.extrinsics(v).astype(np.float32) for v in range(5)]
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    d_ref = (620 + 40 * np.sin(xx / 90.0) * np.cos(yy / 70.0) + rank).astype(np.float32)
+    d_src = np.stack([(d_ref + np.float32(0.2 * s)) for s in range(S)]).astype(np.float32)
+    cams = torch.from_numpy(np.stack([_pair_cams(k, ex[0], k, ex[1 + s % 4]) for s in range(S)])).to(dev)
+    pin_ref, pin_src = torch.from_numpy(d_ref).pin_memory(), torch.from_numpy(d_src).pin_memory()
+    dr = pin_ref.to(dev).unsqueeze(0).expand(S, -1, -1).contiguous()
+    ds = pin_src.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host_mask = torch.empty(S, H, W, dtype=torch.bool).pin_memory()
+    host_depth = torch.empty(S, H, W, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        return ops.geo_consistency(dr, ds, cams)
+
+    def step_e2e():
+        r = pin_ref.to(dev, non_blocking=True).unsqueeze(0).expand(S, -1, -1).contiguous()
+        o = ops.geo_consistency(r, pin_src.to(dev, non_blocking=True), cams)
+        host_mask.copy_(o[0], non_blocking=True)
+        host_depth.copy_(o[1], non_blocking=True)
+
+    l0 = ssmvs_b200._lib.launches
+    with ClockSampler(local) as clk:
+        ms_total = _timed_steps(step_resident, args.steps, args.warmup, dev, flush, parallel)
+        launches = ssmvs_b200._lib.launches - l0
+        ms_e2e = _timed_steps(step_e2e, args.steps, 1, dev, flush, parallel)
+    clocks = clk.summary()
+    peaks = load_peaks()
+    px = S * H * W
+    geo_bytes = px * (4 + 4 + 1 + 5 * 4)          # both depth maps read, the mask and five float maps written
+    t_geo = ms_total / args.steps
+    small = torch.rand(16, 128, 160, device=dev) * 500 + 400
+    t_up = _event_ms(lambda: ops.upsample_nearest(small, (H, W), flip_rows=True), dev, flush)
+    up_bytes = 16 * (128 * 160 + H * W) * 4
+    V = 10
+    nd = fz.constant_normals(torch.from_numpy(np.stack([d_ref] * V)).to(dev))
+    fcams = torch.stack([fz.camera_block(k, synth.extrinsics(v % 5)) for v in range(V)]).to(dev)
+    t_fuse = _event_ms(lambda: fz.fuse_view(nd, fcams, 0, None, 0.25, 0.52, 3), dev, flush)
+    if rank == 0:
+        line = {"metric": "pixels/sec through the geometric-consistency filter (reference view vs 10 source views, 1200x1600)",
+                "value": world * args.steps * px / (ms_total * 1e-3), "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_geo, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 per-pixel algebra, f32 maps (the reference's NumPy promotions)", "data": "synthetic",
+                "config": {"workload": "inference output side: reproject_with_depth + check_geometric_consistency, 10 pairs of 1200x1600 maps per step "
+                                       "(jdacs/eval_dense.py:177-232)", "pairs_per_step": S,
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step event pairs)", "launch": "python (one C-ABI launch per step)"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": world * args.steps * px / (ms_e2e * 1e-3), "unit": "pixels/s", "h2d_bytes_per_step": world * (1 + S) * H * W * 4,
+                        "d2h_bytes_per_step": world * S * H * W * 5, "ms_per_step": ms_e2e / args.steps,
+                        "how": "every step uploads the reference and the 10 source depth maps from pinned memory and reads masks + re-projected depths back"},
+                "roofline": {"kernel": "geo_consistency_kernel", "bound": "hbm", "achieved": geo_bytes / (t_geo * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": geo_bytes / (t_geo * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": t_geo,
+                             "peak_source": peaks["source"], "algorithmic_bytes": geo_bytes,
+                             "note": "~120 fp64 FMAs per pixel and a scattered 4-tap gather: fp64-issue bound below the HBM roofline"},
+                "upsample_nearest": {"maps": 16, "ms": t_up, "algorithmic_bytes": up_bytes, "gbs": up_bytes / t_up / 1e6, "frac_of_hbm_peak": up_bytes / t_up / 1e6 / peaks["hbm_gbs"]},
+                "fusibile": {"views": V, "ms_per_reference_view": t_fuse}}
+        if world == 1 and not args.no_cpu_baseline:
+            spec = importlib.util.spec_from_file_location("output_side_oracle", os.path.join(ROOT, "oracle", "output_side.py"))
+            side = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(side)
+            t0 = time.perf_counter()
+            for s_ in range(3):
+                side.check_geometric_consistency(d_ref, k, ex[0], d_src[s_], k, ex[1 + s_ % 4])
+            sec = (time.perf_counter() - t0) / 3
+            line["cpu_baseline"] = {"value": H * W / sec, "unit": "pixels/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "3 of the 10 pairs: NumPy restatement of reproject_with_depth + check_geometric_consistency (fp64 BLAS matmuls, "
+                                              "remap restated in NumPy) on the host"}
+        print(json.dumps(line))
+    parallel.barrier()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["mvsnet", "cvp", "train"], default="mvsnet",
+    ap.add_argument("--workload", choices=["mvsnet", "cvp", "train", "output"], default="mvsnet",
                     help="mvsnet = the headline metric (BASELINE configs[1]); cvp = configs[2]; train = configs[3] (one JDACS training batch)")
     ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default=None, help="storage dtype of the inference workloads (default fp16; cvp: bf16)")
     ap.add_argument("--train-dtype", choices=["fp16", "bf16", "fp32"], default="bf16")
@@ -557,6 +647,8 @@ def main():
         return run_train(args)
     if args.workload == "cvp":
         return run_cvp(args)
+    if args.workload == "output":
+        return run_output(args)
 
     rank, world, local = parallel.init_from_env("nccl")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the plane-sweep path has no CPU fallback)"

@@ -19,6 +19,7 @@ for S in $STEPS; do echo "=== $S"; case $S in
  synccheck) timeout 1500 compute-sanitizer --tool synccheck --error-exitcode 9 python tools/sanitize_cases.py > ${O}_synccheck.log 2>&1; echo "synccheck rc=$?" >> ${O}_synccheck.log; tail -12 ${O}_synccheck.log;;
  ncu)     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file ${O}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-graph --batch ${NCU_BATCH:-8} --ncu-range > ${O}_ncu_bench.log 2>&1; tail -2 ${O}_ncu_bench.log;;
  ncufull) for K in ${NCU_KERNELS:-warp_var_fwd_tma_kernel softargmin_fwd_smem_kernel conv3d_tc_kernel featnet_front_kernel}; do timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$K -c ${NCU_COUNT:-1} -f -o ${O}_ncu_$K python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --no-graph --batch 1 --ncu-range > ${O}_ncufull_$K.log 2>&1; tail -1 ${O}_ncufull_$K.log; done;;
+ output)  timeout 600 python bench.py --workload output --steps 10 --warmup 3 > ${O}_output.json 2> ${O}_output.err; echo "rc=$?" >> ${O}_output.err; cat ${O}_output.json; tail -3 ${O}_output.err;;
  train)   timeout 900 python bench.py --workload train --steps 5 --warmup 3 > ${O}_train.json 2> ${O}_train.err; echo "rc=$?" >> ${O}_train.err; cat ${O}_train.json; tail -3 ${O}_train.err;;
  cvp)     timeout 900 python bench.py --workload cvp --steps 10 --warmup 3 > ${O}_cvp.json 2> ${O}_cvp.err; echo "rc=$?" >> ${O}_cvp.err; cat ${O}_cvp.json; tail -3 ${O}_cvp.err;;
  ncutrain) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"warp_var_bwd16s_kernel|conv3d_wgrad_mma_kernel" -c 4 -f -o ${O}_ncu_train python tools/train_kernels_prof.py > ${O}_ncutrain.log 2>&1; tail -1 ${O}_ncutrain.log;;
