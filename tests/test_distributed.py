@@ -75,6 +75,46 @@ def test_flat_gradient_bucket_allreduce_keeps_replicas_identical():
     assert all(torch.equal(a, b) for a, b in zip(p0, p1))
 
 
+def _train_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    import ssmvs_b200
+    from build_emu import build_emu
+    from ssmvs_b200 import parallel, synth
+    from ssmvs_b200.jdacs.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200.trainer import TrainStep
+    ssmvs_b200._lib.bind(build_emu())                       # CPU tensors: the host-emulation build of the SIMT kernels
+    parallel.init_from_env("gloo")
+    torch.manual_seed(0)                                    # the same initial weights on both ranks ...
+    model = MVSNet(refine=False, train_dtype=torch.float32)
+    step = TrainStep(model, UnSupLoss(), lr=1e-3)
+    inp = synth.mvsnet_inputs(1, 4, 32, 64, 8, seed=10 + rank)                     # ... different data per rank (its shard of the batch)
+    inp["imgs_aug"] = inp["imgs"] + 0.05 * torch.randn(inp["imgs"].shape, generator=torch.Generator().manual_seed(rank))
+    before = [p.detach().clone() for p in model.parameters()]
+    res = step(inp["imgs"], inp["imgs_aug"], inp["cams"], inp["proj_matrices"], inp["depth_values"])
+    out[rank] = ([p.detach().clone() for p in model.parameters()], before, float(res["loss"]), step.grads.flat.clone())
+    dist.destroy_process_group()
+
+
+def test_two_rank_train_step_keeps_replicas_identical():
+    """trainer.TrainStep under world_size 2 (gloo, host-emulation kernels): each rank runs train_sample + train_sample_aug on its
+    own shard, the flat gradient bucket is all-reduced (averaged) before each of the two Adam steps, and the replicas end the batch
+    with bit-identical weights although their data -- and losses -- differ (jdacs/train.py:65 does the same through DataParallel)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_train_worker, args=(world, 29619, out), nprocs=world, join=True)
+    (p0, b0, l0, f0), (p1, b1, l1, f1) = out[0], out[1]
+    assert all(torch.equal(a, b) for a, b in zip(b0, b1))                 # same start
+    assert abs(l0 - l1) > 1e-6                                            # different shards
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))                 # same end: the gradients were averaged
+    assert torch.equal(f0, f1) and f0.abs().sum() > 0
+    assert sum(int(not torch.equal(a, b)) for a, b in zip(p0, b0)) > 10   # and the step did train
+
+
 def test_shard_items_covers_everything():
     from ssmvs_b200 import parallel
     for n in (1, 7, 8, 13):
