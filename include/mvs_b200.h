@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVS_B200_VERSION 101 /* major*100 + minor */
+#define MVS_B200_VERSION 102 /* major*100 + minor */
 
 enum { MVS_F32 = 0, MVS_F16 = 1, MVS_BF16 = 2 };
 enum { MVS_OK = 0, MVS_E_ARG = -1, MVS_E_SHAPE = -2, MVS_E_LAUNCH = -3, MVS_E_UNSUPPORTED = -4 };

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     lib.mvs_version.restype = ctypes.c_int
-    assert lib.mvs_version() == 101
+    assert lib.mvs_version() == 102
     lib.mvs_is_emulation.restype = ctypes.c_int
     assert lib.mvs_is_emulation() == 0
 
