@@ -90,3 +90,33 @@ def test_new_entry_points_validate_before_touching_the_device():
     # unsupported 2-D layer shapes are reported, not silently computed some other way
     bad = Conv2dDesc(2, 8, 8, 16, 16, 16, 16, 7, 1, 1, 1, 0, 0, 0.0)
     assert lib.mvs_conv2d_workspace_bytes(ctypes.byref(bad)) == 0
+
+
+def test_round2_entry_points_validate_before_touching_the_device():
+    """Argument checks of the round-2 entry points (fused loss, FeatureNet front, 2-D weight gradient, output side, fusion) on
+    the PRODUCT library without a GPU: they return an error code and a message before any CUDA call -- null pointers, fewer than
+    three source views (the reference's top-k with k = 3, hazard H5), inconsistent extents, unsupported storage types."""
+    from ssmvs_b200._lib import Conv3dDesc, DEFAULT_PATH, _SIGS
+    lib = ctypes.CDLL(DEFAULT_PATH)
+    for name in ("mvs_unsup_loss_fwd", "mvs_unsup_loss_bwd", "mvs_featnet_front", "mvs_featnet_front_pack", "mvs_featnet_front_workspace_bytes",
+                 "mvs_conv2d_wgrad_mma", "mvs_upsample_nearest", "mvs_depth_preview_u8", "mvs_geo_consistency", "mvs_fusibile", "mvs_last_error"):
+        getattr(lib, name).argtypes, getattr(lib, name).restype = _SIGS[name]
+    p = 1        # a non-null "pointer" that is never dereferenced on the failing paths
+    assert lib.mvs_unsup_loss_fwd(None, p, p, 1, 5, 64, 80, 16, 20, 1.0, 0.18, p, p, p, p, p, p, p, None) == -1 and b"null" in lib.mvs_last_error()
+    assert lib.mvs_unsup_loss_fwd(p, p, p, 1, 3, 64, 80, 16, 20, 1.0, 0.18, p, p, p, p, p, p, p, None) == -2 and b"3 source views" in lib.mvs_last_error()
+    assert lib.mvs_unsup_loss_fwd(p, p, p, 1, 5, 60, 80, 16, 20, 1.0, 0.18, p, p, p, p, p, p, p, None) == -2 and b"4x" in lib.mvs_last_error()
+    assert lib.mvs_unsup_loss_bwd(p, p, p, p, p, p, p, p, None, 1, 5, 16, 20, 1.0, 0.18, None) == -1
+    assert lib.mvs_featnet_front_workspace_bytes() == 38 * 64 * 4
+    assert lib.mvs_featnet_front(p, 0, p, p, p, 1, 5, 64, 80, 0, None) == -4 and b"16-bit" in lib.mvs_last_error()      # fp32 storage: not on this kernel
+    assert lib.mvs_featnet_front(p, 2, p, p, p, 1, 5, 64, 80, 1, None) == -4 and b"volume dtype" in lib.mvs_last_error()  # bf16 images into fp16 volumes
+    assert lib.mvs_featnet_front(p, 1, p, p, p, 1, 5, 63, 80, 1, None) == -2
+    assert lib.mvs_featnet_front_pack(p, p, None, p, 1, None) == -1
+    d = Conv3dDesc(1, 8, 8, 2, 16, 16, 2, 16, 16, 1, 0, 0, 0, 0, 0)                                                          # fp32 storage
+    assert lib.mvs_conv2d_wgrad_mma(ctypes.byref(d), p, p, p, 8, None) == -4 and b"16-bit" in lib.mvs_last_error()
+    assert lib.mvs_upsample_nearest(p, None, 1, 4, 4, 8, 8, 0, None) == -1
+    assert lib.mvs_upsample_nearest(p, p, 1, 4, 4, 0, 8, 0, None) == -2
+    assert lib.mvs_depth_preview_u8(p, p, 16, 500.0, 0.0, None) == -2
+    assert lib.mvs_geo_consistency(p, None, p, p, p, p, p, p, p, 1, 8, 8, 1.0, 0.01, 1, None) == -1
+    assert lib.mvs_geo_consistency(p, p, p, p, p, p, p, p, p, 1, 8, 40000, 1.0, 0.01, 1, None) == -2 and b"32767" in lib.mvs_last_error()
+    assert lib.mvs_fusibile(p, None, p, p, 3, 4, 8, 8, 7, 0.25, 0.52, 3, p, p, None) == -2                               # ref view out of range
+    assert lib.mvs_fusibile(None, None, p, p, 3, 4, 8, 8, 0, 0.25, 0.52, 3, p, p, None) == -1
