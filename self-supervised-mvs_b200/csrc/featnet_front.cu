@@ -34,6 +34,11 @@ constexpr int kU3 = 6, kKS5 = 13;                          // B-fragment units o
 constexpr int kFragWords = (kU3 + kU3 + 2 * kKS5) * 32 * 2;     // B fragments: per unit 32 lanes x 2 words
 constexpr int kR1Even = (kR1W + 1) / 2;                    // conv1's output is staged de-interleaved by column parity: even columns first
 
+// byte offset, inside the parity-staged conv1 output, of tap `tap` of the 5x5 stride-2 filter relative to (row 2 oy, pair column ox)
+constexpr uint32_t ff_c2_off(int tap) {
+    return (uint32_t)(((tap > 24 ? 24 : tap) / 5) * kR1W + (((tap > 24 ? 24 : tap) % 5) & 1) * kR1Even + (((tap > 24 ? 24 : tap) % 5) >> 1)) * 16u;
+}
+
 __device__ __forceinline__ uint32_t ff_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ff_ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -50,6 +55,9 @@ template <> __device__ __forceinline__ void ff_mma<__nv_bfloat16>(float (&c)[4],
 template <typename T> __device__ __forceinline__ uint32_t ff_pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t ff_pack2<__half>(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
 template <> __device__ __forceinline__ uint32_t ff_pack2<__nv_bfloat16>(float a, float b) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+template <typename T> __device__ __forceinline__ T ff_from_float(float v);
+template <> __device__ __forceinline__ __half ff_from_float<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 ff_from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <typename T> __device__ __forceinline__ float ff_to_float(T v);
 template <> __device__ __forceinline__ float ff_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float ff_to_float<__half>(__half v) { return __half2float(v); }
@@ -132,6 +140,7 @@ featnet_front_kernel(const TS* __restrict__ imgs, const uint32_t* __restrict__ w
     const int Ho = H / 2, Wo = W / 2, M = B * N;
     const int64_t plane = (int64_t)H * W;
     const int tiles = tiles_x * tiles_y;
+    bool img_zeroed = false;
 
     for (int t = blockIdx.x; t < tiles * M; t += gridDim.x) {
         const int m = t / tiles, tt = t - m * tiles;                       // image m = v * B + b of the output stack
@@ -142,16 +151,49 @@ featnet_front_kernel(const TS* __restrict__ imgs, const uint32_t* __restrict__ w
         const int iy0 = 2 * oy0 - 4, ix0 = 2 * ox0 - 4;                    // image-space origin of the staged image tile
         __syncthreads();                                                   // previous tile fully consumed (and s_frag / s_aff visible)
         // ---- image tile -> 16-byte rows (3 channels + zeros), zero outside the image
-        for (int i = threadIdx.x; i < kRIH * kRIW; i += blockDim.x) {
-            const int ry = i / kRIW, rx = i - ry * kRIW;
-            const int y = iy0 + ry, x = ix0 + rx;
-            uint4 row = make_uint4(0u, 0u, 0u, 0u);
-            if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
-                const int64_t o = (int64_t)y * W + x;
-                const float c0 = ff_to_float<TS>(__ldg(im + o)), c1 = ff_to_float<TS>(__ldg(im + plane + o)), c2 = ff_to_float<TS>(__ldg(im + 2 * plane + o));
-                row.x = ff_pack2<T>(c0, c1); row.y = ff_pack2<T>(c2, 0.f);
+        if ((W & 3) == 0) {
+            // one work item = 4 consecutive pixels of one row of one channel plane: ONE vector load (the tile starts at a multiple
+            // of 4 pixels and W % 4 == 0, so a group is wholly inside or wholly outside the image), four 2-byte stores into the
+            // channel slot of the four rows.  Slots 3..7 of every row are zeroed once per CTA and never written again.
+            constexpr int kGroups = (kRIW + 3) / 4;
+            if (!img_zeroed) {
+                for (int i = threadIdx.x; i < kRIH * kRIW; i += blockDim.x) *reinterpret_cast<uint4*>(s_img + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+                img_zeroed = true;
+                __syncthreads();
             }
-            *reinterpret_cast<uint4*>(s_img + (size_t)i * 16) = row;
+            for (int i = threadIdx.x; i < kRIH * 3 * kGroups; i += blockDim.x) {
+                const int gx = i % kGroups, c = (i / kGroups) % 3, ry = i / (3 * kGroups);
+                const int y = iy0 + ry, x = ix0 + 4 * gx;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+                    const TS* src = im + (int64_t)c * plane + (int64_t)y * W + x;
+                    if (sizeof(TS) == 4) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+                        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                    } else {
+                        const uint2 r = __ldg(reinterpret_cast<const uint2*>(src));
+                        const TS* h = reinterpret_cast<const TS*>(&r);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = ff_to_float<TS>(h[e]);
+                    }
+                }
+                T* dst = reinterpret_cast<T*>(s_img) + (size_t)(ry * kRIW + 4 * gx) * 8 + c;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * gx + e < kRIW) dst[e * 8] = ff_from_float<T>(v[e]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < kRIH * kRIW; i += blockDim.x) {
+                const int ry = i / kRIW, rx = i - ry * kRIW;
+                const int y = iy0 + ry, x = ix0 + rx;
+                uint4 row = make_uint4(0u, 0u, 0u, 0u);
+                if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+                    const int64_t o = (int64_t)y * W + x;
+                    const float c0 = ff_to_float<TS>(__ldg(im + o)), c1 = ff_to_float<TS>(__ldg(im + plane + o)), c2 = ff_to_float<TS>(__ldg(im + 2 * plane + o));
+                    row.x = ff_pack2<T>(c0, c1); row.y = ff_pack2<T>(c2, 0.f);
+                }
+                *reinterpret_cast<uint4*>(s_img + (size_t)i * 16) = row;
+            }
         }
         __syncthreads();
         stage3x3<T, kR0H, kR0W, false>(ff_smem_u32(s_img), s_r0, s_frag, s_aff[0], iy0 + 1, ix0 + 1, H, W, warp, lane);
@@ -168,9 +210,9 @@ featnet_front_kernel(const TS* __restrict__ imgs, const uint32_t* __restrict__ w
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int ks = 0; ks < kKS5; ++ks) {
-                const int tap = min(2 * ks + (lj >> 1), 24);               // (unrolled: the tap arithmetic folds to one select per k-step)
+                // matrices 0, 1 read tap 2 ks, matrices 2, 3 tap 2 ks + 1: two compile-time offsets and one select per k-step
                 uint32_t a[4];
-                ff_ldmatrix_x4(row0 + (uint32_t)((tap / 5) * kR1W + ((tap % 5) & 1) * kR1Even + ((tap % 5) >> 1)) * 16u, a);
+                ff_ldmatrix_x4(row0 + ((lj >> 1) ? ff_c2_off(2 * ks + 1) : ff_c2_off(2 * ks)), a);
 #pragma unroll
                 for (int n = 0; n < 2; ++n) {
                     const uint2 bb = *reinterpret_cast<const uint2*>(f2 + ((ks * 2 + n) * 32 + lane) * 2);
