@@ -85,3 +85,35 @@ def test_graphed_train_step_equals_the_eager_step(gpu):
     moved = sum(float((p.detach() - p0).double().pow(2).sum()) for p, p0 in zip(model_b.parameters(), init)) ** 0.5
     apart = sum(float((pa.detach() - pb.detach()).double().pow(2).sum()) for pa, pb in zip(model_a.parameters(), model_b.parameters())) ** 0.5
     assert moved > 1e-3 and apart < 0.5 * moved, (moved, apart)
+
+
+def test_feature_layer_embedding_is_plain_tensor_algebra():
+    """The host-side re-expressions behind FeatureNet.forward_train_tc need no kernel to check: a 3x3 Conv2d is the kd = 1 slice of
+    the embedded 3x3x3 weight (input channels padded to 8), a 5x5 stride-2 pad-2 Conv2d is the 3x3 stride-1 convolution of the
+    parity planes (space_to_depth_c8) with the re-ordered weight -- both differentiable w.r.t. the original weight."""
+    from ssmvs_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 12, 20)
+    w5 = torch.randn(16, 8, 5, 5, requires_grad=True)
+    want = F.conv2d(x, w5, None, 2, 2)
+    x8 = x.permute(0, 2, 3, 1).reshape(2, 1, 1, 12, 20, 8).permute(2, 1, 0, 3, 4, 5).contiguous()      # C8 image volume [1, 1, M, H, W, 8]
+    xs = ops.space_to_depth_c8(x8)
+    assert xs.shape == (1, 4, 2, 6, 10, 8)
+    w3 = ops.embed_conv2d_weight(w5, 2)
+    assert w3.shape == (16, 32, 3, 3, 3) and float(w3[:, :, 0].abs().max()) == 0 and float(w3[:, :, 2].abs().max()) == 0
+    got = F.conv2d(xs[0].permute(1, 0, 4, 2, 3).reshape(2, 32, 6, 10), w3[:, :, 1], None, 1, 1)
+    assert (got - want).abs().max() < 1e-4
+    got.sum().backward()                                                  # the embedding is differentiable: same weight gradient
+    g_embed = w5.grad.clone()
+    w5.grad = None
+    want.sum().backward()
+    assert (g_embed - w5.grad).abs().max() < 1e-3
+    w33 = torch.randn(8, 3, 3, 3)
+    e = ops.embed_conv2d_weight(w33, 1)
+    assert e.shape == (8, 8, 3, 3, 3) and torch.equal(e[:, :3, 1], w33) and float(e[:, 3:].abs().max()) == 0
+    with pytest.raises(ValueError):
+        ops.embed_conv2d_weight(torch.randn(8, 8, 7, 7), 1)
+    # several views at once: the parity split keeps the leading (view) axis
+    xv = torch.randn(3, 2, 4, 6, 8, 8)
+    assert ops.space_to_depth_c8(xv).shape == (3, 8, 4, 3, 4, 8)
+    assert torch.equal(ops.space_to_depth_c8(xv)[1], ops.space_to_depth_c8(xv[1:2])[0])
