@@ -16,6 +16,8 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from .jdacs.models import augmentations
+
 
 class FlatGrads:
     """Every parameter's .grad is a view into ONE flat fp32 buffer, so the gradient all-reduce is a single collective on memory
@@ -97,9 +99,8 @@ class TrainStep:
         self.grads.zero()
         aug, fmask = mask_reference_view(imgs_aug, box)
         depth_aug = m(aug, proj_matrices, depth_values)["depth"]
-        fm = (F.interpolate(fmask.float(), scale_factor=0.25)[:, 0] > 0.5).float()
-        # mean over the selected pixels, written without a boolean gather (no data-dependent shape)
-        aug_loss = (F.smooth_l1_loss(depth_aug, depth_est, reduction="none") * fm).sum() / fm.sum() * self.w_aug
+        # models/augmentations.aug_loss: mean over the un-masked pixels, written without a boolean gather (no data-dependent shape)
+        aug_loss = augmentations.aug_loss(depth_aug, depth_est, F.interpolate(fmask.float(), scale_factor=0.25)[:, 0]) * self.w_aug
         self._backward_and_step(aug_loss)
         return {"loss": loss.detach(), "augment_loss": aug_loss.detach()}
 

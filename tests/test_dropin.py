@@ -7,7 +7,7 @@ import sys
 from conftest import ROOT
 
 SNIPPETS = {
-    "jdacs": ("from models.mvsnet import MVSNet, mvsnet_loss\nfrom models.module import *\nfrom losses.unsup_loss import *\n"
+    "jdacs": ("from models.mvsnet import MVSNet, mvsnet_loss\nfrom models.module import *\nfrom losses.unsup_loss import *\nfrom models.augmentations import random_image_mask, aug_loss\n"
               "from losses.homography import inverse_warping\nfrom losses.modules import SSIM, depth_smoothness\n"
               # (the reference's own datasets/__init__.py makes `datasets` a package; the overlay adds this one file to it)
               "import importlib.util, os\nsp = importlib.util.spec_from_file_location('data_io', os.path.join(os.environ['PYTHONPATH'], 'datasets', 'data_io.py'))\n"

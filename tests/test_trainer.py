@@ -117,3 +117,25 @@ def test_feature_layer_embedding_is_plain_tensor_algebra():
     xv = torch.randn(3, 2, 4, 6, 8, 8)
     assert ops.space_to_depth_c8(xv).shape == (3, 8, 4, 3, 4, 8)
     assert torch.equal(ops.space_to_depth_c8(xv)[1], ops.space_to_depth_c8(xv[1:2])[0])
+
+
+def test_augmentation_mirror_matches_reference_semantics():
+    """models/augmentations.py mirror: the same mask as slicing at the drawn corner, the same loss as the boolean gather."""
+    import numpy as np
+    from ssmvs_b200.jdacs.models.augmentations import aug_loss, random_image_mask
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(2, 3, 24, 36, generator=g)
+    np.random.seed(3)
+    x, y = np.random.randint(0, 36 - 12), np.random.randint(0, 24 - 8)      # the draws random_image_mask is about to make
+    np.random.seed(3)
+    out, mask = random_image_mask(img, (8, 12))
+    want = torch.ones_like(img)
+    want[:, :, y:y + 8, x:x + 12] = 0.0
+    assert torch.equal(mask, want) and torch.equal(out, img * want)
+    out2, mask2 = random_image_mask(img, (8, 12), box=torch.tensor([x, y]))
+    assert torch.equal(mask2, want) and torch.equal(out2, out)
+    same, none = random_image_mask(img, (24, 36))
+    assert none is None and same is img
+    a, b = torch.rand(2, 6, 9, generator=g) * 50 + 400, torch.rand(2, 6, 9, generator=g) * 50 + 400
+    m = torch.rand(2, 6, 9, generator=g)
+    assert abs(float(aug_loss(a, b, m)) - float(F.smooth_l1_loss(a[m > 0.5], b[m > 0.5]))) < 1e-5
