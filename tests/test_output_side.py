@@ -130,3 +130,37 @@ def test_upsample_preview_and_pfm_files(be, gold, tmp_path):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "scan1" / "depth_est" / "00000000.pfm.png")), gold["preview"])
     with pytest.raises(Exception):
         save_pfm(p, gold["upsampled"][0].astype(np.float64))
+
+
+def test_cvp_writer_and_degenerate_geometry(be, side, tmp_path):
+    """jdacs-ms writer (no resize: files hold the maps as they are) and the geometric filter on degenerate inputs: zero / negative
+    reference depth, a source map of zeros, points behind the source camera -- the mask is False wherever the reference's
+    NumPy arithmetic yields inf / nan, exactly as the restatement does."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs import eval_dense as ed
+    from ssmvs_b200.jdacs.datasets.data_io import read_pfm
+    from ssmvs_b200.jdacs_ms.test import save_outputs
+    g = torch.Generator().manual_seed(2)
+    depth = torch.rand(2, 12, 18, generator=g) * 300 + 500
+    conf = torch.rand(2, 12, 18, generator=g)
+    save_outputs({"depth_est_list": [be.to(depth), be.to(depth[:, ::2, ::2])], "prob_confidence": be.to(conf)},
+                 ["s/{}/00000003{}", "s/{}/00000004{}"], str(tmp_path))
+    d, _ = read_pfm(str(tmp_path / "s" / "depth_est" / "00000004.pfm"))
+    c, _ = read_pfm(str(tmp_path / "s" / "confidence" / "00000003.pfm"))
+    assert np.array_equal(d, depth[1].numpy()) and np.array_equal(c, conf[0].numpy())
+    h, w = 24, 32
+    k = synth.intrinsics(w, h).astype(np.float32)
+    e0, e1 = synth.extrinsics(0).astype(np.float32), synth.extrinsics(2).astype(np.float32)
+    rng = np.random.default_rng(1)
+    d_ref = rng.uniform(500, 800, (h, w)).astype(np.float32)
+    d_ref[0, :8] = 0.0                      # division by zero in the relative depth test
+    d_ref[1, :8] = -300.0                   # behind the reference camera
+    d_ref[2, :8] = 1.0e-3                   # projects far outside the source image
+    d_src = rng.uniform(500, 800, (h, w)).astype(np.float32)
+    d_src[10:14] = 0.0
+    for src in (d_src, np.zeros_like(d_src)):
+        want = side.check_geometric_consistency(d_ref, k, e0, src, k, e1)
+        got = ed.check_geometric_consistency(be.to(torch.from_numpy(d_ref)), k, e0, be.to(torch.from_numpy(src)), k, e1)
+        assert np.array_equal(got[0].cpu().numpy(), want[0])
+        assert not got[0][:3, :8].any()
+        assert np.allclose(got[1].cpu().numpy(), want[1], rtol=1e-6, atol=1e-4)
