@@ -91,6 +91,7 @@ class StreamedForward:
         self.graphs = [GraphedForward(fn, example_inputs, warmup=warmup) for _ in range(2)]
         self.keys = tuple(out_keys)
         self.copy = torch.cuda.Stream()
+        self.d2h = torch.cuda.Stream()                  # results leave on their own stream: the next replay does not queue behind them
         self.uploaded = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         g = self.graphs[0]
@@ -116,10 +117,14 @@ class StreamedForward:
         cur.wait_event(self.uploaded[s])
         g.graph.replay()
         _lib.launches += g.launches_per_replay
-        self.consumed[s].record(cur)
-        for k in self.keys:
-            self.out_host[s][k].copy_(g.static_out[k], non_blocking=True)
-        self.out_done[s].record(cur)
+        self.consumed[s].record(cur)                    # inputs consumed, outputs produced
+        # device -> host on the d2h stream.  Graph s is replayed again only at step i + 2, after run() has synchronised
+        # out_done[s] to hand batch i out, so its static outputs are not overwritten under the copy.
+        self.d2h.wait_event(self.consumed[s])
+        with torch.cuda.stream(self.d2h):
+            for k in self.keys:
+                self.out_host[s][k].copy_(g.static_out[k], non_blocking=True)
+            self.out_done[s].record(self.d2h)
         return self.out_host[s]
 
     def run(self, host_batches):
