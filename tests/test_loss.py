@@ -74,3 +74,30 @@ def test_loss_helper_shims_match_oracle(oracle):
     assert torch.equal(m.gradient_x(x), x[:, :, :-1] - x[:, :, 1:]) and torch.equal(m.gradient_y(x), x[:, :-1] - x[:, 1:])
     dx, dy = m.gradient(x)
     assert torch.equal(dx, x[:, :, 1:] - x[:, :, :-1]) and torch.equal(dy, x[:, 1:] - x[:, :-1])
+
+
+def test_fused_loss_random_shapes_against_oracle(emu, oracle):
+    """Property-style sweep on the host-emulation build: random batch / view counts, odd map sizes, depth scales that push parts
+    of the image out of the sources -- scalars and d/d depth must match the oracle every time."""
+    from hypothesis import given, settings, strategies as st
+    from ssmvs_b200 import ops, synth
+
+    @settings(max_examples=10, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 2), views=st.integers(4, 7), hf=st.integers(5, 13), wf=st.integers(5, 17),
+           downscale=st.booleans(), scale=st.sampled_from([1.0, 0.6, 0.35]), seed=st.integers(0, 50))
+    def check(batch, views, hf, wf, downscale, scale, seed):
+        li = synth.mvsnet_inputs(batch, views, hf * 4, wf * 4, 8, seed=seed)
+        imgs = li["imgs"] if downscale else torch.nn.functional.avg_pool2d(li["imgs"].flatten(0, 1), 4).view(batch, views, 3, hf, wf).contiguous()
+        depth = (synth.plausible_depth(batch, hf, wf, seed=seed) * scale).contiguous()
+        w_s = 0.18 if downscale else 0.05
+        d_ref = depth.clone().requires_grad_(True)
+        want = oracle.unsup_loss(imgs, li["cams"], d_ref, downscale, w_s)
+        want["total"].backward()
+        d = depth.clone().requires_grad_(True)
+        out = ops.unsup_loss(imgs, li["cams"], d, 1.0, w_s)
+        out[0].backward()
+        for i, k in enumerate(("total", "reconstr", "ssim", "smooth")):
+            assert rel_err(out[i], want[k]) < 2e-5, (k, float(out[i]), float(want[k]))
+        assert rel_err(d.grad, d_ref.grad) < 3e-4
+
+    check()
