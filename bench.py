@@ -620,7 +620,17 @@ def run_output(args):
     parallel.barrier()
 
 
+def _reserve_stdout_for_the_json_line():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on fd 1 when the
+    box sets NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr and Python's sys.stdout keeps the original descriptor for the line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _reserve_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
