@@ -238,6 +238,20 @@ class MVSNet(nn.Module):
     def forward(self, imgs, proj_matrices, depth_values):
         assert imgs.shape[1] == proj_matrices.shape[1], "Different number of images and projection matrices"
         b, n = imgs.shape[0], imgs.shape[1]
+        if n < 2:
+            # the reference runs on: one view gives an all-zero variance volume (:135) and a depth map that ignores the images
+            raise ValueError("MVSNet.forward needs the reference view and at least one source view (got %d view)" % n)
+        hf, wf = ((imgs.shape[-2] - 1) // 2) // 2 + 1, ((imgs.shape[-1] - 1) // 2) // 2 + 1      # two stride-2 layers (:23,:26)
+        if depth_values.shape[1] % 8 or hf % 8 or wf % 8:
+            # checked before any launch: the 3-D U-Net halves D, H, W three times and adds the skips back (:62-71)
+            raise ValueError("CostRegNet needs D, H, W divisible by 8 (got %s), as the reference does" % ((depth_values.shape[1], hf, wf),))
+        if b == 0:
+            # an empty batch is an empty result, as the reference's library layers return it; the kernels are never launched on it
+            empty = imgs.new_zeros((0, hf, wf), dtype=torch.float32)
+            out = {"depth": empty, "photometric_confidence": empty.clone()}
+            if self.keep_index:
+                out["depth_index"] = empty.long()
+            return out
         # step 1. feature extraction (library code).  In eval mode all views share one batched call; in training
         # each view is its own call, because BatchNorm2d statistics are per call in the reference (:115).
         auto16 = imgs.is_cuda

@@ -144,3 +144,26 @@ def test_replicas_never_populate_or_hit_the_pack_caches(emu, golden):
         assert model.cost_regularization._cache._store            # the owner itself does cache ...
         model.train()
         assert not model.cost_regularization._cache._store        # ... and train() drops everything derived from the weights
+
+
+def test_mvsnet_degenerate_batches(be):
+    """Inputs at the edge of the interface: an empty batch is an empty result (the kernels are not launched on it), a lone
+    reference view is refused with a message (the reference runs on to a depth map that ignores the images), D / H / W that the
+    3-D U-Net cannot halve three times are refused as the reference's own layers refuse them."""
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    inp = be.to(synth.mvsnet_inputs(1, 3, 64, 96, 16, seed=0))
+    model = MVSNet(refine=False).to(be.device).eval()
+    model.keep_index = True
+    with torch.no_grad():
+        out = model(inp["imgs"][:0], inp["proj_matrices"][:0], inp["depth_values"][:0])
+        assert out["depth"].shape == (0, 16, 24) and out["photometric_confidence"].shape == (0, 16, 24)
+        assert out["depth_index"].dtype == torch.int64 and out["depth"].device.type == be.device.type
+        with pytest.raises(ValueError, match="source view"):
+            model(inp["imgs"][:, :1], inp["proj_matrices"][:, :1], inp["depth_values"])
+        with pytest.raises(ValueError, match="divisible by 8"):
+            model(inp["imgs"], inp["proj_matrices"], inp["depth_values"][:, :12])
+        with pytest.raises(ValueError, match="divisible by 8"):
+            model(inp["imgs"][..., :60, :].contiguous(), inp["proj_matrices"], inp["depth_values"])
+        with pytest.raises(AssertionError):                      # mvsnet.py:108
+            model(inp["imgs"], inp["proj_matrices"][:, :2], inp["depth_values"])
