@@ -120,3 +120,41 @@ def test_round2_entry_points_validate_before_touching_the_device():
     assert lib.mvs_geo_consistency(p, p, p, p, p, p, p, p, p, 1, 8, 40000, 1.0, 0.01, 1, None) == -2 and b"32767" in lib.mvs_last_error()
     assert lib.mvs_fusibile(p, None, p, p, 3, 4, 8, 8, 7, 0.25, 0.52, 3, p, p, None) == -2                               # ref view out of range
     assert lib.mvs_fusibile(None, None, p, p, 3, 4, 8, 8, 0, 0.25, 0.52, 3, p, p, None) == -1
+
+
+def test_concurrent_callers_get_their_own_results_and_error_strings(emu):
+    """SURVEY 8b threading contract: the library keeps no mutable state between calls beyond a THREAD-LOCAL error string, so
+    nn.DataParallel's per-device worker threads may call it concurrently.  Checked on the host build (ctypes drops the GIL
+    around each call, so the two threads really overlap): results equal the serial ones, and an error raised on one thread
+    does not show up in the other thread's mvs_last_error()."""
+    import threading
+    import ssmvs_b200
+    from ssmvs_b200 import ops, synth
+    cases = []
+    for seed in range(2):
+        li = synth.mvsnet_inputs(1, 3, 64, 96, 8, seed=seed)
+        feats = [torch.randn(1, 8, 16, 24, generator=torch.Generator().manual_seed(10 * seed + v)) for v in range(3)]
+        cases.append((feats, ops.compose_proj(li["proj_matrices"]), li["depth_values"]))
+    serial = [ops.warp_variance(f[0], f[1:], rt, dv, torch.float32, False, False) for f, rt, dv in cases]
+    got, errs = [None, None], [None, None]
+    gate = threading.Barrier(2)
+    lib = ssmvs_b200._lib.lib()
+
+    def worker(i):
+        f, rt, dv = cases[i]
+        gate.wait()
+        for _ in range(4):
+            got[i] = ops.warp_variance(f[0], f[1:], rt, dv, torch.float32, False, False)
+        gate.wait()
+        if i == 0:
+            assert lib.mvs_compose_proj(1, 1, 1, 12, None) == -2           # too many views: sets this thread's message only
+        gate.wait()
+        errs[i] = bytes(lib.mvs_last_error())
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert all(not t.is_alive() for t in th)
+    for i in range(2):
+        assert torch.equal(got[i], serial[i])
+    assert b"views" in errs[0] and b"views" not in errs[1]
