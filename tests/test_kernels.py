@@ -439,3 +439,65 @@ def test_bn_passes_of_the_training_path(be):
     src = be.to(torch.arange(6.0))
     call("mvs_lift_c1", src, ptr(src), ptr(lifted), dtype_code(torch.float32), 6)
     assert torch.equal(lifted[:, 0].cpu(), torch.arange(6.0)) and torch.count_nonzero(lifted[:, 1:]) == 0
+
+
+def test_random_sweeps_of_the_small_kernels_against_the_oracle(emu, oracle):
+    """Property-style sweeps on the host build (random map sizes, batch, plane counts, cameras of every synthetic view, depth
+    maps that leave the sources): the refined hypotheses (a9), the loss warp with its mask and d/d depth (a10), and the soft-argmin
+    with the truncated expected index bit-exact (a7 / a8, hazard H12)."""
+    from hypothesis import given, settings, strategies as st
+    from ssmvs_b200 import synth
+    ops = _ops()
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 3), h=st.integers(6, 21), w=st.integers(6, 27), view=st.integers(0, 3), seed=st.integers(0, 99),
+           scale=st.sampled_from([1.0, 0.7, 1.4]))
+    def hypos(batch, h, w, view, seed, scale):
+        c = synth.cvp_inputs(batch, 4, h, w, seed=seed)
+        depth_up = (synth.plausible_depth(batch, h, w, seed=seed) * scale).contiguous()
+        args = (depth_up, c["ref_in"], c["src_in"][:, view].contiguous(), c["ref_ex"], c["src_ex"][:, view].contiguous())
+        assert rel_err(ops.depth_hypo_refine(*args), oracle.depth_hypos_refine(*args)) < 1e-6
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 2), h=st.integers(5, 19), w=st.integers(5, 23), view=st.integers(1, 4), seed=st.integers(0, 99),
+           scale=st.sampled_from([1.0, 0.5, 0.3, 2.0]), channels=st.sampled_from([1, 3, 4]))
+    def invwarp(batch, h, w, view, seed, scale, channels):
+        cams = synth.mvsnet_inputs(batch, 5, 4 * h, 4 * w, 8, seed=seed)["cams"]
+        depth = (synth.plausible_depth(batch, h, w, seed=seed) * scale).contiguous()
+        g = torch.Generator().manual_seed(seed)
+        img, weight = torch.randn(batch, h, w, channels, generator=g), torch.randn(batch, h, w, channels, generator=g)
+        d0, d1 = depth.clone().requires_grad_(True), depth.clone().requires_grad_(True)
+        want, wmask = oracle.inverse_warping(img, cams[:, 0], cams[:, view], d0)
+        got, mask = ops.inverse_warp(img, cams[:, 0].contiguous(), cams[:, view].contiguous(), d1)
+        flips = mask != wmask                                 # a bit may flip only where floor() sits on an integer
+        assert flips.sum().item() <= 2
+        keep = (~flips).float()
+        assert rel_err(got * keep, want * keep) < TOL
+        if want.abs().sum() > 0 and flips.sum().item() == 0:
+            (want * weight).sum().backward()
+            (got * weight).sum().backward()
+            assert rel_err(d1.grad, d0.grad) < 2e-4
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 2), d=st.integers(1, 40), h=st.integers(1, 9), w=st.integers(1, 37), seed=st.integers(0, 99),
+           sharp=st.sampled_from([0.0, 1.0, 8.0, 60.0]), per_pixel=st.booleans())
+    def argmin(batch, d, h, w, seed, sharp, per_pixel):
+        g = torch.Generator().manual_seed(seed)
+        cost = torch.randn(batch, d, h, w, generator=g) * sharp
+        planes = 425.0 + 2.65 * torch.arange(d, dtype=torch.float32).unsqueeze(0).repeat(batch, 1)
+        if per_pixel:
+            planes = (planes.view(batch, d, 1, 1) + torch.rand(batch, 1, h, w, generator=g)).contiguous()
+        depth, index, conf, _ = ops.soft_argmin(cost, planes)
+        prob, want_depth = oracle.soft_argmin(cost, planes)
+        want_index, want_conf = oracle.photometric_confidence(prob)
+        assert rel_err(depth, want_depth) < 1e-6
+        # the expected index is a float sum truncated to an integer: equal wherever the oracle's own sum is not within
+        # float rounding of an integer (ascending-order accumulation is part of the contract; ties are hazard H12)
+        expect = (prob * torch.arange(d, dtype=torch.float32).view(1, d, 1, 1)).sum(1)
+        safe = (expect - expect.round()).abs() > 1e-4
+        assert torch.equal(index.long()[safe], want_index.long()[safe])
+        assert (conf - want_conf).abs()[safe].max().item() < 1e-5 if safe.any() else True
+
+    hypos()
+    invwarp()
+    argmin()
