@@ -501,3 +501,68 @@ def test_random_sweeps_of_the_small_kernels_against_the_oracle(emu, oracle):
     hypos()
     invwarp()
     argmin()
+
+
+def test_random_sweeps_of_the_plane_sweep_against_the_oracle(emu, oracle):
+    """The fused warp + variance (a1 / a3 / a4), forward and every gradient, on random shapes: 1-6 source views, 8 / 16 channels,
+    ragged maps, plane counts that do not divide the chunking, shared and per-pixel hypotheses, both variance variants (hazard H2),
+    both sampling geometries (hazard H1), plane ranges that push the samples out of the sources."""
+    from hypothesis import given, settings, strategies as st
+    from ssmvs_b200 import synth
+    ops = _ops()
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 2), nsrc=st.integers(1, 6), channels=st.sampled_from([8, 16]), h=st.integers(3, 14), w=st.integers(3, 19),
+           d=st.integers(1, 11), seed=st.integers(0, 99), ref_sq=st.booleans(), align=st.booleans(), per_pixel=st.booleans(),
+           scale=st.sampled_from([1.0, 0.4, 2.5]))
+    def check(batch, nsrc, channels, h, w, d, seed, ref_sq, align, per_pixel, scale):
+        inp = synth.feature_inputs(batch, nsrc + 1, channels, h, w, d, seed=seed)
+        P, planes = inp["proj_matrices"], (inp["depth_values"] * scale).contiguous()
+        g = torch.Generator().manual_seed(seed)
+        if per_pixel:
+            planes = (planes.view(batch, d, 1, 1) + 3.0 * torch.rand(batch, d, h, w, generator=g)).contiguous()
+        wt = torch.randn(batch, channels, d, h, w, generator=g)
+        a = [t.detach().clone().requires_grad_(True) for t in inp["features"]]
+        b = [t.detach().clone().requires_grad_(True) for t in inp["features"]]
+        var = ops.warp_variance(a[0], a[1:], ops.compose_proj(P), planes, torch.float32, align, ref_sq)
+        want = oracle.variance_volume(b[0], b[1:], P[:, 0], [P[:, v] for v in range(1, nsrc + 1)], planes, ref_sq, align)
+        assert rel_err(ops.unpack_c8(var), want) < TOL
+        (var * ops.pack_c8(wt)).sum().backward()
+        (want * wt).sum().backward()
+        for x, y in zip(a, b):
+            assert rel_err(x.grad, y.grad) < 2 * TOL
+
+    check()
+
+
+def test_random_sweeps_of_the_fp32_convolution_against_aten(emu):
+    """The fp32 3-D convolution (a5 / a6 layer shapes: stride 1 / 2, transposed with output padding, a single output channel with
+    bias) on random extents -- odd D / H / W for stride 1 and the transposed layers, even for stride 2 as the reference needs --
+    forward, input gradient, weight gradient against ATen."""
+    from hypothesis import given, settings, strategies as st
+    ops = _ops()
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 2), cin=st.sampled_from([8, 16, 32]), cout=st.sampled_from([1, 8, 16]), mode=st.sampled_from(["s1", "s2", "t1", "t2"]),
+           d=st.integers(1, 5), h=st.integers(1, 7), w=st.integers(1, 9), seed=st.integers(0, 99))
+    def check(batch, cin, cout, mode, d, h, w, seed):
+        stride, tr = (2 if mode[1] == "2" else 1), mode[0] == "t"
+        if stride == 2 and not tr:
+            d, h, w = 2 * d, 2 * h, 2 * w
+        if cout == 1 and (tr or stride == 2):
+            cout = 8                                     # the single-channel layer is `prob`: stride 1, not transposed, biased
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(batch, cin, d, h, w, generator=g)
+        wgt = 0.1 * (torch.randn(cin, cout, 3, 3, 3, generator=g) if tr else torch.randn(cout, cin, 3, 3, 3, generator=g))
+        bias = torch.randn(cout, generator=g) if cout == 1 else None
+        xa, wa = ops.pack_c8(x).requires_grad_(True), wgt.clone().requires_grad_(True)
+        ya = ops.conv3d(xa, wa, bias, stride, tr)
+        xb, wb = x.clone().requires_grad_(True), wgt.clone().requires_grad_(True)
+        yb = F.conv_transpose3d(xb, wb, bias, stride, 1, stride - 1) if tr else F.conv3d(xb, wb, bias, stride, 1)
+        wt = torch.randn(yb.shape, generator=g)
+        (ya * (wt.squeeze(1) if cout == 1 else ops.pack_c8(wt))).sum().backward()
+        (yb * wt).sum().backward()
+        assert rel_err(ya.detach().unsqueeze(1) if cout == 1 else ops.unpack_c8(ya), yb) < 1e-5
+        assert rel_err(ops.unpack_c8(xa.grad), xb.grad) < 1e-5 and rel_err(wa.grad, wb.grad) < 1e-5
+
+    check()
