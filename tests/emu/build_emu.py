@@ -17,12 +17,18 @@ SOURCES = ["core.cu", "warp.cu", "softargmin.cu", "conv3d_simt.cu", "invwarp.cu"
 
 
 def build_emu() -> str:
+    """MVS_EMU_ASAN=1: the same build with AddressSanitizer + UBSan (tools/asan_emu.sh runs the CPU kernel tests under it; the
+    interpreter must then be started with libasan preloaded)."""
     os.makedirs(OUT, exist_ok=True)
+    asan = os.environ.get("MVS_EMU_ASAN", "0") == "1"
+    LIB = os.path.join(OUT, "libmvs_emu_asan.so" if asan else "libmvs_emu.so")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [os.path.join(ROOT, "include", "mvs_b200.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DMVS_CPU_EMU", "-Wno-unknown-pragmas", "-o", LIB]
+    if asan:
+        cmd[3:3] = ["-g", "-fno-omit-frame-pointer", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]
     for s in srcs:
         cmd += ["-x", "c++", s]
     r = subprocess.run(cmd, capture_output=True, text=True)
