@@ -158,3 +158,28 @@ def test_concurrent_callers_get_their_own_results_and_error_strings(emu):
     for i in range(2):
         assert torch.equal(got[i], serial[i])
     assert b"views" in errs[0] and b"views" not in errs[1]
+
+
+def test_plain_c_client_of_the_header(emu, tmp_path):
+    """include/mvs_b200.h is the boundary a binding in the reference's host language would compile against: it must be valid
+    C99 on its own (pedantic), and a C program using only that header must link and run.  tests/cabi_client.c is run against
+    the host build (host pointers) and LINKED against the product library (every symbol it uses resolves; no GPU needed)."""
+    import subprocess
+    import ssmvs_b200
+    inc = os.path.join(ROOT, "include")
+    src = os.path.join(ROOT, "tests", "cabi_client.c")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from build_emu import build_emu
+    emu_lib = build_emu()
+    for lib_path, run in ((emu_lib, True), (ssmvs_b200._lib.DEFAULT_PATH, False)):
+        if not os.path.exists(lib_path):
+            continue
+        exe = str(tmp_path / ("client_" + os.path.basename(lib_path)))
+        cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, src, "-o", exe, lib_path, "-lm",
+               "-Wl,-rpath," + os.path.dirname(lib_path)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        if run:
+            r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+            assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
