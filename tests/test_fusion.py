@@ -82,3 +82,37 @@ def test_consistent_scene_fuses_onto_its_surface_and_outliers_are_voted_out(be):
     x, n, c = fz.fuse_scene(be.to(nd), be.to(cams), num_consistent=3)
     assert x.shape[1] == 3 and x.shape[0] == n.shape[0] == c.shape[0] > 1000
     assert np.abs(x.cpu().double().numpy() @ n_w - d_w).max() < 3.0
+
+
+def test_fusion_random_scenes_against_restatement(emu, fusion_oracle):
+    """Property-style sweep on the host build: random view counts, map sizes, reference views, view subsets, noise, thresholds and
+    consensus counts -- the kept-pixel decisions must agree with the restatement except on last-bit threshold ties, and the fused
+    points / normals / colours must agree wherever both keep the pixel."""
+    from hypothesis import given, settings, strategies as st
+    from ssmvs_b200.jdacs.fusion import fusibile as fz
+
+    @settings(max_examples=15, deadline=None, derandomize=True)
+    @given(views=st.integers(3, 6), h=st.integers(6, 20), w=st.integers(6, 26), seed=st.integers(0, 99), noise=st.sampled_from([0.0, 0.2, 1.0]),
+           disp=st.sampled_from([0.1, 0.25, 1.0]), normal=st.sampled_from([0.2, 0.52]), consistent=st.integers(1, 3), data=st.data())
+    def check(views, h, w, seed, noise, disp, normal, consistent, data):
+        cams, depths, _ = _scene(views, h, w)
+        g = torch.Generator().manual_seed(seed)
+        depths = depths + noise * torch.randn(depths.shape, generator=g)
+        depths[torch.rand(depths.shape, generator=g) < 0.05] = 0.0                               # holes, as a filtered map has them
+        nd = fz.constant_normals(depths)
+        nd[..., :3] += 0.15 * torch.randn(nd[..., :3].shape, generator=g)
+        nd[..., :3] /= nd[..., :3].norm(dim=-1, keepdim=True)
+        imgs = torch.rand(views, h, w, 4, generator=g)
+        ref = data.draw(st.integers(0, views - 1))
+        others = [v for v in range(views) if v != ref]
+        subset = [ref] + data.draw(st.lists(st.sampled_from(others), min_size=1, max_size=len(others), unique=True))
+        want_p, want_v = fusion_oracle.fusibile(nd.numpy(), cams.numpy(), ref, subset, disp, normal, consistent, imgs.numpy())
+        pts, valid = fz.fuse_view(nd, cams, ref, subset, disp, normal, consistent, imgs)
+        agree = valid.numpy() == want_v
+        assert agree.mean() > 0.99, agree.mean()
+        both = torch.from_numpy(want_v & valid.numpy())
+        if both.any():
+            wp = torch.from_numpy(want_p)
+            assert ((pts[both] - wp[both]).abs().max() / wp[both].abs().max()).item() < 1e-5
+
+    check()
