@@ -188,3 +188,50 @@ def test_self_supervised_training_trajectory_matches_the_oracle(emu, oracle):
     # (parameters are not compared: at this size the deep layers see 6 voxels, most of their gradients are cancellation residue,
     # and Adam turns residue into +-lr steps -- prob.bias, whose true gradient is exactly zero under the softmax, wanders by 30 %)
     assert max(float((p.detach() - start[k]).abs().max()) for k, p in model.named_parameters()) > 3e-3      # and it did train
+
+
+def test_cvp_self_supervised_trajectory_matches_the_oracle(emu, oracle):
+    """The same lockstep check for JDACS-MS (jdacs-ms/train.py:200-258): CVP-MVSNet forward (2 levels, per-pixel hypotheses at the
+    fine one), every level's depth resized to the image (nearest), UnSupLoss per level, summed, backward, Adam -- four steps
+    against the oracle's cvp_forward / unsup_loss from the same weights."""
+    from types import SimpleNamespace
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs_ms.losses.unsup_loss import UnSupLoss
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+    torch.manual_seed(1)
+    nsrc, nscale, h, w = 3, 2, 32, 48
+    model = CVPMVSNet(SimpleNamespace(nsrc=nsrc, nscale=nscale, mode="train"), volume_dtype=torch.float32, train_dtype=torch.float32)
+    names = [k for k, _ in model.named_parameters()]
+    params = {k: v.detach().clone().requires_grad_(k in names) for k, v in model.state_dict().items()}
+    criterion = UnSupLoss()
+    opt_a = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    opt_b = torch.optim.Adam([params[k] for k in names], lr=1e-3, betas=(0.9, 0.999))
+    c = synth.cvp_inputs(1, nsrc, h, w, seed=5)
+    keys = ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")
+    imgs = torch.cat([c["ref_img"].unsqueeze(1), c["src_imgs"]], 1)
+    cams = torch.zeros(1, nsrc + 1, 2, 4, 4)
+    cams[:, 0, 0], cams[:, 1:, 0] = c["ref_ex"], c["src_ex"]
+    cams[:, 0, 1, :3, :3], cams[:, 1:, 1, :3, :3] = c["ref_in"], c["src_in"]
+
+    def total(ests, loss_fn):
+        return sum(loss_fn(F.interpolate(d.unsqueeze(1), size=[h, w]).squeeze(1)) for d in ests)
+
+    got, want = [], []
+    for _ in range(4):
+        model.train()
+        opt_a.zero_grad()
+        loss = total(model(*[c[k] for k in keys])["depth_est_list"], lambda d: criterion(imgs, cams, d))
+        loss.backward()
+        opt_a.step()
+        got.append(float(loss.detach()))
+        opt_b.zero_grad()
+        ref = total(oracle.cvp_forward(c, params, nscale, training=True)["depth_est_list"],
+                    lambda d: oracle.unsup_loss(imgs, cams, d, False, 0.05)["total"])
+        ref.backward()
+        opt_b.step()
+        want.append(float(ref.detach()))
+    got, want = torch.tensor(got), torch.tensor(want)
+    assert torch.isfinite(got).all() and abs(got[0] - want[0]) / want[0] < 1e-5
+    assert ((got - want).abs() / want).max().item() < 3e-3, (got, want)
+    assert (got - got[0]).abs().max() > 0.05          # the weights moved the loss (on random images four steps need not lower it:
+    #                                                   the oracle's run goes the same way, which is the point of the comparison)
