@@ -167,3 +167,46 @@ def test_mvsnet_degenerate_batches(be):
             model(inp["imgs"][..., :60, :].contiguous(), inp["proj_matrices"], inp["depth_values"])
         with pytest.raises(AssertionError):                      # mvsnet.py:108
             model(inp["imgs"], inp["proj_matrices"][:, :2], inp["depth_values"])
+
+
+def test_model_forward_random_configurations_against_the_oracle(emu, oracle):
+    """Property-style sweep at module level on the host build: MVSNet.eval() over random batch / view counts / image sizes / plane
+    counts and CVPMVSNet over random source counts / pyramid depths, BatchNorm statistics randomised so that the softmax is not
+    flat (hazard H11), against the oracle's whole-forward restatements with the same state dict."""
+    from hypothesis import given, settings, strategies as st
+    from ssmvs_b200 import synth
+    from ssmvs_b200.jdacs.models.mvsnet import MVSNet
+    from ssmvs_b200.jdacs_ms.models.network import CVPMVSNet
+
+    @settings(max_examples=14, deadline=None, derandomize=True)
+    @given(batch=st.integers(1, 2), views=st.integers(2, 5), hb=st.integers(1, 2), wb=st.integers(1, 3), db=st.integers(1, 3), seed=st.integers(0, 20))
+    def mvsnet(batch, views, hb, wb, db, seed):
+        torch.manual_seed(seed)
+        model = MVSNet(refine=False, volume_dtype=torch.float32).eval()
+        synth.randomise_bn(model, seed=seed)
+        inp = synth.mvsnet_inputs(batch, views, 32 * hb, 32 * wb, 8 * db, seed=seed)
+        with torch.no_grad():
+            got = model(inp["imgs"], inp["proj_matrices"], inp["depth_values"])
+            want = oracle.mvsnet_forward(inp["imgs"], inp["proj_matrices"], inp["depth_values"], model.state_dict())
+        assert rel_err(got["depth"], want["depth"]) < 1e-4
+        assert rel_err(got["photometric_confidence"], want["photometric_confidence"]) < 2e-3
+
+    @settings(max_examples=10, deadline=None, derandomize=True)
+    @given(nsrc=st.integers(1, 4), nscale=st.integers(1, 3), hb=st.integers(1, 2), wb=st.integers(1, 2), seed=st.integers(0, 20))
+    def cvp(nsrc, nscale, hb, wb, seed):
+        torch.manual_seed(seed)
+        model = CVPMVSNet(SimpleNamespace(nsrc=nsrc, nscale=nscale, mode="test"), volume_dtype=torch.float32).eval()
+        synth.randomise_bn(model, seed=seed)
+        f = 2 ** nscale                                        # the coarsest level must still be even (network.py:44-74)
+        c = synth.cvp_inputs(1, nsrc, f * 4 * hb, f * 4 * wb, seed=seed)
+        keys = ("ref_img", "src_imgs", "ref_in", "src_in", "ref_ex", "src_ex", "depth_min", "depth_max")
+        with torch.no_grad():
+            got = model(*[c[k] for k in keys])
+            want = oracle.cvp_forward(c, model.state_dict(), nscale)
+        assert len(got["depth_est_list"]) == nscale
+        for a, b in zip(got["depth_est_list"], want["depth_est_list"]):
+            assert rel_err(a, b) < 1e-4
+        assert rel_err(got["prob_confidence"], want["prob_confidence"]) < 2e-3
+
+    mvsnet()
+    cvp()
