@@ -623,10 +623,13 @@ def run_output(args):
 def _reserve_stdout_for_the_json_line():
     """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on fd 1 when the
     box sets NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr and Python's sys.stdout keeps the original descriptor for the line."""
-    sys.stdout.flush()
-    real = os.dup(1)
-    os.dup2(2, 1)
-    sys.stdout = os.fdopen(real, "w", buffering=1)
+    try:
+        sys.stdout.flush()
+        real = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real, "w", buffering=1)
+    except OSError:          # no usable stderr / stdout descriptor: leave the streams as they are
+        pass
 
 
 def main():
